@@ -1,0 +1,178 @@
+/* sage_b200.h — C ABI of the B200-native fragment-index search-and-score library.
+ *
+ * Drop-in boundary for ONE path of lazear/sage (reference @0639176): sage-core's
+ *   IndexedDatabase::query / IndexedQuery::page_search   crates/sage/src/database.rs:402-536
+ *   Scorer::score (score_standard / score_chimera_fast)   crates/sage/src/scoring.rs:300-767
+ * A Rust shim keeps `Scorer` / `IndexedDatabase` / `ProcessedSpectrum` as they are and forwards
+ * `Scorer::score` / a new `Scorer::score_batch` to these entry points. Plain pointers and sizes only; no C++ or
+ * torch types cross this boundary. All functions return 0 on success and a negative SAGE_B200_E* code on failure
+ * (never unwind; the reference panics instead — see sage_b200_last_error for the message).
+ *
+ * Ownership: the caller owns every input/output buffer for the duration of a call; the library copies what it needs
+ * to the device and keeps no host pointers. Thread-safety: one sage_b200_scorer may be used by one host thread at a
+ * time (calls are serialised internally by a per-scorer mutex); distinct scorers on the same db are independent.
+ */
+#ifndef SAGE_B200_H
+#define SAGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAGE_B200_OK 0
+#define SAGE_B200_EINVAL (-1)     /* bad argument */
+#define SAGE_B200_ECUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define SAGE_B200_ENOTMS2 (-3)    /* reference: assert_eq!(query.level, 2)            scoring.rs:301-304 */
+#define SAGE_B200_ENOPRECURSOR (-4) /* reference: panic!("missing MS1 precursor")      scoring.rs:466-468 */
+#define SAGE_B200_ELIMIT (-5)     /* a documented capacity limit was exceeded */
+
+typedef struct sage_b200_db sage_b200_db;         /* replaces &IndexedDatabase (device-resident)  database.rs:384-395 */
+typedef struct sage_b200_scorer sage_b200_scorer; /* replaces Scorer<'db>                          scoring.rs:210-232 */
+
+/* mass.rs:10-16  Tolerance::{Ppm,Pct,Da}(lo,hi) */
+enum { SAGE_B200_TOL_PPM = 0, SAGE_B200_TOL_PCT = 1, SAGE_B200_TOL_DA = 2 };
+typedef struct { int32_t kind; float lo, hi; } sage_b200_tolerance;
+
+/* ion_series.rs:8-15  Kind */
+enum { SAGE_B200_KIND_A = 0, SAGE_B200_KIND_B = 1, SAGE_B200_KIND_C = 2, SAGE_B200_KIND_X = 3, SAGE_B200_KIND_Y = 4, SAGE_B200_KIND_Z = 5 };
+
+/* Peptides as the hot path reads them (peptide.rs:13-31), flattened CSR/SoA. `PeptideIx` == row index. */
+typedef struct {
+    uint64_t n_peptides;
+    const uint32_t* residue_offsets; /* n_peptides+1; residues of peptide i are [off[i], off[i+1]) */
+    const uint8_t* sequence;         /* Peptide::sequence bytes, concatenated */
+    const float* modifications;      /* Peptide::modifications, parallel to sequence */
+    const float* nterm;              /* Peptide::nterm, NaN = None */
+    const float* monoisotopic;       /* Peptide::monoisotopic, ascending (database.rs:226-230) */
+    const uint8_t* decoy;            /* Peptide::decoy */
+    const uint8_t* missed_cleavages; /* Peptide::missed_cleavages */
+} sage_b200_peptides;
+
+/* The fragment index exactly as IndexedDatabase holds it (database.rs:378-395). */
+typedef struct {
+    uint64_t n_fragments;
+    const uint32_t* fragment_peptide; /* Theoretical::peptide_index */
+    const float* fragment_mz;         /* Theoretical::fragment_mz   */
+    uint64_t n_buckets;
+    const float* bucket_min;          /* IndexedDatabase::min_value */
+    uint64_t bucket_size;             /* IndexedDatabase::bucket_size */
+    const uint8_t* ion_kinds;         /* IndexedDatabase::ion_kinds (SAGE_B200_KIND_*) */
+    uint64_t n_ion_kinds;
+} sage_b200_index;
+
+typedef struct {
+    uint64_t n_peptides, n_fragments, n_buckets, bucket_size, n_ion_kinds, total_residues;
+    uint64_t device_bytes; /* HBM held by this db */
+    int32_t device;
+} sage_b200_db_info;
+
+/* Mirror of Scorer's public fields (scoring.rs:210-232). */
+typedef struct {
+    sage_b200_tolerance precursor_tol, fragment_tol;
+    uint16_t min_matched_peaks;
+    int8_t min_isotope_err, max_isotope_err;
+    uint8_t min_precursor_charge, max_precursor_charge, override_precursor_charge;
+    int8_t max_fragment_charge; /* Option<u8>: <0 = None */
+    uint8_t chimera, wide_window, annotate_matches;
+    uint8_t score_type; /* 0 = SageHyperScore, 1 = OpenMSHyperScore (scoring.rs:10-14) */
+    uint32_t report_psms;
+} sage_b200_scorer_params;
+
+/* &[ProcessedSpectrum] flattened (spectrum.rs:47-79); only precursors.first() is read (scoring.rs:466). */
+typedef struct {
+    uint64_t n;
+    const uint64_t* peak_offsets;     /* n+1 */
+    const float* masses;              /* ProcessedSpectrum::masses (ascending) */
+    const float* intensities;         /* ProcessedSpectrum::intensities */
+    const float* precursor_mz;        /* Precursor::mz; NaN = spectrum has no precursor */
+    const uint8_t* precursor_charge;  /* Precursor::charge; 0 = None */
+    const float* isolation_lo;        /* Precursor::isolation_window = Some(Da(lo,hi)); NaN = None. May be NULL (all None) */
+    const float* isolation_hi;
+    const float* total_ion_current;   /* ProcessedSpectrum::total_ion_current */
+    const uint8_t* level;             /* ProcessedSpectrum::level; NULL = all 2 */
+    const float* scan_start_time;     /* -> Feature::rt / aligned_rt; NULL = 0 */
+    const float* inverse_ion_mobility;/* Precursor::inverse_ion_mobility, NaN/NULL = None -> Feature::ims = 0 */
+} sage_b200_spectra;
+
+/* Numeric fields of Feature that the path computes (scoring.rs:69-149, 535-593). spec_id/file_id are re-attached by
+ * the caller from `spectrum`; psm_id (global atomic, scoring.rs:163-167) is assigned by the caller after the call. */
+typedef struct {
+    uint32_t spectrum;      /* index into the batch */
+    uint32_t peptide_idx;   /* PeptideIx */
+    uint32_t peptide_len;
+    uint32_t rank;
+    int32_t label;          /* -1 decoy, 1 target */
+    float expmass, calcmass;
+    uint32_t charge;
+    float rt, ims;
+    float delta_mass, isotope_error, average_ppm;
+    double hyperscore, delta_next, delta_best;
+    uint32_t matched_peaks, longest_b, longest_y;
+    float longest_y_pct;
+    uint32_t missed_cleavages;
+    float matched_intensity_pct;
+    uint32_t scored_candidates;
+    float ms2_intensity;
+    double poisson;
+    uint32_t fragment_offset, fragment_count; /* into the fragments array when annotate_matches */
+} sage_b200_feature;
+
+/* One matched fragment (scoring.rs:152-161, 738-751). */
+typedef struct { int32_t kind, charge, ordinal; float intensity, mz_calculated, mz_experimental; } sage_b200_fragment;
+
+/* Work counters of the last score_batch (SURVEY.md §8d algorithmic-bytes terms) + device timings (CUDA events, ms). */
+typedef struct {
+    uint64_t spectra, peaks, queries, tasks /* (peak,fragment-charge) probes */, pages, entries_scanned, matched_fragments,
+        candidates_scored, peptide_record_floats, psms, wide_queries;
+    uint64_t algorithmic_bytes;    /* SURVEY.md §8d formula, whole batch */
+    uint64_t prelim_bytes;         /* the part of it the preliminary-scoring kernel(s) move */
+    uint64_t h2d_bytes, d2h_bytes; /* bytes copied across PCIe for the batch */
+    uint64_t kernel_launches;
+    float ms_total, ms_h2d, ms_setup, ms_prelim, ms_score, ms_d2h; /* summed over chunks */
+} sage_b200_counters;
+
+int sage_b200_device_count(void);
+
+/* IndexedDatabase -> device. `index` as built by Parameters::build (database.rs:260-365). */
+int sage_b200_db_create(const sage_b200_peptides* peptides, const sage_b200_index* index, int device, sage_b200_db** out);
+
+/* Parameters::build_from_peptides on the device (database.rs:265-365): fragment generation for `ion_kinds` with the
+ * `min_ion_index` filter, global sort by fragment m/z, bucketing, per-bucket sort by PeptideIx. */
+int sage_b200_db_build(const sage_b200_peptides* peptides, uint64_t bucket_size, const uint8_t* ion_kinds, uint64_t n_ion_kinds,
+                       uint64_t min_ion_index, int device, sage_b200_db** out);
+
+int sage_b200_db_get_info(const sage_b200_db* db, sage_b200_db_info* info);
+/* Copies the index back in the reference layout (IndexedDatabase::fragments / min_value); any pointer may be NULL. */
+int sage_b200_db_export_index(const sage_b200_db* db, uint32_t* fragment_peptide, float* fragment_mz, float* bucket_min);
+void sage_b200_db_destroy(sage_b200_db* db);
+
+int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_scorer_params* params, sage_b200_scorer** out);
+void sage_b200_scorer_destroy(sage_b200_scorer* scorer);
+
+/* Scorer::score over a batch (runner.rs:311-325 `par_iter().flat_map(|s| scorer.score(s))`).
+ * features: caller-allocated, n * report_psms entries; spectrum i's PSMs are features[i*report_psms .. +counts[i]).
+ * fragments/fragment_capacity/fragments_used: only with annotate_matches (may be NULL otherwise). */
+int sage_b200_score_batch(sage_b200_scorer* scorer, const sage_b200_spectra* spectra, sage_b200_feature* features, uint32_t* counts,
+                          sage_b200_fragment* fragments, uint64_t fragment_capacity, uint64_t* fragments_used);
+
+/* Scorer::initial_hits for one spectrum (scoring.rs:418-462): the preliminary list in the reference's heap order.
+ * White-box hook used by the parity tests. Returns the list length (<= cap written) or a negative error. */
+int64_t sage_b200_initial_hits(sage_b200_scorer* scorer, const sage_b200_spectra* one_spectrum, uint16_t* matched, uint32_t* peptide,
+                               uint8_t* charge, int8_t* isotope_error, uint64_t cap, uint64_t* matched_peaks, uint64_t* scored_candidates);
+
+int sage_b200_counters_get(const sage_b200_scorer* scorer, sage_b200_counters* out);
+
+/* Page-locked host buffers: spectra/feature arrays placed here are copied by DMA without a staging memcpy. */
+void* sage_b200_host_alloc(size_t bytes);
+void sage_b200_host_free(void* p);
+
+/* Message of the last failure on the calling thread. Returns the message length. */
+size_t sage_b200_last_error(char* buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAGE_B200_H */

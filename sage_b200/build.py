@@ -1,0 +1,36 @@
+"""Builds libsage_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_PKG, "csrc", "sage_b200.cu")
+_DEPS = [os.path.join(_PKG, "csrc", f) for f in ("sage_b200.cu", "kernels.cuh", "device_common.cuh")] + [
+    os.path.join(os.path.dirname(_PKG), "include", "sage_b200.h")]
+_OUT = os.path.join(_PKG, "lib", "libsage_b200.so")
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def library_path() -> str:
+    return _OUT
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(os.path.dirname(_OUT), exist_ok=True)
+    if not force and os.path.exists(_OUT) and all(os.path.getmtime(_OUT) >= os.path.getmtime(d) for d in _DEPS):
+        return _OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _OUT, _SRC]
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    subprocess.check_call(cmd, env=env)
+    return _OUT
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

@@ -1,0 +1,173 @@
+// device_common.cuh — shared device-side definitions for the sage_b200 kernels (sm_100a).
+//
+// Numeric contract (SURVEY.md §7 hard part 2): every f32 product / sum / quotient on the path is a separately
+// rounded IEEE operation, exactly as rustc emits for the reference (no FMA contraction). We use the explicit
+// round-to-nearest intrinsics AND compile with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+constexpr int K_MAX = 128;            // max preliminary candidates kept per spectrum: max(50, 2*report_psms)
+constexpr uint32_t NARROW_CAP = 8192; // precursor windows up to this many peptides are counted in shared memory
+constexpr int PRELIM_THREADS = 256;
+constexpr int SCORE_THREADS = 256;
+constexpr int MAX_KINDS = 6;
+
+// mass.rs:5-8
+constexpr float PROTON = 1.0072764f;
+constexpr float NEUTRON = 1.00335f;
+
+struct Tol { int kind; float lo, hi; };
+
+// f32::total_cmp as an integer key
+__device__ __forceinline__ int f32_key(float x) {
+    int b = __float_as_int(x);
+    return b ^ (int)(((unsigned)(b >> 31)) >> 1);
+}
+
+// Tolerance::bounds (mass.rs:21-35)
+__device__ __forceinline__ void tol_bounds(const Tol& t, float c, float& lo, float& hi) {
+    if (t.kind == 0) {
+        lo = __fadd_rn(c, __fdiv_rn(__fmul_rn(c, t.lo), 1000000.0f));
+        hi = __fadd_rn(c, __fdiv_rn(__fmul_rn(c, t.hi), 1000000.0f));
+    } else if (t.kind == 1) {
+        lo = __fadd_rn(c, __fdiv_rn(__fmul_rn(c, t.lo), 100.0f));
+        hi = __fadd_rn(c, __fdiv_rn(__fmul_rn(c, t.hi), 100.0f));
+    } else {
+        lo = __fadd_rn(c, t.lo);
+        hi = __fadd_rn(c, t.hi);
+    }
+}
+
+// binary_search_slice (database.rs:549-561) over an abstract sorted sequence.
+//   less_lo(i): key(slice[i], low) == Less        le_hi(i): key(slice[i], high) != Greater
+template <class LessLo, class LeHi>
+__device__ __forceinline__ void binary_search_slice(uint32_t n, LessLo less_lo, LeHi le_hi, uint32_t& left, uint32_t& right) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (less_lo(mid)) lo = mid + 1; else hi = mid;
+    }
+    left = lo == 0 ? 0 : lo - 1;
+    lo = left; hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (le_hi(mid)) lo = mid + 1; else hi = mid;
+    }
+    right = lo;
+}
+
+// max_fragment_charge (scoring.rs:239-247); opt < 0 == None. Returns the EXCLUSIVE upper bound of 1..N.
+__device__ __forceinline__ uint32_t max_fragment_charge(int opt, uint32_t precursor_charge) {
+    uint32_t m = opt >= 0 ? (uint32_t)(opt + 1) : precursor_charge;
+    m &= 0xFF;  // u8 arithmetic in the reference (c + 1 on u8)
+    uint32_t r = precursor_charge < m ? precursor_charge : m;
+    return r < 2 ? 2 : r;
+}
+
+// PreScore (scoring.rs:43-49) packed so that u64 order == derived lexicographic Ord:
+//   matched:u16 | peptide:u32 | precursor_charge:u8 | isotope_error:i8 (biased)
+__device__ __forceinline__ uint64_t prescore_key(uint32_t matched, uint32_t peptide, uint32_t charge, int iso) {
+    return ((uint64_t)matched << 48) | ((uint64_t)peptide << 16) | ((uint64_t)(charge & 0xFF) << 8) | (uint64_t)((uint32_t)(iso + 128) & 0xFF);
+}
+constexpr uint64_t PRESCORE_DEFAULT = ((uint64_t)0xFFFFFFFFull << 16) | 128ull;  // matched 0, PeptideIx::default()==MAX, charge 0, iso 0
+__device__ __forceinline__ uint32_t key_matched(uint64_t k) { return (uint32_t)(k >> 48); }
+__device__ __forceinline__ uint32_t key_peptide(uint64_t k) { return (uint32_t)(k >> 16); }
+__device__ __forceinline__ uint32_t key_charge(uint64_t k) { return (uint32_t)(k >> 8) & 0xFF; }
+__device__ __forceinline__ int key_iso(uint64_t k) { return (int)(k & 0xFF) - 128; }
+
+// sift_down (heap.rs:40-60) on a min-heap of packed PreScore keys
+__device__ __forceinline__ void sift_down(uint64_t* s, uint32_t len, uint32_t index) {
+    while (index * 2 + 1 < len) {
+        uint32_t smallest = index, l = index * 2 + 1, r = index * 2 + 2;
+        if (s[l] < s[smallest]) smallest = l;
+        if (r < len && s[r] < s[smallest]) smallest = r;
+        if (smallest != index) {
+            uint64_t t = s[smallest]; s[smallest] = s[index]; s[index] = t;
+            index = smallest;
+        } else break;
+    }
+}
+// bounded_min_heapify (heap.rs:7-28), sequential (one thread), used on short lists
+__device__ __forceinline__ void bounded_min_heapify_seq(uint64_t* s, uint32_t len, uint32_t k) {
+    if (len <= k) return;
+    for (uint32_t i = k / 2; i-- > 0;) sift_down(s, k, i);
+    for (uint32_t i = k; i < len; i++) {
+        if (s[i] > s[0]) {
+            uint64_t t = s[i]; s[i] = s[0]; s[0] = t;
+            sift_down(s, k, 0);
+        }
+    }
+}
+
+struct QueryDesc {
+    uint32_t pre_lo;     // IndexedQuery::pre_idx_lo
+    uint32_t pre_hi;     // IndexedQuery::pre_idx_hi
+    uint32_t potential;  // pre_idx_hi - pre_idx_lo + 1 (scoring.rs:351); 0 = query slot unused
+    uint32_t eff_lo;     // inclusive PeptideIx range accepted by the edge filter (database.rs:526-531)
+    uint32_t eff_hi;     // eff_lo > eff_hi => nothing accepted
+    uint8_t charge;      // precursor charge of this query
+    int8_t iso;          // isotope error recorded in PreScore
+    uint8_t nfc;         // fragment charges searched = max_fragment_charge - 1
+    uint8_t mode;        // 0 unused, 1 narrow (smem counts), 2 wide (global counts)
+};
+
+struct QueryHits {
+    uint32_t n;            // explicit entries in keys[]
+    uint32_t default_run;  // matched_peaks == 0: the untrimmed all-default Vec of this length (scoring.rs:376-378)
+    uint32_t matched_peaks;
+    uint32_t scored_candidates;
+};
+
+// Device counters (u64 slots)
+enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_COUNT };
+
+struct DbView {
+    const uint2* frag;        // {peptide_index, fragment_mz bits}, reference bucket layout
+    const float* bucket_min;
+    const float* pep_mono;
+    const uint32_t* ion_off;  // n_pep+1, offsets into ions (n_kinds*(L-1) floats per peptide)
+    const float* ions;
+    const uint8_t* pep_len;
+    const uint8_t* pep_flags; // bit0 decoy
+    const uint8_t* pep_missed;
+    uint32_t n_pep, n_bucket, bucket_size, n_kinds;
+    uint64_t n_frag;
+    uint8_t kinds[MAX_KINDS];
+};
+
+struct ScorerView {
+    Tol precursor_tol, fragment_tol;
+    uint32_t min_matched_peaks;
+    int min_iso, max_iso;
+    uint32_t min_charge, max_charge;
+    int override_charge, max_fragment_charge_opt, chimera, wide_window, annotate, score_type;
+    uint32_t report_psms;
+    uint32_t kparam;   // max(50, 2*report_psms)
+    uint32_t n_iso;    // isotope errors folded per charge (1 when min==max)
+    uint32_t n_ch_max; // charges folded per spectrum (upper bound)
+    uint32_t qmax;     // n_iso * n_ch_max query slots per spectrum
+    uint32_t lcap;     // list capacity for merges
+};
+
+struct BatchView {
+    uint32_t n;                 // spectra in this chunk
+    const uint32_t* peak_off;   // n+1
+    const float* masses;
+    const float* intens;
+    const float* prec_mz;
+    const uint8_t* prec_charge;
+    const float* iso_lo;        // nullable
+    const float* iso_hi;
+    const float* tic;
+    const float* rt;            // nullable
+    const float* ims;           // nullable
+    QueryDesc* queries;         // n * qmax
+    QueryHits* hits;            // n * qmax
+    uint64_t* hit_keys;         // n * qmax * kparam
+    unsigned long long* counters;
+};
+
+}  // namespace sb

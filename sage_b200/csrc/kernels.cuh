@@ -1,0 +1,783 @@
+// kernels.cuh — hand-written sm_100a kernels for the fragment-index search-and-score path.
+//
+//   k_setup_queries   IndexedDatabase::query per (spectrum, charge, isotope)      database.rs:402-425, scoring.rs:418-458
+//   k_prelim_narrow   matched_peaks_with_isotope + trim_hits, counts in smem       scoring.rs:335-382, database.rs:480-536, heap.rs
+//   k_prelim_wide     same, precursor windows > NARROW_CAP: cooperative streaming of page slices, counts in HBM/L2 scratch
+//   k_score           fold/trim of per-query hits, score_candidate, build_features, chimera loop   scoring.rs:384-767
+//
+// All of this is integer/f32 gather-reduce work bound by memory latency/bandwidth; tensor cores are not used.
+#pragma once
+#include "device_common.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------------ setup
+// One thread per spectrum: enumerate the (charge, isotope) queries of Scorer::initial_hits and resolve each
+// precursor window to a PeptideIx range (two binary searches over peptides[].monoisotopic).
+__global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.n) return;
+    const float pmz = b.prec_mz[s];
+    const uint32_t known = b.prec_charge[s];
+    const float mz = __fsub_rn(pmz, PROTON);  // scoring.rs:420
+    const bool fold = sc.wide_window || !(known != 0 && !sc.override_charge);
+    uint32_t c0 = fold ? sc.min_charge : known;
+    uint32_t c1 = fold ? sc.max_charge : known;
+    QueryDesc* out = b.queries + (size_t)s * sc.qmax;
+    uint32_t qi = 0;
+    unsigned long long nq = 0, nwide = 0, maxpot = 0;
+    for (uint32_t z = c0; z <= c1 && qi < sc.qmax; z++) {
+        const float precursor_mass = __fmul_rn(mz, (float)z);
+        Tol ptol = sc.precursor_tol;
+        if (sc.wide_window) {  // scoring.rs:428-431: isolation_window.unwrap_or(Da(-2.4,2.4)) * charge
+            float lo = -2.4f, hi = 2.4f;
+            if (b.iso_lo != nullptr && !isnan(b.iso_lo[s]) && !isnan(b.iso_hi[s])) { lo = b.iso_lo[s]; hi = b.iso_hi[s]; }
+            ptol.kind = 2;
+            ptol.lo = __fmul_rn(lo, (float)z);
+            ptol.hi = __fmul_rn(hi, (float)z);
+        }
+        const uint32_t mfc = max_fragment_charge(sc.max_fragment_charge_opt, z);
+        for (uint32_t ii = 0; ii < sc.n_iso; ii++, qi++) {
+            // scoring.rs:391-415: isotope 0 is used whenever min == max
+            const int iso = (sc.min_iso != sc.max_iso) ? sc.min_iso + (int)ii : 0;
+            const float qmass = __fsub_rn(precursor_mass, __fmul_rn((float)iso, NEUTRON));  // scoring.rs:344
+            float plo, phi;
+            tol_bounds(ptol, qmass, plo, phi);
+            const int klo = f32_key(plo), khi = f32_key(phi);
+            uint32_t left, right;
+            binary_search_slice(db.n_pep, [&](uint32_t i) { return f32_key(__ldg(db.pep_mono + i)) < klo; },
+                                [&](uint32_t i) { return f32_key(__ldg(db.pep_mono + i)) <= khi; }, left, right);
+            QueryDesc q;
+            q.pre_lo = left;
+            q.pre_hi = right;
+            q.potential = right - left + 1;
+            const bool lo_ok = left < db.n_pep && __ldg(db.pep_mono + left) >= plo;
+            const bool hi_ok = right < db.n_pep && __ldg(db.pep_mono + right) <= phi;
+            const long long elo = (long long)left + (lo_ok ? 0 : 1);
+            const long long ehi = (long long)right - (hi_ok ? 0 : 1);
+            if (ehi < elo) { q.eff_lo = 1; q.eff_hi = 0; } else { q.eff_lo = (uint32_t)elo; q.eff_hi = (uint32_t)ehi; }
+            q.charge = (uint8_t)z;
+            q.iso = (int8_t)iso;
+            q.nfc = (uint8_t)(mfc - 1);
+            q.mode = q.potential > NARROW_CAP ? 2 : 1;
+            out[qi] = q;
+            nq++;
+            if (q.mode == 2) nwide++;
+            if (q.potential > maxpot) maxpot = q.potential;
+        }
+    }
+    for (; qi < sc.qmax; qi++) {
+        QueryDesc q = {};
+        out[qi] = q;
+    }
+    if (nq) atomicAdd(b.counters + C_QUERIES, nq);
+    if (nwide) atomicAdd(b.counters + C_WIDE, nwide);
+    atomicMax(b.counters + C_MAXPOT, maxpot);
+}
+
+// --------------------------------------------------------------------------------------------- trim (exact)
+// trim_hits (scoring.rs:322-329) == bounded_min_heapify(dense, k) + truncate(k) applied to the dense per-window
+// Vec<PreScore> (one slot per PeptideIx of the window, untouched slots == PreScore::default()).
+// The heap ORDER is observable downstream (stable sort by hyperscore), so it is reproduced exactly:
+//   * the first k dense slots seed the heap literally (zeros included) and are heapified sequentially;
+//   * only slots with matched > 0 can ever exceed the heap minimum, and the minimum is monotone, so the block
+//     scans the remaining slots in index order, filters against the minimum as of the chunk start (a superset
+//     of the true insertions), compacts survivors in index order and lets one thread replay them.
+// cnt(i) -> matched count of dense slot i. Returns the number of entries written to heap[] (min(n,k)); *nonzero =
+// number of slots with matched > 0 (== scored_candidates).
+template <class CountFn>
+__device__ uint32_t trim_dense(CountFn cnt, uint32_t n, uint32_t k, uint32_t pre_lo, uint32_t charge, int iso, uint64_t* heap /*K_MAX*/,
+                               uint64_t* queue /*blockDim.x*/, uint32_t* s_warp /*>= 33 words*/, uint32_t* nonzero) {
+    const uint32_t tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    uint32_t nz = 0;
+    const uint32_t head = n < k ? n : k;
+    for (uint32_t i = tid; i < head; i += nthreads) {
+        const uint32_t c = cnt(i);
+        nz += c != 0;
+        heap[i] = c ? prescore_key(c, pre_lo + i, charge, iso) : PRESCORE_DEFAULT;
+    }
+    __syncthreads();
+    if (n > k) {
+        if (tid == 0)
+            for (uint32_t i = k / 2; i-- > 0;) sift_down(heap, k, i);
+        __syncthreads();
+        for (uint32_t base = k; base < n; base += nthreads) {
+            const uint32_t i = base + tid;
+            const uint32_t c = i < n ? cnt(i) : 0;
+            nz += c != 0;
+            const uint64_t key = prescore_key(c, pre_lo + i, charge, iso);
+            const bool cand = c != 0 && key > heap[0];
+            if (__syncthreads_or(cand)) {
+                const uint32_t ball = __ballot_sync(0xffffffffu, cand);
+                if (lane == 0) s_warp[warp] = __popc(ball);
+                __syncthreads();
+                uint32_t off = 0, total = 0;
+                for (uint32_t w = 0; w < nwarps; w++) {
+                    const uint32_t x = s_warp[w];
+                    if (w < warp) off += x;
+                    total += x;
+                }
+                if (cand) queue[off + __popc(ball & ((1u << lane) - 1))] = key;
+                __syncthreads();
+                if (tid == 0) {
+                    for (uint32_t j = 0; j < total; j++) {
+                        const uint64_t kq = queue[j];
+                        if (kq > heap[0]) {  // slice[i] > slice[0]: swap, sift_down (the swapped-out root lands at i >= k and is truncated)
+                            heap[0] = kq;
+                            sift_down(heap, k, 0);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // block-reduce nz
+    for (int o = 16; o > 0; o >>= 1) nz += __shfl_down_sync(0xffffffffu, nz, o);
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = nz;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t = 0;
+        for (uint32_t w = 0; w < nwarps; w++) t += s_warp[w];
+        *nonzero = t;
+    }
+    __syncthreads();
+    return head;
+}
+
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* s_warp) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = v;
+    __syncthreads();
+    uint32_t t = 0;
+    for (uint32_t w = 0; w < nwarps; w++) t += s_warp[w];
+    __syncthreads();
+    return t;
+}
+
+// ------------------------------------------------------------------------------------- preliminary scoring, narrow
+// One CTA per (spectrum, query). Each thread owns (peak, fragment charge) probes: bucket binary search over
+// min_value, per-page binary search over PeptideIx, exact filter, shared-memory count increment.
+__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b) {
+    __shared__ uint32_t cnt32[NARROW_CAP / 2 + 1];
+    __shared__ uint64_t heap[K_MAX];
+    __shared__ uint64_t queue[PRELIM_THREADS];
+    __shared__ uint32_t s_warp[40];
+    __shared__ uint32_t s_nonzero;
+
+    const uint32_t item = blockIdx.x;
+    const QueryDesc q = b.queries[item];
+    if (q.mode != 1) return;
+    const uint32_t s = item / sc.qmax;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
+    const uint32_t nwords = (q.potential + 1) >> 1;
+    for (uint32_t i = tid; i < nwords; i += PRELIM_THREADS) cnt32[i] = 0;
+    __syncthreads();
+
+    const uint32_t nfc = q.nfc;
+    const uint32_t ntask = np * nfc;
+    uint32_t my_matched = 0, my_pages = 0, my_entries = 0;
+    for (uint32_t t = tid; t < ntask; t += PRELIM_THREADS) {
+        const uint32_t p = t / nfc, fc = t - p * nfc + 1;
+        const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
+        float flo, fhi;
+        tol_bounds(sc.fragment_tol, mass, flo, fhi);
+        const int klo = f32_key(flo), khi = f32_key(fhi);
+        uint32_t bl, br;
+        binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
+                            [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
+        for (uint32_t page = bl; page < br; page++) {
+            const uint64_t pbase = (uint64_t)page * db.bucket_size;
+            const uint64_t pend = min(pbase + db.bucket_size, db.n_frag);
+            const uint2* slice = db.frag + pbase;
+            const uint32_t pn = (uint32_t)(pend - pbase);
+            uint32_t il, ir;
+            binary_search_slice(pn, [&](uint32_t i) { return __ldg(&slice[i].x) < q.pre_lo; }, [&](uint32_t i) { return __ldg(&slice[i].x) <= q.pre_hi; },
+                                il, ir);
+            my_pages++;
+            my_entries += ir - il;
+            for (uint32_t e = il; e < ir; e++) {
+                const uint2 f = __ldg(&slice[e]);
+                const float fmz = __uint_as_float(f.y);
+                if (f.x >= q.eff_lo && f.x <= q.eff_hi && fmz >= flo && fmz <= fhi) {
+                    const uint32_t idx = f.x - q.pre_lo;
+                    atomicAdd(&cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                    my_matched++;
+                }
+            }
+        }
+    }
+    const uint32_t matched_total = block_sum_u32(my_matched, s_warp);
+    const uint32_t pages_total = block_sum_u32(my_pages, s_warp);
+    const uint32_t entries_total = block_sum_u32(my_entries, s_warp);
+    if (tid == 0) {
+        atomicAdd(b.counters + C_TASKS, (unsigned long long)ntask);
+        atomicAdd(b.counters + C_PAGES, (unsigned long long)pages_total);
+        atomicAdd(b.counters + C_ENTRIES, (unsigned long long)entries_total);
+        atomicAdd(b.counters + C_MATCHED, (unsigned long long)matched_total);
+    }
+    QueryHits* h = b.hits + item;
+    if (matched_total == 0) {  // scoring.rs:376-378 returns the untrimmed all-default Vec
+        if (tid == 0) { h->n = 0; h->default_run = q.potential; h->matched_peaks = 0; h->scored_candidates = 0; }
+        return;
+    }
+    const uint32_t k = min(q.potential, sc.kparam);
+    auto cnt = [&](uint32_t i) -> uint32_t { return (cnt32[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu; };
+    const uint32_t nout = trim_dense(cnt, q.potential, k, q.pre_lo, q.charge, q.iso, heap, queue, s_warp, &s_nonzero);
+    uint64_t* keys = b.hit_keys + (size_t)item * sc.kparam;
+    for (uint32_t i = tid; i < nout; i += PRELIM_THREADS) keys[i] = heap[i];
+    if (tid == 0) { h->n = nout; h->default_run = 0; h->matched_peaks = matched_total; h->scored_candidates = s_nonzero; }
+}
+
+// --------------------------------------------------------------------------------------- preliminary scoring, wide
+// Persistent CTAs (one scratch slot each) pull wide queries from a work counter. Per query: zero the dense u16 count
+// array in the CTA's scratch (L2-resident for human-scale windows), resolve the page ranges of 256 probes at a time
+// (one per thread), then stream each [inner_left, inner_right) page slice with whole warps (coalesced 8-byte
+// loads, 4 in flight per lane), filter and count with half-word atomics, finally run the exact trim.
+struct WideRange { uint64_t start; uint32_t len; float flo, fhi; };
+
+__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_wide(DbView db, ScorerView sc, BatchView b, uint32_t* scratch, uint64_t scratch_stride_words,
+                                                                 uint32_t n_items) {
+    __shared__ WideRange ranges[PRELIM_THREADS];
+    __shared__ uint64_t heap[K_MAX];
+    __shared__ uint64_t queue[PRELIM_THREADS];
+    __shared__ uint32_t s_warp[40];
+    __shared__ uint32_t s_nonzero, s_item;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = PRELIM_THREADS / 32;
+    uint32_t* cnt = scratch + (size_t)blockIdx.x * scratch_stride_words;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t it;
+            for (;;) {  // next wide item
+                it = (uint32_t)atomicAdd(b.counters + C_WORK, 1ull);
+                if (it >= n_items || b.queries[it].mode == 2) break;
+            }
+            s_item = it;
+        }
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_items) return;
+        const QueryDesc q = b.queries[item];
+        const uint32_t s = item / sc.qmax;
+        const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
+        const uint32_t nwords = (q.potential + 1) >> 1;
+        for (uint32_t i = tid; i < nwords; i += PRELIM_THREADS) cnt[i] = 0;
+        __syncthreads();
+
+        const uint32_t nfc = q.nfc, ntask = np * nfc;
+        uint32_t my_matched = 0, my_pages = 0, my_entries = 0;
+        for (uint32_t tbase = 0; tbase < ntask; tbase += PRELIM_THREADS) {
+            const uint32_t t = tbase + tid;
+            uint32_t bl = 0, br = 0;
+            float flo = 0.f, fhi = 0.f;
+            if (t < ntask) {
+                const uint32_t p = t / nfc, fc = t - p * nfc + 1;
+                const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);
+                tol_bounds(sc.fragment_tol, mass, flo, fhi);
+                const int klo = f32_key(flo), khi = f32_key(fhi);
+                binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
+                                    [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
+            }
+            for (uint32_t round = 0;; round++) {
+                const bool have = bl + round < br;
+                if (!__syncthreads_or(have)) break;
+                WideRange r;
+                r.start = 0; r.len = 0; r.flo = flo; r.fhi = fhi;
+                if (have) {
+                    const uint32_t page = bl + round;
+                    const uint64_t pbase = (uint64_t)page * db.bucket_size;
+                    const uint64_t pend = min(pbase + db.bucket_size, db.n_frag);
+                    const uint2* slice = db.frag + pbase;
+                    uint32_t il, ir;
+                    binary_search_slice((uint32_t)(pend - pbase), [&](uint32_t i) { return __ldg(&slice[i].x) < q.pre_lo; },
+                                        [&](uint32_t i) { return __ldg(&slice[i].x) <= q.pre_hi; }, il, ir);
+                    r.start = pbase + il;
+                    r.len = ir - il;
+                    my_pages++;
+                    my_entries += ir - il;
+                }
+                ranges[tid] = r;
+                __syncthreads();
+                for (uint32_t ri = warp; ri < PRELIM_THREADS; ri += nwarps) {
+                    const WideRange rr = ranges[ri];
+                    if (rr.len == 0) continue;
+                    const uint2* src = db.frag + rr.start;
+                    for (uint32_t e0 = 0; e0 < rr.len; e0 += 128) {
+                        uint2 f[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t e = e0 + u * 32 + lane;
+                            f[u] = e < rr.len ? __ldg(src + e) : make_uint2(0xFFFFFFFFu, 0x7FC00000u);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const float fmz = __uint_as_float(f[u].y);
+                            if (f[u].x >= q.eff_lo && f[u].x <= q.eff_hi && fmz >= rr.flo && fmz <= rr.fhi) {
+                                const uint32_t idx = f[u].x - q.pre_lo;
+                                atomicAdd(&cnt[idx >> 1], 1u << ((idx & 1) * 16));
+                                my_matched++;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const uint32_t matched_total = block_sum_u32(my_matched, s_warp);
+        const uint32_t pages_total = block_sum_u32(my_pages, s_warp);
+        const uint32_t entries_total = block_sum_u32(my_entries, s_warp);
+        if (tid == 0) {
+            atomicAdd(b.counters + C_TASKS, (unsigned long long)ntask);
+            atomicAdd(b.counters + C_PAGES, (unsigned long long)pages_total);
+            atomicAdd(b.counters + C_ENTRIES, (unsigned long long)entries_total);
+            atomicAdd(b.counters + C_MATCHED, (unsigned long long)matched_total);
+        }
+        QueryHits* h = b.hits + item;
+        if (matched_total == 0) {
+            if (tid == 0) { h->n = 0; h->default_run = q.potential; h->matched_peaks = 0; h->scored_candidates = 0; }
+            continue;
+        }
+        const uint32_t k = min(q.potential, sc.kparam);
+        auto cntf = [&](uint32_t i) -> uint32_t { return (__ldcg(cnt + (i >> 1)) >> ((i & 1) * 16)) & 0xFFFFu; };
+        const uint32_t nout = trim_dense(cntf, q.potential, k, q.pre_lo, q.charge, q.iso, heap, queue, s_warp, &s_nonzero);
+        uint64_t* keys = b.hit_keys + (size_t)item * sc.kparam;
+        for (uint32_t i = tid; i < nout; i += PRELIM_THREADS) keys[i] = heap[i];
+        if (tid == 0) { h->n = nout; h->default_run = 0; h->matched_peaks = matched_total; h->scored_candidates = s_nonzero; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ scoring
+struct ScoreRec {
+    double hyperscore;
+    uint32_t peptide;
+    uint32_t matched_b, matched_y;
+    float summed_b, summed_y;
+    uint32_t longest_b, longest_y;
+    float ppm_difference;
+    uint32_t charge;
+    int iso;
+    uint32_t valid;
+};
+
+// select_most_intense_peak (spectrum.rs:134-159), offset None
+__device__ __forceinline__ int select_most_intense_peak(const float* masses, const float* intens, uint32_t n, float center, const Tol& tol) {
+    float lo, hi;
+    tol_bounds(tol, center, lo, hi);
+    lo = __fadd_rn(lo, 0.0f);
+    hi = __fadd_rn(hi, 0.0f);
+    const int klo = f32_key(lo), khi = f32_key(hi);
+    uint32_t i, j;
+    binary_search_slice(n, [&](uint32_t k) { return f32_key(masses[k]) < klo; }, [&](uint32_t k) { return f32_key(masses[k]) <= khi; }, i, j);
+    int best = -1;
+    float max_int = 0.0f;
+    for (uint32_t idx = i; idx < j; idx++) {
+        const float m = masses[idx];
+        if (m >= lo && m <= hi) {
+            const float it = intens[idx];
+            if (it >= max_int) { max_int = it; best = (int)idx; }
+        }
+    }
+    return best;
+}
+
+// lnfact (scoring.rs:170-177)
+__device__ __forceinline__ double lnfact(uint32_t n) {
+    if (n == 0) return 1.0;
+    const double x = (double)n;
+    return x * log(x) - x + 0.5 * log(x) + 0.5 * log(3.14159265358979323846 * 2.0 * x);
+}
+// ScoreType::score (scoring.rs:179-201)
+__device__ __forceinline__ double hyperscore_of(int score_type, uint32_t mb, uint32_t my, float sb, float sy) {
+    double s;
+    if (score_type == 0) {
+        const double i = (double)__fadd_rn(sb, 1.0f) * (double)__fadd_rn(sy, 1.0f);
+        s = log(i) + lnfact(mb) + lnfact(my);
+    } else {
+        const float si = __fadd_rn(sb, sy);
+        s = (double)(float)log1p((double)si) + lnfact(mb) + lnfact(my);
+    }
+    return isfinite(s) ? s : 255.0;
+}
+
+// Run (scoring.rs:771-793)
+struct Run {
+    uint32_t start, length, last, longest;
+    __device__ __forceinline__ void matched(uint32_t index) {
+        if (last == index) return;
+        if (start + length == index) { length += 1; longest = max(longest, length); }
+        else { start = index; length = 1; longest = max(longest, length); }
+        last = index;
+    }
+};
+
+// One warp scores one candidate (score_candidate, scoring.rs:675-767). Lanes look up theoretical fragments in
+// parallel (ions precomputed per peptide), then matched fragments are folded in the reference's order
+// (kind, ion index, charge) with a ballot loop so the f32 accumulations are bit-identical.
+__device__ __forceinline__ void score_candidate_warp(const DbView& db, const ScorerView& sc, uint64_t key, const float* masses, const float* intens,
+                                                     uint32_t np, ScoreRec* out, uint8_t* mark /*nullable: remove_matched_peaks marks*/) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t pep = key_peptide(key), charge = key_charge(key);
+    const uint32_t L = __ldg(db.pep_len + pep);
+    const uint32_t nions = L - 1;
+    const uint32_t nfc = max_fragment_charge(sc.max_fragment_charge_opt, charge) - 1;
+    const float* ions = db.ions + __ldg(db.ion_off + pep);
+    const uint32_t per_kind = nions * nfc, total = per_kind * db.n_kinds;
+    uint32_t mb = 0, my = 0;
+    float sb = 0.f, sy = 0.f, ppm = 0.f;
+    Run brun = {0, 0, 0, 0}, yrun = {0, 0, 0, 0};
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t f = base + lane;
+        int pk = -1;
+        float mz = 0.f;
+        uint32_t kind_i = 0, idx = 0;
+        if (f < total) {
+            kind_i = f / per_kind;
+            const uint32_t rem = f - kind_i * per_kind;
+            idx = rem / nfc;
+            const uint32_t fc = rem - idx * nfc + 1;
+            mz = __fdiv_rn(__ldg(ions + kind_i * nions + idx), (float)fc);  // scoring.rs:707
+            pk = select_most_intense_peak(masses, intens, np, mz, sc.fragment_tol);
+        }
+        uint32_t mask = __ballot_sync(0xffffffffu, pk >= 0);
+        if (mark != nullptr) {
+            if (pk >= 0) mark[pk] = 1;
+            continue;
+        }
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int pkb = __shfl_sync(0xffffffffu, pk, src);
+            const float mzb = __shfl_sync(0xffffffffu, mz, src);
+            const uint32_t kb = __shfl_sync(0xffffffffu, kind_i, src);
+            const uint32_t ib = __shfl_sync(0xffffffffu, idx, src);
+            const float peak_mass = masses[pkb], peak_int = intens[pkb];
+            // scoring.rs:719-720: peak_intensity * (mz - peak_mass).abs() * 2E6 / (mz + peak_mass)
+            ppm = __fadd_rn(ppm, __fdiv_rn(__fmul_rn(__fmul_rn(peak_int, fabsf(__fsub_rn(mzb, peak_mass))), 2E6f), __fadd_rn(mzb, peak_mass)));
+            if (db.kinds[kb] <= 2) { mb++; sb = __fadd_rn(sb, peak_int); brun.matched(ib); }
+            else { my++; sy = __fadd_rn(sy, peak_int); yrun.matched(ib); }
+        }
+    }
+    if (mark == nullptr && lane == 0) {
+        ScoreRec r;
+        r.peptide = pep; r.charge = charge; r.iso = key_iso(key);
+        r.matched_b = mb & 0xFFFF; r.matched_y = my & 0xFFFF; r.summed_b = sb; r.summed_y = sy;
+        r.longest_b = brun.longest; r.longest_y = yrun.longest;
+        r.hyperscore = hyperscore_of(sc.score_type, r.matched_b, r.matched_y, sb, sy);
+        r.ppm_difference = __fdiv_rn(ppm, __fadd_rn(sb, sy));  // scoring.rs:759
+        r.valid = ((r.matched_b + r.matched_y) & 0xFFFF) >= sc.min_matched_peaks;
+        *out = r;
+    }
+}
+
+struct FeatureOut {  // layout == sage_b200_feature
+    uint32_t spectrum, peptide_idx, peptide_len, rank;
+    int32_t label;
+    float expmass, calcmass;
+    uint32_t charge;
+    float rt, ims, delta_mass, isotope_error, average_ppm;
+    uint32_t _pad0;
+    double hyperscore, delta_next, delta_best;
+    uint32_t matched_peaks, longest_b, longest_y;
+    float longest_y_pct;
+    uint32_t missed_cleavages;
+    float matched_intensity_pct;
+    uint32_t scored_candidates;
+    float ms2_intensity;
+    double poisson;
+    uint32_t fragment_offset, fragment_count;
+};
+static_assert(sizeof(FeatureOut) == 128, "feature layout");
+
+// Append a per-query hit list to a merge buffer (InitialHits += , scoring.rs:60-67). All-default runs are capped at
+// kparam entries: defaults beyond the first k positions can never displace the heap root, so the replay is unchanged.
+__device__ __forceinline__ uint32_t append_hits(uint64_t* buf, uint32_t len, uint32_t cap, const QueryHits& h, const uint64_t* keys, uint32_t kparam) {
+    if (h.n) {
+        for (uint32_t i = 0; i < h.n && len < cap; i++) buf[len++] = keys[i];
+    } else {
+        const uint32_t d = min(h.default_run, kparam);
+        for (uint32_t i = 0; i < d && len < cap; i++) buf[len++] = PRESCORE_DEFAULT;
+    }
+    return len;
+}
+
+// One CTA per spectrum.
+__global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
+                                                         uint64_t* dbg_keys /*nullable: initial_hits dump*/, uint32_t* dbg_meta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: masses[pmax] intens[pmax] cur[lcap] tot[lcap] recs[kparam] order[kparam] mark[pmax]
+    float* masses = reinterpret_cast<float*>(smem_raw);
+    float* intens = masses + pmax;
+    uint64_t* cur = reinterpret_cast<uint64_t*>(intens + pmax + (pmax & 1));
+    uint64_t* tot = cur + sc.lcap;
+    ScoreRec* recs = reinterpret_cast<ScoreRec*>(tot + sc.lcap);
+    uint32_t* order = reinterpret_cast<uint32_t*>(recs + sc.kparam);
+    uint8_t* mark = reinterpret_cast<uint8_t*>(order + sc.kparam);
+    __shared__ uint32_t s_ntot, s_ncand, s_np, s_nvalid;
+    __shared__ unsigned long long s_matched_peaks, s_scored;
+    __shared__ float s_tic;
+
+    const uint32_t s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SCORE_THREADS / 32;
+    const uint32_t p0 = b.peak_off[s];
+    uint32_t np = b.peak_off[s + 1] - p0;
+    for (uint32_t i = tid; i < np; i += SCORE_THREADS) { masses[i] = b.masses[p0 + i]; intens[i] = b.intens[p0 + i]; }
+
+    // ---- fold the per-query hits: matched_peaks (isotope fold, scoring.rs:384-416) then initial_hits (charge fold, :418-462)
+    if (tid == 0) {
+        const QueryDesc* qd = b.queries + (size_t)s * sc.qmax;
+        const QueryHits* qh = b.hits + (size_t)s * sc.qmax;
+        const uint64_t* qk = b.hit_keys + (size_t)s * sc.qmax * sc.kparam;
+        unsigned long long mp = 0, scd = 0;
+        uint32_t ntot = 0;
+        const bool iso_fold = sc.min_iso != sc.max_iso;
+        uint32_t nq = 0;
+        while (nq < sc.qmax && qd[nq].mode != 0) nq++;
+        const uint32_t nch = sc.n_iso ? nq / sc.n_iso : 0;
+        for (uint32_t ci = 0; ci < nch; ci++) {
+            uint32_t ncur = 0;
+            for (uint32_t ii = 0; ii < sc.n_iso; ii++) {
+                const uint32_t qi = ci * sc.n_iso + ii;
+                mp += qh[qi].matched_peaks;
+                scd += qh[qi].scored_candidates;
+                ncur = append_hits(cur, ncur, sc.lcap, qh[qi], qk + (size_t)qi * sc.kparam, sc.kparam);
+            }
+            if (iso_fold) {  // trim_hits on the concatenation (scoring.rs:405)
+                const uint32_t k = min(ncur, sc.kparam);
+                bounded_min_heapify_seq(cur, ncur, k);
+                ncur = k;
+            }
+            for (uint32_t i = 0; i < ncur && ntot < sc.lcap; i++) tot[ntot++] = cur[i];
+        }
+        {  // final trim_hits (scoring.rs:460)
+            const uint32_t k = min(ntot, sc.kparam);
+            bounded_min_heapify_seq(tot, ntot, k);
+            ntot = k;
+        }
+        s_ntot = ntot;
+        s_matched_peaks = mp;
+        s_scored = scd;
+        // build_features filter: peptide != PeptideIx::default() (scoring.rs:489), order preserved
+        uint32_t nc = 0;
+        for (uint32_t i = 0; i < ntot; i++)
+            if (key_peptide(tot[i]) != 0xFFFFFFFFu) cur[nc++] = tot[i];
+        s_ncand = nc;
+        s_np = np;
+        s_tic = b.tic[s];
+    }
+    __syncthreads();
+    if (dbg_keys != nullptr) {  // white-box dump of initial_hits
+        for (uint32_t i = tid; i < s_ntot; i += SCORE_THREADS) dbg_keys[(size_t)s * sc.kparam + i] = tot[i];
+        if (tid == 0) { dbg_meta[s * 4 + 0] = s_ntot; dbg_meta[s * 4 + 1] = (uint32_t)s_matched_peaks; dbg_meta[s * 4 + 2] = (uint32_t)s_scored; }
+    }
+    const uint32_t ncand = s_ncand;
+    const float mzp = __fsub_rn(b.prec_mz[s], PROTON);
+    const double lambda = (double)s_matched_peaks / (double)s_scored;  // scoring.rs:499
+    const uint32_t rounds = sc.chimera ? sc.report_psms : 1;
+    const uint32_t per_round = sc.chimera ? 1 : sc.report_psms;
+    uint32_t nout = 0;
+    if (tid == 0 && ncand) {
+        unsigned long long fl = 0;
+        for (uint32_t c = 0; c < ncand; c++) fl += 2ull * db.pep_len[key_peptide(cur[c])] + 2ull;
+        atomicAdd(b.counters + C_CANDS, (unsigned long long)ncand * rounds);
+        atomicAdd(b.counters + C_PEPFLOATS, fl * rounds);
+    }
+    for (uint32_t round = 0; round < rounds; round++) {
+        np = s_np;
+        for (uint32_t c = warp; c < ncand; c += nwarps) score_candidate_warp(db, sc, cur[c], masses, intens, np, recs + c, nullptr);
+        __syncthreads();
+        // stable sort by hyperscore descending (scoring.rs:495) via rank counting
+        if (tid == 0) s_nvalid = 0;
+        __syncthreads();
+        if (tid < ncand && recs[tid].valid) {
+            const double h = recs[tid].hyperscore;
+            uint32_t pos = 0;
+            for (uint32_t j = 0; j < ncand; j++) {
+                if (!recs[j].valid) continue;
+                const double hj = recs[j].hyperscore;
+                pos += (hj > h) || (hj == h && j < tid);
+            }
+            order[pos] = tid;
+            atomicAdd(&s_nvalid, 1u);
+        }
+        __syncthreads();
+        const uint32_t nvalid = s_nvalid;
+        const uint32_t emit = min(per_round, nvalid);
+        if (tid < emit) {
+            const ScoreRec r = recs[order[tid]];
+            const double next = tid + 1 < nvalid ? recs[order[tid + 1]].hyperscore : 0.0;
+            const double best = recs[order[0]].hyperscore;
+            const uint32_t k = (r.matched_b + r.matched_y) & 0xFFFF;
+            const double log10_poisson = ((double)k * log(lambda) - lambda - lnfact(k)) / 2.302585092994045684;
+            const float precursor_mass = __fmul_rn(mzp, (float)r.charge);
+            const float iso = __fmul_rn((float)r.iso, NEUTRON);
+            const float mono = db.pep_mono[r.peptide];
+            // scoring.rs:530-531
+            const float delta_mass = __fdiv_rn(__fmul_rn(__fsub_rn(__fsub_rn(precursor_mass, mono), iso), 2E6f), __fadd_rn(__fsub_rn(precursor_mass, iso), mono));
+            const uint32_t plen = db.pep_len[r.peptide];
+            const float sum = __fadd_rn(r.summed_b, r.summed_y);
+            FeatureOut f;
+            f.spectrum = s; f.peptide_idx = r.peptide; f.peptide_len = plen;
+            f.rank = sc.chimera ? round + 1 : tid + 1;
+            f.label = (db.pep_flags[r.peptide] & 1) ? -1 : 1;
+            f.expmass = precursor_mass; f.calcmass = mono; f.charge = r.charge;
+            f.rt = b.rt ? b.rt[s] : 0.0f;
+            f.ims = (b.ims && !isnan(b.ims[s])) ? b.ims[s] : 0.0f;
+            f.delta_mass = delta_mass; f.isotope_error = iso; f.average_ppm = r.ppm_difference; f._pad0 = 0;
+            f.hyperscore = r.hyperscore; f.delta_next = r.hyperscore - next; f.delta_best = best - r.hyperscore;
+            f.matched_peaks = k; f.longest_b = r.longest_b; f.longest_y = r.longest_y;
+            f.longest_y_pct = __fdiv_rn((float)r.longest_y, (float)plen);
+            f.missed_cleavages = db.pep_missed[r.peptide];
+            f.matched_intensity_pct = __fdiv_rn(__fmul_rn(100.0f, sum), s_tic);
+            f.scored_candidates = (uint32_t)s_scored;
+            f.ms2_intensity = sum;
+            f.poisson = isfinite(log10_poisson) ? log10_poisson : -INFINITY;
+            f.fragment_offset = 0; f.fragment_count = 0;
+            features[(size_t)s * sc.report_psms + nout + tid] = f;
+        }
+        nout += emit;
+        if (!sc.chimera || emit == 0 || round + 1 == rounds) break;
+        // ---- remove_matched_peaks (scoring.rs:598-644) for the PSM just accepted
+        for (uint32_t i = tid; i < np; i += SCORE_THREADS) mark[i] = 0;
+        __syncthreads();
+        if (warp == 0) {
+            const ScoreRec r = recs[order[0]];
+            score_candidate_warp(db, sc, prescore_key(0, r.peptide, r.charge, r.iso), masses, intens, np, nullptr, mark);
+        }
+        __syncthreads();
+        // a peak is removed when its (mass, intensity) pair equals a marked one (Vec::contains on (f32,f32))
+        for (uint32_t i = tid; i < np; i += SCORE_THREADS) {
+            if (mark[i]) continue;
+            const float m = masses[i], it = intens[i];
+            bool rm = false;
+            for (int j = (int)i - 1; j >= 0 && masses[j] == m && !rm; j--) rm = mark[j] == 1 && intens[j] == it;
+            for (uint32_t j = i + 1; j < np && masses[j] == m && !rm; j++) rm = mark[j] == 1 && intens[j] == it;
+            if (rm) mark[i] = 2;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = 0;
+            for (uint32_t base = 0; base < np; base += 32) {
+                const uint32_t i = base + lane;
+                const bool keep = i < np && mark[i] == 0;
+                const float m = i < np ? masses[i] : 0.f, it = i < np ? intens[i] : 0.f;
+                const uint32_t ball = __ballot_sync(0xffffffffu, keep);
+                __syncwarp();
+                if (keep) {
+                    const uint32_t d = w + __popc(ball & ((1u << lane) - 1));
+                    masses[d] = m;
+                    intens[d] = it;
+                }
+                w += __popc(ball);
+                __syncwarp();
+            }
+            if (lane == 0) {
+                float t = 0.0f;  // iter().sum::<f32>() (scoring.rs:643)
+                for (uint32_t i = 0; i < w; i++) t = __fadd_rn(t, intens[i]);
+                s_tic = t;
+                s_np = w;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        counts[s] = nout;
+        if (nout) atomicAdd(b.counters + C_PSMS, (unsigned long long)nout);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- index construction
+// IonSeries (ion_series.rs:36-85) for every kind of every peptide; one thread per peptide (sequential f32 running sum).
+__global__ void k_build_ions(uint32_t n_pep, const uint32_t* seq_off, const uint8_t* seq, const float* mods, const float* nterm, const float* mono,
+                             const uint32_t* ion_off, uint32_t n_kinds, DbView kinds_src, float* ions, const float* residue_mass) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pep) return;
+    const float Cm = 12.0f, O = 15.994914f, H = 1.007825f, PRO = 1.0072764f, N = 14.003074f;
+    const float NH3 = __fadd_rn(__fadd_rn(N, __fmul_rn(H, 2.0f)), PRO);
+    const uint32_t o0 = seq_off[p], L = seq_off[p + 1] - o0;
+    if (L == 0) return;
+    const float nt = isnan(nterm[p]) ? 0.0f : nterm[p];
+    const float m = mono[p];
+    float* out = ions + ion_off[p];
+    for (uint32_t k = 0; k < n_kinds; k++) {
+        const uint32_t kind = kinds_src.kinds[k];
+        float cum;
+        switch (kind) {
+            case 0: cum = __fsub_rn(nt, __fadd_rn(Cm, O)); break;
+            case 1: cum = nt; break;
+            case 2: cum = __fadd_rn(nt, NH3); break;
+            case 3: cum = __fadd_rn(__fsub_rn(m, nt), __fadd_rn(__fadd_rn(__fsub_rn(__fadd_rn(Cm, O), NH3), N), H)); break;
+            case 4: cum = __fsub_rn(m, nt); break;
+            default: cum = __fsub_rn(__fsub_rn(m, nt), NH3); break;
+        }
+        for (uint32_t i = 0; i + 1 < L; i++) {
+            const uint8_t r = seq[o0 + i];
+            const float rm = __fadd_rn((r >= 'A' && r <= 'Z') ? residue_mass[r - 'A'] : 0.0f, mods[o0 + i]);
+            cum = kind <= 2 ? __fadd_rn(cum, rm) : __fadd_rn(cum, -rm);
+            out[k * (L - 1) + i] = cum;
+        }
+    }
+}
+
+// Fragment generation for the index (database.rs:272-297): keep ions with index > min_ion_index.
+// Pass 0 (frag_off == nullptr -> counts[p]); pass 1 writes keys (total-order key of mz) and peptide ids.
+__global__ void k_gen_fragments(uint32_t n_pep, const uint8_t* pep_len, const uint32_t* ion_off, const float* ions, uint32_t n_kinds, DbView kinds_src,
+                                uint32_t min_ion_index, uint32_t* counts, const uint64_t* frag_off, uint32_t* out_key, uint32_t* out_pep) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pep) return;
+    const uint32_t L = pep_len[p];
+    if (L == 0) { if (counts) counts[p] = 0; return; }
+    const float* src = ions + ion_off[p];
+    uint64_t w = frag_off ? frag_off[p] : 0;
+    uint32_t c = 0;
+    for (uint32_t k = 0; k < n_kinds; k++) {
+        const uint32_t kind = kinds_src.kinds[k];
+        for (uint32_t i = 0; i + 1 < L; i++) {
+            const bool keep = kind <= 2 ? (i + 1) > min_ion_index : ((L - 1) - i) > min_ion_index;
+            if (!keep) continue;
+            if (frag_off) {
+                out_key[w] = (uint32_t)f32_key(src[k * (L - 1) + i]) ^ 0x80000000u;  // unsigned order == total_cmp order
+                out_pep[w] = p;
+                w++;
+            }
+            c++;
+        }
+    }
+    if (counts) counts[p] = c;
+}
+
+// After the global sort by m/z: record bucket minima and form (bucket, peptide) 64-bit keys with the m/z as payload.
+__global__ void k_bucket_keys(uint64_t n_frag, uint32_t bucket_shift, const uint32_t* key_sorted, const uint32_t* pep_sorted, uint64_t* key64,
+                              uint32_t* mzbits, float* bucket_min) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frag) return;
+    const uint32_t u = key_sorted[i] ^ 0x80000000u;                 // back to the signed total-order key
+    const uint32_t bits = u ^ (((uint32_t)((int)u >> 31)) >> 1);    // inverse of f32_key
+    mzbits[i] = bits;
+    const uint64_t bucket = i >> bucket_shift;
+    key64[i] = (bucket << 32) | pep_sorted[i];
+    if ((i & ((1ull << bucket_shift) - 1)) == 0) bucket_min[bucket] = __uint_as_float(bits);
+}
+__global__ void k_pack_fragments(uint64_t n_frag, const uint64_t* key64, const uint32_t* mzbits, uint2* frag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frag) return;
+    frag[i] = make_uint2((uint32_t)key64[i], mzbits[i]);
+}
+__global__ void k_pack_fragments_soa(uint64_t n_frag, const uint32_t* pep, const float* mz, uint2* frag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frag) return;
+    frag[i] = make_uint2(pep[i], __float_as_uint(mz[i]));
+}
+__global__ void k_unpack_fragments(uint64_t n_frag, const uint2* frag, uint32_t* pep, float* mz) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frag) return;
+    const uint2 f = frag[i];
+    if (pep) pep[i] = f.x;
+    if (mz) mz[i] = __uint_as_float(f.y);
+}
+
+}  // namespace sb

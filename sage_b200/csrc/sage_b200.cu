@@ -1,0 +1,690 @@
+// sage_b200.cu — host runtime and C ABI (include/sage_b200.h) of the B200-native search-and-score library.
+//
+// Host side of the boundary, written in C++ because the reference (Rust) toolchain is absent in this image; it
+// mirrors the reference's call structure: IndexedDatabase (database.rs:384-395) -> sage_b200_db, Scorer
+// (scoring.rs:210-232) -> sage_b200_scorer, `par_iter().flat_map(|s| scorer.score(s))` (runner.rs:311-325) ->
+// sage_b200_score_batch. No CPU fallback exists: every entry point fails loudly when CUDA is unavailable.
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sage_b200.h"
+#include "kernels.cuh"
+
+using namespace sb;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) return fail(SAGE_B200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// mass.rs:64-76
+static const float kResidueMass[26] = {71.03711f, 0.0f,      103.00919f, 115.02694f, 129.04259f, 147.0684f, 57.02146f,  137.05891f, 113.08406f,
+                                       0.0f,      128.09496f, 113.08406f, 131.0405f,  114.04293f, 237.14774f, 97.05276f, 128.05858f, 156.1011f,
+                                       87.03203f, 101.04768f, 150.95363f, 99.06841f,  186.07932f, 0.0f,       163.06332f, 0.0f};
+
+// ------------------------------------------------------------------------------------------- device buffers
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(SAGE_B200_ECUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+        if (e != cudaSuccess) return fail(SAGE_B200_ECUDA, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// ------------------------------------------------------------------------------------------------ db
+struct sage_b200_db {
+    int device = 0;
+    DbView v{};
+    void *d_frag = nullptr, *d_bucket_min = nullptr, *d_pep_mono = nullptr, *d_ion_off = nullptr, *d_ions = nullptr, *d_pep_len = nullptr,
+         *d_pep_flags = nullptr, *d_pep_missed = nullptr;
+    uint64_t total_residues = 0, device_bytes = 0;
+    int sm_count = 148;
+};
+
+static int dmalloc(sage_b200_db* db, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    CUDA_TRY(cudaMalloc(p, bytes));
+    db->device_bytes += bytes;
+    return 0;
+}
+
+static uint32_t ceil_log2_u64(uint64_t n) {
+    uint32_t l = 0;
+    while ((1ull << l) < n) l++;
+    return l;
+}
+
+// Uploads the peptide table and builds the per-peptide ion tables. On return tmp_* hold device copies still needed by db_build.
+static int db_upload_peptides(sage_b200_db* db, const sage_b200_peptides* P, const uint8_t* kinds, uint64_t n_kinds) {
+    if (!P || (P->n_peptides && (!P->residue_offsets || !P->sequence || !P->modifications || !P->nterm || !P->monoisotopic || !P->decoy || !P->missed_cleavages)))
+        return fail(SAGE_B200_EINVAL, "peptides: null array");
+    if (n_kinds == 0 || n_kinds > MAX_KINDS) return fail(SAGE_B200_EINVAL, "ion_kinds: need 1..%d kinds", MAX_KINDS);
+    if (P->n_peptides >= 0xFFFFFFFEull) return fail(SAGE_B200_ELIMIT, "too many peptides for u32 PeptideIx");
+    const uint64_t n = P->n_peptides;
+    db->v.n_pep = (uint32_t)n;
+    db->v.n_kinds = (uint32_t)n_kinds;
+    for (uint64_t k = 0; k < n_kinds; k++) {
+        if (kinds[k] > 5) return fail(SAGE_B200_EINVAL, "ion kind %u out of range", kinds[k]);
+        db->v.kinds[k] = kinds[k];
+    }
+    const uint64_t nres = n ? P->residue_offsets[n] : 0;
+    db->total_residues = nres;
+    std::vector<uint8_t> len(n), flags(n);
+    std::vector<uint32_t> ion_off(n + 1);
+    uint64_t acc = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t L = P->residue_offsets[i + 1] - P->residue_offsets[i];
+        if (L == 0 || L > 255) return fail(SAGE_B200_ELIMIT, "peptide %llu has length %llu (supported 1..255)", (unsigned long long)i, (unsigned long long)L);
+        len[i] = (uint8_t)L;
+        flags[i] = P->decoy[i] ? 1 : 0;
+        ion_off[i] = (uint32_t)acc;
+        acc += n_kinds * (L - 1);
+        if (acc > 0xFFFFFFFFull) return fail(SAGE_B200_ELIMIT, "ion table exceeds 2^32 entries");
+    }
+    ion_off[n] = (uint32_t)acc;
+    int rc;
+    if ((rc = dmalloc(db, &db->d_pep_mono, 4 * n))) return rc;
+    if ((rc = dmalloc(db, &db->d_pep_len, n))) return rc;
+    if ((rc = dmalloc(db, &db->d_pep_flags, n))) return rc;
+    if ((rc = dmalloc(db, &db->d_pep_missed, n))) return rc;
+    if ((rc = dmalloc(db, &db->d_ion_off, 4 * (n + 1)))) return rc;
+    if ((rc = dmalloc(db, &db->d_ions, 4 * acc))) return rc;
+    CUDA_TRY(cudaMemcpy(db->d_pep_mono, P->monoisotopic, 4 * n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db->d_pep_len, len.data(), n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db->d_pep_flags, flags.data(), n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db->d_pep_missed, P->missed_cleavages, n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db->d_ion_off, ion_off.data(), 4 * (n + 1), cudaMemcpyHostToDevice));
+    // temporaries for ion generation
+    void *t_off = nullptr, *t_seq = nullptr, *t_mods = nullptr, *t_nterm = nullptr, *t_res = nullptr;
+    CUDA_TRY(cudaMalloc(&t_off, 4 * (n + 1) + 16));
+    CUDA_TRY(cudaMalloc(&t_seq, nres + 16));
+    CUDA_TRY(cudaMalloc(&t_mods, 4 * nres + 16));
+    CUDA_TRY(cudaMalloc(&t_nterm, 4 * n + 16));
+    CUDA_TRY(cudaMalloc(&t_res, sizeof kResidueMass));
+    if (n) {
+        CUDA_TRY(cudaMemcpy(t_off, P->residue_offsets, 4 * (n + 1), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(t_seq, P->sequence, nres, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(t_mods, P->modifications, 4 * nres, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(t_nterm, P->nterm, 4 * n, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemcpy(t_res, kResidueMass, sizeof kResidueMass, cudaMemcpyHostToDevice));
+    db->v.pep_mono = (const float*)db->d_pep_mono;
+    db->v.pep_len = (const uint8_t*)db->d_pep_len;
+    db->v.pep_flags = (const uint8_t*)db->d_pep_flags;
+    db->v.pep_missed = (const uint8_t*)db->d_pep_missed;
+    db->v.ion_off = (const uint32_t*)db->d_ion_off;
+    db->v.ions = (const float*)db->d_ions;
+    if (n) {
+        k_build_ions<<<(unsigned)((n + 127) / 128), 128>>>((uint32_t)n, (const uint32_t*)t_off, (const uint8_t*)t_seq, (const float*)t_mods,
+                                                           (const float*)t_nterm, (const float*)db->d_pep_mono, (const uint32_t*)db->d_ion_off,
+                                                           (uint32_t)n_kinds, db->v, (float*)db->d_ions, (const float*)t_res);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(t_off); cudaFree(t_seq); cudaFree(t_mods); cudaFree(t_nterm); cudaFree(t_res);
+    return 0;
+}
+
+static int db_new(int device, sage_b200_db** out) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SAGE_B200_ECUDA, "no CUDA device available (%s): sage_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(SAGE_B200_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    sage_b200_db* db = new sage_b200_db();
+    db->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) db->sm_count = prop.multiProcessorCount;
+    *out = db;
+    return 0;
+}
+
+extern "C" int sage_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" void sage_b200_db_destroy(sage_b200_db* db) {
+    if (!db) return;
+    cudaSetDevice(db->device);
+    void* ps[] = {db->d_frag, db->d_bucket_min, db->d_pep_mono, db->d_ion_off, db->d_ions, db->d_pep_len, db->d_pep_flags, db->d_pep_missed};
+    for (void* p : ps)
+        if (p) cudaFree(p);
+    delete db;
+}
+
+extern "C" int sage_b200_db_create(const sage_b200_peptides* peptides, const sage_b200_index* index, int device, sage_b200_db** out) {
+    if (!out || !index) return fail(SAGE_B200_EINVAL, "db_create: null argument");
+    if (index->bucket_size == 0 || index->bucket_size > 0x7FFFFFFFull) return fail(SAGE_B200_EINVAL, "bucket_size out of range");
+    if (index->n_fragments && (!index->fragment_peptide || !index->fragment_mz || !index->bucket_min)) return fail(SAGE_B200_EINVAL, "index: null array");
+    const uint64_t nb_expect = (index->n_fragments + index->bucket_size - 1) / index->bucket_size;
+    if (index->n_buckets != nb_expect) return fail(SAGE_B200_EINVAL, "n_buckets %llu != ceil(n_fragments/bucket_size) %llu", (unsigned long long)index->n_buckets, (unsigned long long)nb_expect);
+    sage_b200_db* db = nullptr;
+    int rc = db_new(device, &db);
+    if (rc) return rc;
+    if ((rc = db_upload_peptides(db, peptides, index->ion_kinds, index->n_ion_kinds))) { sage_b200_db_destroy(db); return rc; }
+    const uint64_t nf = index->n_fragments;
+    db->v.n_frag = nf;
+    db->v.n_bucket = (uint32_t)index->n_buckets;
+    db->v.bucket_size = (uint32_t)index->bucket_size;
+    if ((rc = dmalloc(db, &db->d_frag, 8 * nf))) { sage_b200_db_destroy(db); return rc; }
+    if ((rc = dmalloc(db, &db->d_bucket_min, 4 * index->n_buckets))) { sage_b200_db_destroy(db); return rc; }
+    void *t_pep = nullptr, *t_mz = nullptr;
+    auto cleanup = [&]() { if (t_pep) cudaFree(t_pep); if (t_mz) cudaFree(t_mz); };
+    if (nf) {
+        if (cudaMalloc(&t_pep, 4 * nf) != cudaSuccess || cudaMalloc(&t_mz, 4 * nf) != cudaSuccess) { cleanup(); sage_b200_db_destroy(db); return fail(SAGE_B200_ECUDA, "cudaMalloc of upload temporaries failed"); }
+        cudaMemcpy(t_pep, index->fragment_peptide, 4 * nf, cudaMemcpyHostToDevice);
+        cudaMemcpy(t_mz, index->fragment_mz, 4 * nf, cudaMemcpyHostToDevice);
+        cudaMemcpy(db->d_bucket_min, index->bucket_min, 4 * index->n_buckets, cudaMemcpyHostToDevice);
+        k_pack_fragments_soa<<<(unsigned)((nf + 255) / 256), 256>>>(nf, (const uint32_t*)t_pep, (const float*)t_mz, (uint2*)db->d_frag);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cleanup();
+    if (e != cudaSuccess) { sage_b200_db_destroy(db); return fail(SAGE_B200_ECUDA, "index upload failed: %s", cudaGetErrorString(e)); }
+    db->v.frag = (const uint2*)db->d_frag;
+    db->v.bucket_min = (const float*)db->d_bucket_min;
+    *out = db;
+    return 0;
+}
+
+extern "C" int sage_b200_db_build(const sage_b200_peptides* peptides, uint64_t bucket_size, const uint8_t* ion_kinds, uint64_t n_ion_kinds,
+                                  uint64_t min_ion_index, int device, sage_b200_db** out) {
+    if (!out || !peptides || !ion_kinds) return fail(SAGE_B200_EINVAL, "db_build: null argument");
+    if (bucket_size == 0 || (bucket_size & (bucket_size - 1)) || bucket_size > (1ull << 30))
+        return fail(SAGE_B200_EINVAL, "bucket_size must be a power of two (Builder::make_parameters rounds up, database.rs:97)");
+    sage_b200_db* db = nullptr;
+    int rc = db_new(device, &db);
+    if (rc) return rc;
+    if ((rc = db_upload_peptides(db, peptides, ion_kinds, n_ion_kinds))) { sage_b200_db_destroy(db); return rc; }
+    const uint64_t n = peptides->n_peptides;
+    // fragments kept per peptide: n_kinds * max(0, L-1-min_ion_index)   (database.rs:281-291)
+    std::vector<uint64_t> frag_off(n + 1);
+    uint64_t nf = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        frag_off[i] = nf;
+        const uint64_t L = peptides->residue_offsets[i + 1] - peptides->residue_offsets[i];
+        const uint64_t keep = (L - 1) > min_ion_index ? (L - 1) - min_ion_index : 0;
+        nf += n_ion_kinds * keep;
+    }
+    frag_off[n] = nf;
+    const uint32_t shift = ceil_log2_u64(bucket_size);
+    const uint64_t nb = (nf + bucket_size - 1) / bucket_size;
+    if (nb > 0xFFFFFFFFull) { sage_b200_db_destroy(db); return fail(SAGE_B200_ELIMIT, "too many buckets"); }
+    db->v.n_frag = nf;
+    db->v.n_bucket = (uint32_t)nb;
+    db->v.bucket_size = (uint32_t)bucket_size;
+    if ((rc = dmalloc(db, &db->d_frag, 8 * nf))) { sage_b200_db_destroy(db); return rc; }
+    if ((rc = dmalloc(db, &db->d_bucket_min, 4 * nb))) { sage_b200_db_destroy(db); return rc; }
+    db->v.frag = (const uint2*)db->d_frag;
+    db->v.bucket_min = (const float*)db->d_bucket_min;
+    if (nf == 0) { *out = db; return 0; }
+
+    void *d_off = nullptr, *k32a = nullptr, *k32b = nullptr, *pa = nullptr, *pb = nullptr, *k64a = nullptr, *k64b = nullptr, *mza = nullptr, *mzb = nullptr, *tmp = nullptr;
+    auto cleanup = [&]() { for (void* p : {d_off, k32a, k32b, pa, pb, k64a, k64b, mza, mzb, tmp}) if (p) cudaFree(p); };
+#define TRY_BUILD(expr)                                                                                                    \
+    do {                                                                                                                   \
+        cudaError_t _e = (expr);                                                                                           \
+        if (_e != cudaSuccess) { cleanup(); sage_b200_db_destroy(db); return fail(SAGE_B200_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } \
+    } while (0)
+    TRY_BUILD(cudaMalloc(&d_off, 8 * (n + 1)));
+    TRY_BUILD(cudaMemcpy(d_off, frag_off.data(), 8 * (n + 1), cudaMemcpyHostToDevice));
+    TRY_BUILD(cudaMalloc(&k32a, 4 * nf)); TRY_BUILD(cudaMalloc(&k32b, 4 * nf));
+    TRY_BUILD(cudaMalloc(&pa, 4 * nf)); TRY_BUILD(cudaMalloc(&pb, 4 * nf));
+    k_gen_fragments<<<(unsigned)((n + 127) / 128), 128>>>((uint32_t)n, db->v.pep_len, db->v.ion_off, db->v.ions, db->v.n_kinds, db->v, (uint32_t)std::min<uint64_t>(min_ion_index, 0xFFFFFFFFull),
+                                                          nullptr, (const uint64_t*)d_off, (uint32_t*)k32a, (uint32_t*)pa);
+    TRY_BUILD(cudaGetLastError());
+    // (1) stable LSD radix sort by fragment m/z (par_sort_unstable_by fragment_mz, database.rs:301; ties keep PeptideIx order)
+    size_t tb = 0;
+    if (nf > 0x7FFFFFFFull) { cleanup(); sage_b200_db_destroy(db); return fail(SAGE_B200_ELIMIT, "more than 2^31 fragments: sort in slabs not implemented"); }
+    TRY_BUILD(cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint32_t*)k32a, (uint32_t*)k32b, (const uint32_t*)pa, (uint32_t*)pb, (int)nf));
+    TRY_BUILD(cudaMalloc(&tmp, tb + 16));
+    TRY_BUILD(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint32_t*)k32a, (uint32_t*)k32b, (const uint32_t*)pa, (uint32_t*)pb, (int)nf));
+    cudaFree(tmp); tmp = nullptr;
+    cudaFree(k32a); k32a = nullptr; cudaFree(pa); pa = nullptr;
+    // (2) bucket minima + (bucket, PeptideIx) keys, then a stable sort inside buckets (database.rs:337-346)
+    TRY_BUILD(cudaMalloc(&k64a, 8 * nf)); TRY_BUILD(cudaMalloc(&k64b, 8 * nf));
+    TRY_BUILD(cudaMalloc(&mza, 4 * nf)); TRY_BUILD(cudaMalloc(&mzb, 4 * nf));
+    k_bucket_keys<<<(unsigned)((nf + 255) / 256), 256>>>(nf, shift, (const uint32_t*)k32b, (const uint32_t*)pb, (uint64_t*)k64a, (uint32_t*)mza, (float*)db->d_bucket_min);
+    TRY_BUILD(cudaGetLastError());
+    const int end_bit = std::min<int>(64, 32 + (int)ceil_log2_u64(nb + 1) + 1);
+    TRY_BUILD(cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint64_t*)k64a, (uint64_t*)k64b, (const uint32_t*)mza, (uint32_t*)mzb, (int)nf, 0, end_bit));
+    TRY_BUILD(cudaMalloc(&tmp, tb + 16));
+    TRY_BUILD(cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint64_t*)k64a, (uint64_t*)k64b, (const uint32_t*)mza, (uint32_t*)mzb, (int)nf, 0, end_bit));
+    k_pack_fragments<<<(unsigned)((nf + 255) / 256), 256>>>(nf, (const uint64_t*)k64b, (const uint32_t*)mzb, (uint2*)db->d_frag);
+    TRY_BUILD(cudaGetLastError());
+    TRY_BUILD(cudaDeviceSynchronize());
+    cleanup();
+#undef TRY_BUILD
+    *out = db;
+    return 0;
+}
+
+extern "C" int sage_b200_db_get_info(const sage_b200_db* db, sage_b200_db_info* info) {
+    if (!db || !info) return fail(SAGE_B200_EINVAL, "db_info: null argument");
+    info->n_peptides = db->v.n_pep; info->n_fragments = db->v.n_frag; info->n_buckets = db->v.n_bucket; info->bucket_size = db->v.bucket_size;
+    info->n_ion_kinds = db->v.n_kinds; info->total_residues = db->total_residues; info->device_bytes = db->device_bytes; info->device = db->device;
+    return 0;
+}
+
+extern "C" int sage_b200_db_export_index(const sage_b200_db* db, uint32_t* fragment_peptide, float* fragment_mz, float* bucket_min) {
+    if (!db) return fail(SAGE_B200_EINVAL, "db_export_index: null db");
+    CUDA_TRY(cudaSetDevice(db->device));
+    const uint64_t nf = db->v.n_frag;
+    if (nf && (fragment_peptide || fragment_mz)) {
+        void *t_pep = nullptr, *t_mz = nullptr;
+        CUDA_TRY(cudaMalloc(&t_pep, 4 * nf));
+        CUDA_TRY(cudaMalloc(&t_mz, 4 * nf));
+        k_unpack_fragments<<<(unsigned)((nf + 255) / 256), 256>>>(nf, db->v.frag, (uint32_t*)t_pep, (float*)t_mz);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess && fragment_peptide) e = cudaMemcpy(fragment_peptide, t_pep, 4 * nf, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && fragment_mz) e = cudaMemcpy(fragment_mz, t_mz, 4 * nf, cudaMemcpyDeviceToHost);
+        cudaFree(t_pep); cudaFree(t_mz);
+        if (e != cudaSuccess) return fail(SAGE_B200_ECUDA, "export failed: %s", cudaGetErrorString(e));
+    }
+    if (bucket_min && db->v.n_bucket) CUDA_TRY(cudaMemcpy(bucket_min, db->d_bucket_min, 4ull * db->v.n_bucket, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ scorer
+struct sage_b200_scorer {
+    const sage_b200_db* db = nullptr;
+    sage_b200_scorer_params params{};
+    ScorerView sv{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::mutex mu;
+    // device
+    DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_scratch, d_dbgk, d_dbgm;
+    // pinned staging
+    PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
+    sage_b200_counters last{};
+    int wide_ctas = 0;
+};
+
+extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_scorer_params* p, sage_b200_scorer** out) {
+    if (!db || !p || !out) return fail(SAGE_B200_EINVAL, "scorer_create: null argument");
+    if (p->report_psms == 0) return fail(SAGE_B200_EINVAL, "report_psms must be >= 1");
+    if (p->report_psms > K_MAX / 2) return fail(SAGE_B200_ELIMIT, "report_psms %u > %d not supported", p->report_psms, K_MAX / 2);
+    if (p->precursor_tol.kind < 0 || p->precursor_tol.kind > 2 || p->fragment_tol.kind < 0 || p->fragment_tol.kind > 2) return fail(SAGE_B200_EINVAL, "bad tolerance kind");
+    if (p->score_type > 1) return fail(SAGE_B200_EINVAL, "bad score_type");
+    if (p->annotate_matches) return fail(SAGE_B200_ELIMIT, "annotate_matches (Fragments output) is not implemented in this round");
+    CUDA_TRY(cudaSetDevice(db->device));
+    sage_b200_scorer* s = new sage_b200_scorer();
+    s->db = db;
+    s->params = *p;
+    ScorerView& v = s->sv;
+    v.precursor_tol = {p->precursor_tol.kind, p->precursor_tol.lo, p->precursor_tol.hi};
+    v.fragment_tol = {p->fragment_tol.kind, p->fragment_tol.lo, p->fragment_tol.hi};
+    v.min_matched_peaks = p->min_matched_peaks;
+    v.min_iso = p->min_isotope_err; v.max_iso = p->max_isotope_err;
+    v.min_charge = p->min_precursor_charge; v.max_charge = p->max_precursor_charge;
+    v.override_charge = p->override_precursor_charge; v.max_fragment_charge_opt = p->max_fragment_charge;
+    v.chimera = p->chimera; v.wide_window = p->wide_window; v.annotate = p->annotate_matches; v.score_type = p->score_type;
+    v.report_psms = p->report_psms;
+    v.kparam = std::max<uint32_t>(50, 2 * p->report_psms);  // trim_hits (scoring.rs:323-326): k = min(len, max(50, 2*report_psms))
+    v.n_iso = (v.min_iso != v.max_iso) ? (uint32_t)std::max(0, v.max_iso - v.min_iso + 1) : 1;
+    v.n_ch_max = v.max_charge >= v.min_charge ? v.max_charge - v.min_charge + 1 : 0;
+    if (v.n_ch_max < 1) v.n_ch_max = 1;  // known-charge spectra still need one slot
+    if (v.n_iso > 32 || v.n_ch_max > 16) { delete s; return fail(SAGE_B200_ELIMIT, "isotope range > 32 or charge range > 16 not supported"); }
+    v.qmax = std::max<uint32_t>(1, v.n_iso) * v.n_ch_max;
+    v.lcap = std::max<uint32_t>(std::max<uint32_t>(v.n_iso, v.n_ch_max), 1) * v.kparam;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
+    s->wide_ctas = db->sm_count * 2;
+    *out = s;
+    return 0;
+}
+
+extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
+    if (!s) return;
+    cudaSetDevice(s->db->device);
+    for (DevBuf* b : {&s->d_small, &s->d_masses, &s->d_intens, &s->d_queries, &s->d_hits, &s->d_keys, &s->d_features, &s->d_counts, &s->d_counters, &s->d_scratch, &s->d_dbgk, &s->d_dbgm}) b->release();
+    for (PinBuf* b : {&s->h_small, &s->h_masses, &s->h_intens, &s->h_features, &s->h_counts, &s->h_counters}) b->release();
+    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// One chunk [c0, c1) of the batch through the device pipeline. dbg != 0: also dump initial_hits.
+static int run_chunk(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64_t c0, uint64_t c1, sage_b200_feature* features, uint32_t* counts, bool dbg) {
+    const sage_b200_db* db = S->db;
+    const ScorerView& sv = S->sv;
+    cudaStream_t st = S->stream;
+    const uint32_t n = (uint32_t)(c1 - c0);
+    const uint64_t pk0 = sp->peak_offsets[c0], pk1 = sp->peak_offsets[c1];
+    const uint64_t npk = pk1 - pk0;
+    if (npk > 0xFFFFFFF0ull) return fail(SAGE_B200_ELIMIT, "chunk has too many peaks");
+
+    // ---- small per-spectrum arrays -> one pinned blob -> one H2D
+    const size_t o_off = 0;
+    const size_t o_pmz = align_up(o_off + 4 * (size_t)(n + 1), 16);
+    const size_t o_tic = align_up(o_pmz + 4 * (size_t)n, 16);
+    const size_t o_ilo = align_up(o_tic + 4 * (size_t)n, 16);
+    const size_t o_ihi = align_up(o_ilo + 4 * (size_t)n, 16);
+    const size_t o_rt = align_up(o_ihi + 4 * (size_t)n, 16);
+    const size_t o_ims = align_up(o_rt + 4 * (size_t)n, 16);
+    const size_t o_chg = align_up(o_ims + 4 * (size_t)n, 16);
+    const size_t small_bytes = align_up(o_chg + n, 16);
+    int rc;
+    if ((rc = S->h_small.reserve(small_bytes))) return rc;
+    if ((rc = S->d_small.reserve(small_bytes))) return rc;
+    unsigned char* hs = (unsigned char*)S->h_small.p;
+    uint32_t* h_off = (uint32_t*)(hs + o_off);
+    uint32_t pmax = 2;
+    for (uint32_t i = 0; i <= n; i++) h_off[i] = (uint32_t)(sp->peak_offsets[c0 + i] - pk0);
+    for (uint32_t i = 0; i < n; i++) {
+        if (sp->peak_offsets[c0 + i + 1] < sp->peak_offsets[c0 + i]) return fail(SAGE_B200_EINVAL, "peak_offsets not monotone at spectrum %llu", (unsigned long long)(c0 + i));
+        pmax = std::max(pmax, h_off[i + 1] - h_off[i]);
+        if (sp->level && sp->level[c0 + i] != 2)
+            return fail(SAGE_B200_ENOTMS2, "internal bug, trying to score a non-MS2 scan! (spectrum %llu has level %u)", (unsigned long long)(c0 + i), sp->level[c0 + i]);
+        if (std::isnan(sp->precursor_mz[c0 + i])) return fail(SAGE_B200_ENOPRECURSOR, "missing MS1 precursor for spectrum %llu", (unsigned long long)(c0 + i));
+    }
+    pmax = (pmax + 1) & ~1u;
+    memcpy(hs + o_pmz, sp->precursor_mz + c0, 4 * (size_t)n);
+    memcpy(hs + o_tic, sp->total_ion_current + c0, 4 * (size_t)n);
+    float* h_ilo = (float*)(hs + o_ilo);
+    float* h_ihi = (float*)(hs + o_ihi);
+    float* h_rt = (float*)(hs + o_rt);
+    float* h_ims = (float*)(hs + o_ims);
+    for (uint32_t i = 0; i < n; i++) {
+        h_ilo[i] = sp->isolation_lo ? sp->isolation_lo[c0 + i] : NAN;
+        h_ihi[i] = sp->isolation_hi ? sp->isolation_hi[c0 + i] : NAN;
+        h_rt[i] = sp->scan_start_time ? sp->scan_start_time[c0 + i] : 0.0f;
+        h_ims[i] = sp->inverse_ion_mobility ? sp->inverse_ion_mobility[c0 + i] : NAN;
+    }
+    memcpy(hs + o_chg, sp->precursor_charge + c0, n);
+
+    const size_t smem = (size_t)pmax * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + pmax + 16;
+    if (smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", pmax);
+
+    if ((rc = S->d_masses.reserve(4 * npk + 16))) return rc;
+    if ((rc = S->d_intens.reserve(4 * npk + 16))) return rc;
+    const size_t nitems = (size_t)n * sv.qmax;
+    if (nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
+    if ((rc = S->d_queries.reserve(nitems * sizeof(QueryDesc)))) return rc;
+    if ((rc = S->d_hits.reserve(nitems * sizeof(QueryHits)))) return rc;
+    if ((rc = S->d_keys.reserve(nitems * sv.kparam * 8))) return rc;
+    if ((rc = S->d_features.reserve((size_t)n * sv.report_psms * sizeof(FeatureOut)))) return rc;
+    if ((rc = S->d_counts.reserve(4 * (size_t)n))) return rc;
+    if ((rc = S->d_counters.reserve(8 * C_COUNT))) return rc;
+    if ((rc = S->h_counters.reserve(8 * C_COUNT))) return rc;
+    if (dbg) {
+        if ((rc = S->d_dbgk.reserve((size_t)n * sv.kparam * 8))) return rc;
+        if ((rc = S->d_dbgm.reserve((size_t)n * 16))) return rc;
+    }
+
+    CUDA_TRY(cudaEventRecord(S->ev[0], st));
+    // ---- H2D
+    CUDA_TRY(cudaMemcpyAsync(S->d_small.p, hs, small_bytes, cudaMemcpyHostToDevice, st));
+    const float* src_m = sp->masses + pk0;
+    const float* src_i = sp->intensities + pk0;
+    if (npk) {
+        if (!is_pinned(src_m)) {
+            if ((rc = S->h_masses.reserve(4 * npk))) return rc;
+            memcpy(S->h_masses.p, src_m, 4 * npk);
+            src_m = (const float*)S->h_masses.p;
+        }
+        if (!is_pinned(src_i)) {
+            if ((rc = S->h_intens.reserve(4 * npk))) return rc;
+            memcpy(S->h_intens.p, src_i, 4 * npk);
+            src_i = (const float*)S->h_intens.p;
+        }
+        CUDA_TRY(cudaMemcpyAsync(S->d_masses.p, src_m, 4 * npk, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(S->d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemsetAsync(S->d_counters.p, 0, 8 * C_COUNT, st));
+    CUDA_TRY(cudaEventRecord(S->ev[1], st));
+
+    BatchView bv{};
+    unsigned char* ds = (unsigned char*)S->d_small.p;
+    bv.n = n;
+    bv.peak_off = (const uint32_t*)(ds + o_off);
+    bv.masses = S->d_masses.as<float>();
+    bv.intens = S->d_intens.as<float>();
+    bv.prec_mz = (const float*)(ds + o_pmz);
+    bv.prec_charge = (const uint8_t*)(ds + o_chg);
+    bv.iso_lo = (const float*)(ds + o_ilo);
+    bv.iso_hi = (const float*)(ds + o_ihi);
+    bv.tic = (const float*)(ds + o_tic);
+    bv.rt = (const float*)(ds + o_rt);
+    bv.ims = (const float*)(ds + o_ims);
+    bv.queries = S->d_queries.as<QueryDesc>();
+    bv.hits = S->d_hits.as<QueryHits>();
+    bv.hit_keys = S->d_keys.as<uint64_t>();
+    bv.counters = S->d_counters.as<unsigned long long>();
+
+    // ---- setup: resolve precursor windows
+    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, sv, bv);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(S->ev[2], st));
+    unsigned long long* hc = (unsigned long long*)S->h_counters.p;
+    CUDA_TRY(cudaMemcpyAsync(hc, S->d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint64_t n_queries = hc[C_QUERIES], n_wide = hc[C_WIDE], max_pot = hc[C_MAXPOT];
+    uint64_t launches = 1;
+
+    // ---- preliminary scoring
+    if (n_queries > n_wide) {
+        k_prelim_narrow<<<(unsigned)nitems, PRELIM_THREADS, 0, st>>>(db->v, sv, bv);
+        CUDA_TRY(cudaGetLastError());
+        launches++;
+    }
+    if (n_wide) {
+        const uint64_t stride_words = align_up((max_pot + 2) / 2 + 1, 64);
+        const int ctas = (int)std::min<uint64_t>((uint64_t)S->wide_ctas, n_wide);
+        if ((rc = S->d_scratch.reserve(stride_words * 4 * (uint64_t)S->wide_ctas))) return rc;
+        k_prelim_wide<<<ctas, PRELIM_THREADS, 0, st>>>(db->v, sv, bv, S->d_scratch.as<uint32_t>(), stride_words, (uint32_t)nitems);
+        CUDA_TRY(cudaGetLastError());
+        launches++;
+    }
+    CUDA_TRY(cudaEventRecord(S->ev[3], st));
+
+    // ---- candidate scoring + feature assembly
+    CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_score<<<n, SCORE_THREADS, smem, st>>>(db->v, sv, bv, S->d_features.as<FeatureOut>(), S->d_counts.as<uint32_t>(), pmax,
+                                           dbg ? S->d_dbgk.as<uint64_t>() : nullptr, dbg ? S->d_dbgm.as<uint32_t>() : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    launches++;
+    CUDA_TRY(cudaEventRecord(S->ev[4], st));
+
+    // ---- D2H
+    const size_t fbytes = (size_t)n * sv.report_psms * sizeof(sage_b200_feature);
+    sage_b200_feature* fdst = features + c0 * sv.report_psms;
+    uint32_t* cdst = counts + c0;
+    const bool f_pinned = is_pinned(fdst), c_pinned = is_pinned(cdst);
+    if (!f_pinned && (rc = S->h_features.reserve(fbytes))) return rc;
+    if (!c_pinned && (rc = S->h_counts.reserve(4 * (size_t)n))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(f_pinned ? (void*)fdst : S->h_features.p, S->d_features.p, fbytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c_pinned ? (void*)cdst : S->h_counts.p, S->d_counts.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hc, S->d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(S->ev[5], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!f_pinned) memcpy(fdst, S->h_features.p, fbytes);
+    if (!c_pinned) memcpy(cdst, S->h_counts.p, 4 * (size_t)n);
+
+    // ---- counters
+    sage_b200_counters& L = S->last;
+    float ms;
+    cudaEventElapsedTime(&ms, S->ev[0], S->ev[1]); L.ms_h2d += ms;
+    cudaEventElapsedTime(&ms, S->ev[1], S->ev[2]); L.ms_setup += ms;
+    cudaEventElapsedTime(&ms, S->ev[2], S->ev[3]); L.ms_prelim += ms;
+    cudaEventElapsedTime(&ms, S->ev[3], S->ev[4]); L.ms_score += ms;
+    cudaEventElapsedTime(&ms, S->ev[4], S->ev[5]); L.ms_d2h += ms;
+    cudaEventElapsedTime(&ms, S->ev[0], S->ev[5]); L.ms_total += ms;
+    L.spectra += n; L.peaks += npk; L.queries += hc[C_QUERIES]; L.tasks += hc[C_TASKS]; L.pages += hc[C_PAGES]; L.entries_scanned += hc[C_ENTRIES];
+    L.matched_fragments += hc[C_MATCHED]; L.candidates_scored += hc[C_CANDS]; L.peptide_record_floats += hc[C_PEPFLOATS]; L.psms += hc[C_PSMS];
+    L.wide_queries += hc[C_WIDE];
+    L.h2d_bytes += small_bytes + 8 * npk;
+    L.d2h_bytes += fbytes + 4 * (size_t)n + 2 * 8 * C_COUNT;
+    L.kernel_launches += launches;
+    return 0;
+}
+
+static void finish_counters(sage_b200_scorer* S) {
+    // B = 8*P + sum_q[8*ceil(log2 N_pep)] + sum_tasks[8*ceil(log2 N_bucket)] + sum_pages[8*ceil(log2 bucket_size) + 8*entries]
+    //                    + sum_candidates 4*(2L+2) + 64*n_psm
+    sage_b200_counters& L = S->last;
+    const DbView& v = S->db->v;
+    const uint64_t lp = ceil_log2_u64(v.n_pep), lb = ceil_log2_u64(v.n_bucket), ls = ceil_log2_u64(v.bucket_size);
+    L.prelim_bytes = 4 * L.peaks + 8 * lb * L.tasks + 8 * ls * L.pages + 8 * L.entries_scanned;
+    L.algorithmic_bytes = 8 * L.peaks + 8 * lp * L.queries + 8 * lb * L.tasks + 8 * ls * L.pages + 8 * L.entries_scanned + 4 * L.peptide_record_floats + 64 * L.psms;
+}
+
+static int check_spectra(const sage_b200_spectra* sp) {
+    if (!sp) return fail(SAGE_B200_EINVAL, "spectra: null");
+    if (sp->n && (!sp->peak_offsets || !sp->precursor_mz || !sp->precursor_charge || !sp->total_ion_current)) return fail(SAGE_B200_EINVAL, "spectra: null array");
+    if (sp->n && sp->peak_offsets[sp->n] > sp->peak_offsets[0] && (!sp->masses || !sp->intensities)) return fail(SAGE_B200_EINVAL, "spectra: null peak arrays");
+    return 0;
+}
+
+extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectra* sp, sage_b200_feature* features, uint32_t* counts,
+                                     sage_b200_fragment* fragments, uint64_t fragment_capacity, uint64_t* fragments_used) {
+    (void)fragments; (void)fragment_capacity;
+    if (!S) return fail(SAGE_B200_EINVAL, "score_batch: null scorer");
+    int rc = check_spectra(sp);
+    if (rc) return rc;
+    if (sp->n && (!features || !counts)) return fail(SAGE_B200_EINVAL, "score_batch: null output");
+    std::lock_guard<std::mutex> lock(S->mu);
+    CUDA_TRY(cudaSetDevice(S->db->device));
+    S->last = sage_b200_counters{};
+    if (fragments_used) *fragments_used = 0;
+    // chunks bounded by spectra count and peak count so device staging stays modest
+    const uint64_t max_spec = 1u << 17, max_peaks = 1ull << 25;
+    uint64_t c0 = 0;
+    while (c0 < sp->n) {
+        uint64_t c1 = std::min<uint64_t>(sp->n, c0 + max_spec);
+        while (c1 > c0 + 1 && sp->peak_offsets[c1] - sp->peak_offsets[c0] > max_peaks) c1 = c0 + (c1 - c0) / 2;
+        if ((rc = run_chunk(S, sp, c0, c1, features, counts, false))) return rc;
+        c0 = c1;
+    }
+    finish_counters(S);
+    return 0;
+}
+
+extern "C" int64_t sage_b200_initial_hits(sage_b200_scorer* S, const sage_b200_spectra* sp, uint16_t* matched, uint32_t* peptide, uint8_t* charge,
+                                          int8_t* isotope_error, uint64_t cap, uint64_t* matched_peaks, uint64_t* scored_candidates) {
+    if (!S) return fail(SAGE_B200_EINVAL, "initial_hits: null scorer");
+    int rc = check_spectra(sp);
+    if (rc) return rc;
+    if (sp->n != 1) return fail(SAGE_B200_EINVAL, "initial_hits takes exactly one spectrum");
+    std::lock_guard<std::mutex> lock(S->mu);
+    if (cudaSetDevice(S->db->device) != cudaSuccess) return fail(SAGE_B200_ECUDA, "cudaSetDevice failed");
+    S->last = sage_b200_counters{};
+    std::vector<sage_b200_feature> f(S->sv.report_psms);
+    uint32_t cnt = 0;
+    if ((rc = run_chunk(S, sp, 0, 1, f.data(), &cnt, true))) return rc;
+    std::vector<uint64_t> keys(S->sv.kparam);
+    uint32_t meta[4] = {0, 0, 0, 0};
+    if (cudaMemcpy(keys.data(), S->d_dbgk.p, 8 * (size_t)S->sv.kparam, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(meta, S->d_dbgm.p, 16, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(SAGE_B200_ECUDA, "initial_hits: readback failed");
+    const uint32_t nk = meta[0];
+    for (uint32_t i = 0; i < nk && i < cap; i++) {
+        const uint64_t k = keys[i];
+        if (matched) matched[i] = (uint16_t)(k >> 48);
+        if (peptide) peptide[i] = (uint32_t)(k >> 16);
+        if (charge) charge[i] = (uint8_t)(k >> 8);
+        if (isotope_error) isotope_error[i] = (int8_t)((int)(k & 0xFF) - 128);
+    }
+    if (matched_peaks) *matched_peaks = meta[1];
+    if (scored_candidates) *scored_candidates = meta[2];
+    return (int64_t)nk;
+}
+
+extern "C" int sage_b200_counters_get(const sage_b200_scorer* S, sage_b200_counters* out) {
+    if (!S || !out) return fail(SAGE_B200_EINVAL, "counters_get: null argument");
+    *out = S->last;
+    return 0;
+}
+
+extern "C" void* sage_b200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable) != cudaSuccess) {
+        fail(SAGE_B200_ECUDA, "cudaHostAlloc(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void sage_b200_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" size_t sage_b200_last_error(char* buf, size_t cap) {
+    if (buf && cap) {
+        snprintf(buf, cap, "%s", g_last_error.c_str());
+    }
+    return g_last_error.size();
+}

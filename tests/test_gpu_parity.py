@@ -1,0 +1,188 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import sage_b200
+from sage_b200 import IndexedDatabase, Precursor, ProcessedSpectrum, Scorer, SpectraBatch, Tolerance, synth
+from oracle import oracle as O
+
+from helpers import assert_features_equal, oracle_cfg, oracle_db_from_peptides, peptides_from_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small():
+    pep = synth.make_peptides(20000, seed=11, static_c=True)
+    odb = oracle_db_from_peptides(pep)
+    gdb = IndexedDatabase.build_from_peptides(pep)
+    spectra = synth.make_spectra(pep, 1500, seed=12)
+    return pep, odb, gdb, spectra
+
+
+def run_both(odb, gdb, spectra, **kw):
+    sc = Scorer(gdb, **kw)
+    gf, gc = sc.score_batch(spectra)
+    of, oc, _, octr = odb.score_batch(oracle_cfg(**kw), spectra.as_dict(), counters=True)
+    n = assert_features_equal(gf, gc, of, oc, kw.get("report_psms", 1), what=str({k: v for k, v in kw.items() if "tol" not in k}))
+    return sc, n, octr
+
+
+def test_index_build_matches_oracle(small):
+    pep, odb, gdb, _ = small
+    fp, fm, bm = gdb.export_index()
+    e = odb.export()
+    assert np.array_equal(bm.view(np.uint32), e["bucket_min"].view(np.uint32))
+    assert np.array_equal(fp, e["frag_pep"])
+    assert np.array_equal(fm.view(np.uint32), e["frag_mz"].view(np.uint32))
+
+
+def test_reference_layout_upload_roundtrip(small):
+    pep, odb, _, spectra = small
+    e = odb.export()
+    gdb2 = IndexedDatabase.from_reference_layout(pep, e["frag_pep"], e["frag_mz"], e["bucket_min"], e["bucket_size"])
+    fp, fm, bm = gdb2.export_index()
+    assert np.array_equal(fp, e["frag_pep"]) and np.array_equal(fm.view(np.uint32), e["frag_mz"].view(np.uint32))
+    run_both(odb, gdb2, spectra.slice(0, 300), precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20))
+
+
+def test_config1_known_answer(config1):
+    # crates/sage-cli/tests/integration.rs: psm.len()==1, matched_peaks==21, through the C ABI
+    odb = O.OracleDB.from_fasta(config1["fasta"])
+    pep = peptides_from_oracle(odb)
+    gdb = IndexedDatabase.build_from_peptides(pep)
+    masses, intens, tic = O.process_ms2(config1["mz"], config1["intensity"], config1["precursor_charge"], 100, True, 0.0)
+    spec = ProcessedSpectrum(level=2, id=config1["spectrum_id"], scan_start_time=config1["scan_start_time_min"],
+                             precursors=[Precursor(mz=config1["precursor_mz"], charge=config1["precursor_charge"],
+                                                   isolation_window=Tolerance.da(*config1["isolation_window_da"]))],
+                             masses=masses, intensities=intens, total_ion_current=float(tic))
+    scorer = Scorer(gdb, precursor_tol=Tolerance.ppm(-50.0, 50.0), fragment_tol=Tolerance.ppm(-10.0, 10.0), min_matched_peaks=4, min_isotope_err=-1,
+                    max_isotope_err=3, min_precursor_charge=2, max_precursor_charge=4, override_precursor_charge=False, max_fragment_charge=1,
+                    chimera=False, report_psms=1, wide_window=False, annotate_matches=False, score_type=0)
+    psm = scorer.score(spec)
+    assert len(psm) == 1
+    assert psm[0]["matched_peaks"] == 21
+    assert pep.sequence(int(psm[0]["peptide_idx"])) == "LQSRPAAPPAPGPGQLTLR"
+    assert abs(psm[0]["hyperscore"] - 69.90865222) < 1e-6
+    assert psm[0]["rt"] == np.float32(config1["scan_start_time_min"])
+
+
+def test_narrow_search(small):
+    pep, odb, gdb, spectra = small
+    sc, n, octr = run_both(odb, gdb, spectra, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20))
+    assert n > 1000
+    c = sc.counters()
+    for k in ("queries", "pages", "entries_scanned", "candidates_scored", "psms"):
+        assert c[k] == octr[k], (k, c[k], octr[k])
+    assert c["peptide_record_floats"] == octr["peptide_record_floats"]
+
+
+def test_narrow_report5_fragcharge1(small):
+    pep, odb, gdb, spectra = small
+    run_both(odb, gdb, spectra, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=5, max_fragment_charge=1,
+             min_matched_peaks=2)
+
+
+def test_isotope_errors(small):
+    pep, odb, gdb, spectra = small
+    run_both(odb, gdb, spectra, precursor_tol=Tolerance.ppm(-50, 50), fragment_tol=Tolerance.ppm(-10, 10), min_isotope_err=-1, max_isotope_err=3,
+             report_psms=2)
+
+
+def test_isotope_min_eq_max_nonzero(small):
+    # scoring.rs:391-415: min == max (even non-zero) searches isotope 0 only
+    pep, odb, gdb, spectra = small
+    run_both(odb, gdb, spectra.slice(0, 400), precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), min_isotope_err=1, max_isotope_err=1)
+
+
+def test_unknown_charge_and_override(small):
+    pep, odb, gdb, spectra = small
+    unk = SpectraBatch(**{**spectra.__dict__, "prec_charge": np.where(np.arange(len(spectra)) % 3 == 0, 0, spectra.prec_charge).astype(np.uint8)})
+    run_both(odb, gdb, unk, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=3)
+    run_both(odb, gdb, spectra.slice(0, 500), precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), override_precursor_charge=True,
+             min_precursor_charge=1, max_precursor_charge=4)
+
+
+def test_wide_window(small):
+    pep, odb, gdb, spectra = small
+    n = len(spectra)
+    iso_lo = np.where(np.arange(n) % 2 == 0, np.float32(-1.5), np.float32(np.nan)).astype(np.float32)
+    iso_hi = np.where(np.arange(n) % 2 == 0, np.float32(1.5), np.float32(np.nan)).astype(np.float32)
+    ww = SpectraBatch(**{**spectra.__dict__, "iso_lo": iso_lo, "iso_hi": iso_hi})
+    run_both(odb, gdb, ww.slice(0, 600), precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), wide_window=True, report_psms=2,
+             min_precursor_charge=2, max_precursor_charge=3)
+
+
+def test_open_search_wide_path(small):
+    pep, odb, gdb, spectra = small
+    sc, n, _ = run_both(odb, gdb, spectra.slice(0, 400), precursor_tol=Tolerance.da(-500, 500), fragment_tol=Tolerance.ppm(-20, 20), report_psms=2)
+    assert sc.counters()["wide_queries"] > 300  # exercised the streaming kernel
+    run_both(odb, gdb, spectra.slice(400, 600), precursor_tol=Tolerance.da(-500, 100), fragment_tol=Tolerance.ppm(-20, 20), min_isotope_err=-1,
+             max_isotope_err=1)
+
+
+def test_chimera(small):
+    pep, odb, gdb, _ = small
+    chim = synth.make_spectra(pep, 800, seed=13, chimeric=True)
+    run_both(odb, gdb, chim, precursor_tol=Tolerance.da(-1.5, 1.5), fragment_tol=Tolerance.ppm(-20, 20), chimera=True, report_psms=5)
+    run_both(odb, gdb, chim.slice(0, 200), precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), chimera=True, report_psms=2)
+
+
+def test_tolerance_kinds_and_openms_score(small):
+    pep, odb, gdb, spectra = small
+    run_both(odb, gdb, spectra.slice(0, 400), precursor_tol=Tolerance.pct(-0.01, 0.01), fragment_tol=Tolerance.da(-0.02, 0.02), score_type=1)
+
+
+def test_initial_hits_heap_order(small):
+    # white box: the preliminary list must come back in the reference's bounded_min_heapify order
+    pep, odb, gdb, spectra = small
+    kw = dict(precursor_tol=Tolerance.da(-30, 30), fragment_tol=Tolerance.ppm(-20, 20), min_isotope_err=-1, max_isotope_err=2)
+    sc = Scorer(gdb, **kw)
+    for i in (0, 7, 19, 123):
+        one = spectra.slice(i, i + 1)
+        g = sc.initial_hits(one)
+        o = odb.initial_hits(oracle_cfg(**kw), one.masses, one.intensities, float(one.prec_mz[0]), int(one.prec_charge[0]))
+        for k in ("matched", "peptide", "charge", "iso"):
+            assert np.array_equal(g[k], o[k]), (i, k)
+        assert g["matched_peaks"] == o["matched_peaks"] and g["scored_candidates"] == o["scored_candidates"]
+
+
+def test_edge_cases(small):
+    pep, odb, gdb, spectra = small
+    # ragged spectra: empty, 1 peak, precursor far outside the peptide mass range, duplicate masses
+    specs = [
+        ProcessedSpectrum(precursors=[Precursor(mz=500.0, charge=2)]),
+        ProcessedSpectrum(precursors=[Precursor(mz=800.0, charge=2)], masses=np.float32([500.0]), intensities=np.float32([10.0]), total_ion_current=10.0),
+        ProcessedSpectrum(precursors=[Precursor(mz=90000.0, charge=3)], masses=np.float32([100, 200, 300]), intensities=np.float32([1, 2, 3]), total_ion_current=6.0),
+        ProcessedSpectrum(precursors=[Precursor(mz=1.0, charge=1)], masses=np.float32([100, 200, 300]), intensities=np.float32([1, 2, 3]), total_ion_current=6.0),
+    ]
+    one = spectra.slice(3, 4)
+    m = np.repeat(one.masses, 2)
+    specs.append(ProcessedSpectrum(precursors=[Precursor(mz=float(one.prec_mz[0]), charge=int(one.prec_charge[0]))], masses=m,
+                                   intensities=np.repeat(one.intensities, 2), total_ion_current=float(one.tic[0]) * 2))
+    batch = SpectraBatch.from_spectra(specs)
+    run_both(odb, gdb, batch, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=2)
+    run_both(odb, gdb, batch, precursor_tol=Tolerance.da(-500, 500), fragment_tol=Tolerance.ppm(-20, 20), min_isotope_err=-1, max_isotope_err=1, chimera=True,
+             report_psms=2)
+
+
+def test_reference_panics_become_errors(small):
+    pep, odb, gdb, spectra = small
+    sc = Scorer(gdb, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20))
+    with pytest.raises(sage_b200.SageB200Error) as e:
+        sc.score(ProcessedSpectrum(level=1, precursors=[Precursor(mz=500.0, charge=2)]))
+    assert e.value.code == -3 and "non-MS2" in e.value.message
+    with pytest.raises(sage_b200.SageB200Error) as e:
+        sc.score(ProcessedSpectrum(level=2, precursors=[]))
+    assert e.value.code == -4 and "missing MS1 precursor" in e.value.message
+
+
+def test_small_bucket_sizes():
+    # bucket sizes down to 1 (the reference's quickcheck range) through both index paths
+    pep = synth.make_peptides(3000, seed=21)
+    spectra = synth.make_spectra(pep, 200, seed=22)
+    for bs in (1, 2, 64, 1024):
+        odb = oracle_db_from_peptides(pep, bucket_size=bs)
+        gdb = IndexedDatabase.build_from_peptides(pep, bucket_size=bs)
+        run_both(odb, gdb, spectra, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20))
+        run_both(odb, gdb, spectra.slice(0, 50), precursor_tol=Tolerance.da(-2000, 2000), fragment_tol=Tolerance.da(-0.5, 0.5))
