@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — spectra/sec of the fragment-index search-and-score hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port, all host threads), rank 0 only
+
+A "step" is one pass of the hot path over one batch of synthetic spectra (workload `cfg2` = BASELINE.json configs[1]:
+50k MS2 spectra x 200 peaks vs a ~2M-peptide tryptic index, +-20 ppm precursor / +-20 ppm fragment). Per GPU the work is
+fixed (weak scaling: every rank scores its own 50k spectra against a replicated index; no collective on the data path).
+
+  value      spectra/s with the spectra already resident in HBM: K x (k_setup_queries -> k_prelim_* -> k_score), timed with CUDA
+             events on the launching stream (sage_b200_batch_run), max over ranks.
+  e2e        spectra/s through the C-ABI call sage_b200_score_batch with pinned HOST buffers: H2D of the spectra and D2H of the
+             Feature rows inside the timed region.
+  roofline   dominant kernel (preliminary scoring): algorithmic bytes / CUDA-event duration vs measured HBM peak.
+  cpu_baseline  the CPU oracle (bit-faithful port of sage-core's path; OpenMP over spectra) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (n_spectra, n_peptides_target, scorer kwargs (tolerances as (kind, lo, hi)), spectra kwargs, cpu sample)
+    "cfg2": dict(desc="50k synthetic MS2 spectra (200 peaks) vs ~2M-peptide tryptic index, +-20 ppm precursor, +-20 ppm fragment", n_spectra=50_000,
+                 n_peptides=2_000_000, scorer=dict(precursor_tol=(0, -20.0, 20.0), fragment_tol=(0, -20.0, 20.0)), spectra={}, cpu_sample=50_000),
+    "cfg4": dict(desc="open search: 50k spectra, -500..+500 Da precursor window, ~2M-peptide tryptic index, +-20 ppm fragment", n_spectra=50_000,
+                 n_peptides=2_000_000, scorer=dict(precursor_tol=(2, -500.0, 500.0), fragment_tol=(0, -20.0, 20.0)), spectra={}, cpu_sample=512),
+    "cfg5": dict(desc="chimeric search (report_psms=5) on 100k co-fragmenting spectra, +-20 ppm / +-20 ppm", n_spectra=100_000, n_peptides=2_000_000,
+                 scorer=dict(precursor_tol=(0, -20.0, 20.0), fragment_tol=(0, -20.0, 20.0), chimera=True, report_psms=5), spectra=dict(chimeric=True),
+                 cpu_sample=20_000),
+    "small": dict(desc="smoke-size: 4k spectra vs 100k peptides, +-20 ppm / +-20 ppm", n_spectra=4_000, n_peptides=100_000,
+                  scorer=dict(precursor_tol=(0, -20.0, 20.0), fragment_tol=(0, -20.0, 20.0)), spectra={}, cpu_sample=4_000),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_or_make(name, wl, rank):
+    """Synthetic peptide table (shared by all ranks) and this rank's spectra; cached under /tmp to keep reruns short."""
+    from sage_b200 import Peptides, SpectraBatch, synth
+    cache = f"/tmp/sage_b200_pep_{wl['n_peptides']}.npz"
+    t0 = time.time()
+    pep = None
+    if os.path.exists(cache):
+        try:
+            z = np.load(cache)
+            pep = Peptides(**{k: z[k] for k in ("seq_off", "seq", "mods", "nterm", "mono", "decoy", "missed")})
+        except Exception:
+            pep = None
+    if pep is None:
+        pep = synth.make_peptides(wl["n_peptides"])
+        if rank == 0:
+            tmp = cache + f".{os.getpid()}.tmp.npz"
+            np.savez(tmp, **pep.__dict__)
+            os.replace(tmp, cache)
+    spectra = synth.make_spectra(pep, wl["n_spectra"], seed=0xB200 + 2 + 1000 * rank, **wl["spectra"])
+    log(f"[rank {rank}] data: {len(pep)} peptides, {len(spectra)} spectra in {time.time() - t0:.1f}s")
+    return pep, spectra
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.stop, self.th = gpu, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"], timeout=5).decode()
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+def oracle_throughput(pep, spectra, wl, steps, warmup, threads=0):
+    """Times the CPU oracle (OpenMP over spectra) on a bounded sample of the same workload. Returns list of spectra/s per step."""
+    from oracle import oracle as O
+    from helpers import oracle_db_from_peptides
+    t0 = time.time()
+    odb = oracle_db_from_peptides(pep)
+    log(f"oracle index built in {time.time() - t0:.1f}s ({odb.n_fragments} fragments)")
+    cfg = O.ScorerConfig(**wl["scorer"])
+    ns = min(wl["cpu_sample"], len(spectra))
+    sub = spectra.slice(0, ns).as_dict()
+    rates = []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        odb.score_batch(cfg, sub, nthreads=threads)
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            rates.append(ns / dt)
+    return rates, ns, O.num_threads() if threads == 0 else threads
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sage_b200", choices=["sage_b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = WORKLOADS[args.workload]
+    warmup = max(3, args.warmup)
+    config = {"workload": f"{args.workload}: {wl['desc']}", "spectra_per_gpu": wl["n_spectra"], "peaks_per_spectrum": 200,
+              "sharding": f"spectra sharded across {args.gpus} GPU(s), index replicated, no collective",
+              "l2": "per-step working set (index + ion tables ~0.7 GB, spectra 80 MB) exceeds the 126 MB L2; no flush needed"}
+
+    # ------------------------------------------------------------------ reference arm: CPU oracle port, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from sage_b200 import synth  # data generator only (numpy); no CUDA on this arm
+        pep, spectra = load_or_make(args.workload, wl, 0)
+        rates, ns, cores = oracle_throughput(pep, spectra, wl, args.steps, warmup)
+        v = float(np.mean(rates))
+        config["n_peptides"] = len(pep)
+        out = {"impl": "reference", "metric": "spectra/sec", "value": v, "unit": "spectra/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
+               "ms_per_step": 1000.0 * ns / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": config,
+               "cpu_baseline": {"value": v, "unit": "spectra/s", "cores": cores, "kind": "port",
+                                "sample": f"{ns} spectra of the workload per step, C++ port of sage-core's Scorer::score (oracle/), OpenMP dynamic over spectra"},
+               "e2e": {"value": v, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out), flush=True)
+        return
+
+    # ------------------------------------------------------------------ this repo's arm
+    import torch
+    import torch.distributed as dist
+    from sage_b200 import IndexedDatabase, Scorer, SpectraBatch, Tolerance, api
+
+    if api.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device — sage_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return float(x)
+
+    def sum_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+        return float(x)
+
+    pep, spectra = load_or_make(args.workload, wl, rank)
+    t0 = time.time()
+    gdb = IndexedDatabase.build_from_peptides(pep, device=local_rank)
+    build_s = time.time() - t0
+    config.update(n_peptides=len(pep), n_fragments=int(gdb.info["n_fragments"]), index_hbm_bytes=int(gdb.info["device_bytes"]), index_build_s=round(build_s, 2))
+    kw = dict(wl["scorer"])
+    kw["precursor_tol"], kw["fragment_tol"] = Tolerance(*kw["precursor_tol"]), Tolerance(*kw["fragment_tol"])
+    scorer = Scorer(gdb, **kw)
+    n = len(spectra)
+
+    # pinned host copies of the inputs/outputs (the e2e path DMA-copies straight from/to these)
+    def pin(a):
+        p = api.pinned_empty(a.shape, a.dtype)
+        p[...] = a
+        return p
+    hspec = SpectraBatch(peak_off=spectra.peak_off, masses=pin(spectra.masses), intensities=pin(spectra.intensities), prec_mz=spectra.prec_mz,
+                         prec_charge=spectra.prec_charge, iso_lo=spectra.iso_lo, iso_hi=spectra.iso_hi, tic=spectra.tic, level=spectra.level, rt=spectra.rt,
+                         ims=spectra.ims)
+    out = api.pinned_empty((n * scorer.report_psms,), api.FEATURE_DTYPE)
+    counts = api.pinned_empty((n,), np.uint32)
+
+    # ---- warm-up (both paths)
+    for _ in range(warmup):
+        scorer.score_batch(hspec, out, counts)
+    scorer.upload(hspec)
+    for _ in range(warmup):
+        scorer.run()
+
+    with ClockSampler(local_rank) as clocks:
+        # ---- timed: K steps with the spectra resident in HBM; CUDA events on the launching stream (inside the library)
+        barrier()
+        dev_ms, prelim_ms, score_ms, setup_ms = 0.0, 0.0, 0.0, 0.0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            scorer.run()
+            c = scorer.counters()
+            dev_ms += c["ms_total"]
+            prelim_ms += c["ms_prelim"]
+            score_ms += c["ms_score"]
+            setup_ms += c["ms_setup"]
+        barrier()
+        wall_resident = time.perf_counter() - t0
+        last = scorer.counters()
+        # ---- timed: K steps end to end through sage_b200_score_batch (pinned host in, pinned host out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            scorer.score_batch(hspec, out, counts)
+        barrier()
+        wall_e2e = time.perf_counter() - t0
+        e2e_c = scorer.counters()
+    dev_s = max_over_ranks(dev_ms / 1000.0)
+    wall_e2e = max_over_ranks(wall_e2e)
+    wall_resident = max_over_ranks(wall_resident)
+    total_spectra = sum_over_ranks(n) * args.steps
+    value = total_spectra / dev_s
+    e2e_value = total_spectra / wall_e2e
+    psms = int(counts.sum())
+
+    peak, peak_src = measured_hbm_peak()
+    prelim_launch_s = prelim_ms / 1000.0 / args.steps
+    achieved = last["prelim_bytes"] / prelim_launch_s / 1e9 if prelim_launch_s > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_prelim_wide" if last["wide_queries"] else "k_prelim_narrow", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": committed_traffic(args.workload), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(last["prelim_bytes"]), "launch_ms": prelim_launch_s * 1e3,
+                "note": "narrow windows are dependent-probe (latency) bound, not stream bound; see DESIGN.md"}
+    result = {"metric": "spectra/sec", "value": value, "unit": "spectra/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
+              "ms_per_step": dev_s * 1000.0 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+              "data": "synthetic", "config": config,
+              "e2e": {"value": e2e_value, "unit": "spectra/s", "h2d_bytes_per_step": int(e2e_c["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_c["d2h_bytes"]),
+                      "ms_per_step": wall_e2e * 1000.0 / args.steps},
+              "gpu_launches": int(last["kernel_launches"]) * args.steps * 2 * args.gpus,
+              "roofline": roofline, "clocks": clocks.summary(),
+              "phases_ms_per_step": {"setup": setup_ms / args.steps, "prelim": prelim_ms / args.steps, "score": score_ms / args.steps,
+                                     "resident_wall": wall_resident * 1000.0 / args.steps, "e2e_h2d": e2e_c["ms_h2d"], "e2e_d2h": e2e_c["ms_d2h"]},
+              "work_per_step": {k: int(last[k]) for k in ("queries", "tasks", "pages", "entries_scanned", "matched_fragments", "candidates_scored", "psms",
+                                                          "algorithmic_bytes")},
+              "psms_per_step_rank0": psms}
+
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        rates, ns, cores = oracle_throughput(pep, spectra, wl, steps=2, warmup=1)
+        result["cpu_baseline"] = {"value": float(max(rates)), "unit": "spectra/s", "cores": cores, "kind": "port",
+                                  "sample": f"{ns} spectra of the same workload, best of 2 after 1 warm-up; C++ port of sage-core's Scorer::score, OpenMP over spectra"}
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -158,6 +158,13 @@ void sage_b200_scorer_destroy(sage_b200_scorer* scorer);
 int sage_b200_score_batch(sage_b200_scorer* scorer, const sage_b200_spectra* spectra, sage_b200_feature* features, uint32_t* counts,
                           sage_b200_fragment* fragments, uint64_t fragment_capacity, uint64_t* fragments_used);
 
+/* The same call split in phases for device-resident reuse (one batch of <= 131072 spectra / 2^25 peaks):
+ * upload makes the spectra resident in HBM, run launches the kernels (results stay on the device; may be repeated),
+ * download copies the Feature rows back. score_batch == upload + run + download per chunk. */
+int sage_b200_batch_upload(sage_b200_scorer* scorer, const sage_b200_spectra* spectra);
+int sage_b200_batch_run(sage_b200_scorer* scorer);
+int sage_b200_batch_download(sage_b200_scorer* scorer, sage_b200_feature* features, uint32_t* counts);
+
 /* Scorer::initial_hits for one spectrum (scoring.rs:418-462): the preliminary list in the reference's heap order.
  * White-box hook used by the parity tests. Returns the list length (<= cap written) or a negative error. */
 int64_t sage_b200_initial_hits(sage_b200_scorer* scorer, const sage_b200_spectra* one_spectrum, uint16_t* matched, uint32_t* peptide,

@@ -83,7 +83,8 @@ assert FEATURE_DTYPE.itemsize == 128
 
 EXPORTED_SYMBOLS = [
     "sage_b200_device_count", "sage_b200_db_create", "sage_b200_db_build", "sage_b200_db_get_info", "sage_b200_db_export_index", "sage_b200_db_destroy",
-    "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_score_batch", "sage_b200_initial_hits", "sage_b200_counters_get",
+    "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_score_batch", "sage_b200_batch_upload", "sage_b200_batch_run",
+    "sage_b200_batch_download", "sage_b200_initial_hits", "sage_b200_counters_get",
     "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
 ]
 
@@ -411,6 +412,25 @@ class Scorer:
         cs = batch._c(keep)
         used = C.c_uint64(0)
         _check(load_library().sage_b200_score_batch(self._h, C.byref(cs), _ptr(out), _ptr(counts), None, C.c_uint64(0), C.byref(used)))
+        return out, counts
+
+    # device-resident phases of score_batch (one chunk): upload once, run many times, download
+    def upload(self, batch: SpectraBatch):
+        keep: list = []
+        cs = batch._c(keep)
+        self._resident_n = len(batch)
+        _check(load_library().sage_b200_batch_upload(self._h, C.byref(cs)))
+
+    def run(self):
+        _check(load_library().sage_b200_batch_run(self._h))
+
+    def download(self, out: np.ndarray | None = None, counts: np.ndarray | None = None):
+        n = self._resident_n
+        if out is None:
+            out = np.zeros(n * self.report_psms, FEATURE_DTYPE)
+        if counts is None:
+            counts = np.zeros(n, np.uint32)
+        _check(load_library().sage_b200_batch_download(self._h, _ptr(out), _ptr(counts)))
         return out, counts
 
     def score(self, spectrum: ProcessedSpectrum):

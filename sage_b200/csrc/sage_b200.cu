@@ -356,6 +356,14 @@ extern "C" int sage_b200_db_export_index(const sage_b200_db* db, uint32_t* fragm
 }
 
 // ------------------------------------------------------------------------------------------------ scorer
+struct ChunkState {
+    bool loaded = false;
+    uint32_t n = 0, pmax = 2;
+    uint64_t npk = 0;
+    size_t nitems = 0, smem = 0, small_bytes = 0;
+    size_t o_off = 0, o_pmz = 0, o_tic = 0, o_ilo = 0, o_ihi = 0, o_rt = 0, o_ims = 0, o_chg = 0;
+};
+
 struct sage_b200_scorer {
     const sage_b200_db* db = nullptr;
     sage_b200_scorer_params params{};
@@ -369,6 +377,7 @@ struct sage_b200_scorer {
     PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
     sage_b200_counters last{};
     int wide_ctas = 0;
+    ChunkState chunk;
 };
 
 extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_scorer_params* p, sage_b200_scorer** out) {
@@ -417,31 +426,35 @@ extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// One chunk [c0, c1) of the batch through the device pipeline. dbg != 0: also dump initial_hits.
-static int run_chunk(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64_t c0, uint64_t c1, sage_b200_feature* features, uint32_t* counts, bool dbg) {
-    const sage_b200_db* db = S->db;
+// ---- one chunk of spectra through the device pipeline, in three phases:
+//   chunk_upload   pack + H2D (spectra become device-resident)
+//   chunk_run      k_setup_queries -> k_prelim_{narrow,wide} -> k_score (results stay on the device)
+//   chunk_download D2H of Feature rows + counts
+static int chunk_upload(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64_t c0, uint64_t c1) {
     const ScorerView& sv = S->sv;
     cudaStream_t st = S->stream;
+    ChunkState& C = S->chunk;
+    C.loaded = false;
     const uint32_t n = (uint32_t)(c1 - c0);
     const uint64_t pk0 = sp->peak_offsets[c0], pk1 = sp->peak_offsets[c1];
     const uint64_t npk = pk1 - pk0;
     if (npk > 0xFFFFFFF0ull) return fail(SAGE_B200_ELIMIT, "chunk has too many peaks");
-
-    // ---- small per-spectrum arrays -> one pinned blob -> one H2D
-    const size_t o_off = 0;
-    const size_t o_pmz = align_up(o_off + 4 * (size_t)(n + 1), 16);
-    const size_t o_tic = align_up(o_pmz + 4 * (size_t)n, 16);
-    const size_t o_ilo = align_up(o_tic + 4 * (size_t)n, 16);
-    const size_t o_ihi = align_up(o_ilo + 4 * (size_t)n, 16);
-    const size_t o_rt = align_up(o_ihi + 4 * (size_t)n, 16);
-    const size_t o_ims = align_up(o_rt + 4 * (size_t)n, 16);
-    const size_t o_chg = align_up(o_ims + 4 * (size_t)n, 16);
-    const size_t small_bytes = align_up(o_chg + n, 16);
+    C.n = n; C.npk = npk;
+    // small per-spectrum arrays -> one pinned blob -> one H2D
+    C.o_off = 0;
+    C.o_pmz = align_up(C.o_off + 4 * (size_t)(n + 1), 16);
+    C.o_tic = align_up(C.o_pmz + 4 * (size_t)n, 16);
+    C.o_ilo = align_up(C.o_tic + 4 * (size_t)n, 16);
+    C.o_ihi = align_up(C.o_ilo + 4 * (size_t)n, 16);
+    C.o_rt = align_up(C.o_ihi + 4 * (size_t)n, 16);
+    C.o_ims = align_up(C.o_rt + 4 * (size_t)n, 16);
+    C.o_chg = align_up(C.o_ims + 4 * (size_t)n, 16);
+    C.small_bytes = align_up(C.o_chg + n, 16);
     int rc;
-    if ((rc = S->h_small.reserve(small_bytes))) return rc;
-    if ((rc = S->d_small.reserve(small_bytes))) return rc;
+    if ((rc = S->h_small.reserve(C.small_bytes))) return rc;
+    if ((rc = S->d_small.reserve(C.small_bytes))) return rc;
     unsigned char* hs = (unsigned char*)S->h_small.p;
-    uint32_t* h_off = (uint32_t*)(hs + o_off);
+    uint32_t* h_off = (uint32_t*)(hs + C.o_off);
     uint32_t pmax = 2;
     for (uint32_t i = 0; i <= n; i++) h_off[i] = (uint32_t)(sp->peak_offsets[c0 + i] - pk0);
     for (uint32_t i = 0; i < n; i++) {
@@ -451,43 +464,36 @@ static int run_chunk(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64_t 
             return fail(SAGE_B200_ENOTMS2, "internal bug, trying to score a non-MS2 scan! (spectrum %llu has level %u)", (unsigned long long)(c0 + i), sp->level[c0 + i]);
         if (std::isnan(sp->precursor_mz[c0 + i])) return fail(SAGE_B200_ENOPRECURSOR, "missing MS1 precursor for spectrum %llu", (unsigned long long)(c0 + i));
     }
-    pmax = (pmax + 1) & ~1u;
-    memcpy(hs + o_pmz, sp->precursor_mz + c0, 4 * (size_t)n);
-    memcpy(hs + o_tic, sp->total_ion_current + c0, 4 * (size_t)n);
-    float* h_ilo = (float*)(hs + o_ilo);
-    float* h_ihi = (float*)(hs + o_ihi);
-    float* h_rt = (float*)(hs + o_rt);
-    float* h_ims = (float*)(hs + o_ims);
+    C.pmax = (pmax + 1) & ~1u;
+    memcpy(hs + C.o_pmz, sp->precursor_mz + c0, 4 * (size_t)n);
+    memcpy(hs + C.o_tic, sp->total_ion_current + c0, 4 * (size_t)n);
+    float* h_ilo = (float*)(hs + C.o_ilo);
+    float* h_ihi = (float*)(hs + C.o_ihi);
+    float* h_rt = (float*)(hs + C.o_rt);
+    float* h_ims = (float*)(hs + C.o_ims);
     for (uint32_t i = 0; i < n; i++) {
         h_ilo[i] = sp->isolation_lo ? sp->isolation_lo[c0 + i] : NAN;
         h_ihi[i] = sp->isolation_hi ? sp->isolation_hi[c0 + i] : NAN;
         h_rt[i] = sp->scan_start_time ? sp->scan_start_time[c0 + i] : 0.0f;
         h_ims[i] = sp->inverse_ion_mobility ? sp->inverse_ion_mobility[c0 + i] : NAN;
     }
-    memcpy(hs + o_chg, sp->precursor_charge + c0, n);
-
-    const size_t smem = (size_t)pmax * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + pmax + 16;
-    if (smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", pmax);
-
+    memcpy(hs + C.o_chg, sp->precursor_charge + c0, n);
+    C.smem = (size_t)C.pmax * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + C.pmax + 16;
+    if (C.smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", C.pmax);
+    C.nitems = (size_t)n * sv.qmax;
+    if (C.nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
     if ((rc = S->d_masses.reserve(4 * npk + 16))) return rc;
     if ((rc = S->d_intens.reserve(4 * npk + 16))) return rc;
-    const size_t nitems = (size_t)n * sv.qmax;
-    if (nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
-    if ((rc = S->d_queries.reserve(nitems * sizeof(QueryDesc)))) return rc;
-    if ((rc = S->d_hits.reserve(nitems * sizeof(QueryHits)))) return rc;
-    if ((rc = S->d_keys.reserve(nitems * sv.kparam * 8))) return rc;
+    if ((rc = S->d_queries.reserve(C.nitems * sizeof(QueryDesc)))) return rc;
+    if ((rc = S->d_hits.reserve(C.nitems * sizeof(QueryHits)))) return rc;
+    if ((rc = S->d_keys.reserve(C.nitems * sv.kparam * 8))) return rc;
     if ((rc = S->d_features.reserve((size_t)n * sv.report_psms * sizeof(FeatureOut)))) return rc;
     if ((rc = S->d_counts.reserve(4 * (size_t)n))) return rc;
     if ((rc = S->d_counters.reserve(8 * C_COUNT))) return rc;
     if ((rc = S->h_counters.reserve(8 * C_COUNT))) return rc;
-    if (dbg) {
-        if ((rc = S->d_dbgk.reserve((size_t)n * sv.kparam * 8))) return rc;
-        if ((rc = S->d_dbgm.reserve((size_t)n * 16))) return rc;
-    }
 
     CUDA_TRY(cudaEventRecord(S->ev[0], st));
-    // ---- H2D
-    CUDA_TRY(cudaMemcpyAsync(S->d_small.p, hs, small_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(S->d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, st));
     const float* src_m = sp->masses + pk0;
     const float* src_i = sp->intensities + pk0;
     if (npk) {
@@ -504,27 +510,49 @@ static int run_chunk(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64_t 
         CUDA_TRY(cudaMemcpyAsync(S->d_masses.p, src_m, 4 * npk, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(S->d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, st));
     }
-    CUDA_TRY(cudaMemsetAsync(S->d_counters.p, 0, 8 * C_COUNT, st));
     CUDA_TRY(cudaEventRecord(S->ev[1], st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // staging buffers are reused by the next chunk
+    float ms;
+    cudaEventElapsedTime(&ms, S->ev[0], S->ev[1]);
+    S->last.ms_h2d += ms;
+    S->last.ms_total += ms;
+    S->last.h2d_bytes += C.small_bytes + 8 * npk;
+    C.loaded = true;
+    return 0;
+}
 
+static int chunk_run(sage_b200_scorer* S, bool dbg) {
+    const sage_b200_db* db = S->db;
+    const ScorerView& sv = S->sv;
+    cudaStream_t st = S->stream;
+    ChunkState& C = S->chunk;
+    if (!C.loaded) return fail(SAGE_B200_EINVAL, "no spectra resident on the device (call batch_upload first)");
+    const uint32_t n = C.n;
+    int rc;
+    if (dbg) {
+        if ((rc = S->d_dbgk.reserve((size_t)n * sv.kparam * 8))) return rc;
+        if ((rc = S->d_dbgm.reserve((size_t)n * 16))) return rc;
+    }
     BatchView bv{};
     unsigned char* ds = (unsigned char*)S->d_small.p;
     bv.n = n;
-    bv.peak_off = (const uint32_t*)(ds + o_off);
+    bv.peak_off = (const uint32_t*)(ds + C.o_off);
     bv.masses = S->d_masses.as<float>();
     bv.intens = S->d_intens.as<float>();
-    bv.prec_mz = (const float*)(ds + o_pmz);
-    bv.prec_charge = (const uint8_t*)(ds + o_chg);
-    bv.iso_lo = (const float*)(ds + o_ilo);
-    bv.iso_hi = (const float*)(ds + o_ihi);
-    bv.tic = (const float*)(ds + o_tic);
-    bv.rt = (const float*)(ds + o_rt);
-    bv.ims = (const float*)(ds + o_ims);
+    bv.prec_mz = (const float*)(ds + C.o_pmz);
+    bv.prec_charge = (const uint8_t*)(ds + C.o_chg);
+    bv.iso_lo = (const float*)(ds + C.o_ilo);
+    bv.iso_hi = (const float*)(ds + C.o_ihi);
+    bv.tic = (const float*)(ds + C.o_tic);
+    bv.rt = (const float*)(ds + C.o_rt);
+    bv.ims = (const float*)(ds + C.o_ims);
     bv.queries = S->d_queries.as<QueryDesc>();
     bv.hits = S->d_hits.as<QueryHits>();
     bv.hit_keys = S->d_keys.as<uint64_t>();
     bv.counters = S->d_counters.as<unsigned long long>();
 
+    CUDA_TRY(cudaEventRecord(S->ev[1], st));
+    CUDA_TRY(cudaMemsetAsync(S->d_counters.p, 0, 8 * C_COUNT, st));
     // ---- setup: resolve precursor windows
     k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, sv, bv);
     CUDA_TRY(cudaGetLastError());
@@ -537,7 +565,7 @@ static int run_chunk(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64_t 
 
     // ---- preliminary scoring
     if (n_queries > n_wide) {
-        k_prelim_narrow<<<(unsigned)nitems, PRELIM_THREADS, 0, st>>>(db->v, sv, bv);
+        k_prelim_narrow<<<(unsigned)C.nitems, PRELIM_THREADS, 0, st>>>(db->v, sv, bv);
         CUDA_TRY(cudaGetLastError());
         launches++;
     }
@@ -545,51 +573,67 @@ static int run_chunk(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64_t 
         const uint64_t stride_words = align_up((max_pot + 2) / 2 + 1, 64);
         const int ctas = (int)std::min<uint64_t>((uint64_t)S->wide_ctas, n_wide);
         if ((rc = S->d_scratch.reserve(stride_words * 4 * (uint64_t)S->wide_ctas))) return rc;
-        k_prelim_wide<<<ctas, PRELIM_THREADS, 0, st>>>(db->v, sv, bv, S->d_scratch.as<uint32_t>(), stride_words, (uint32_t)nitems);
+        k_prelim_wide<<<ctas, PRELIM_THREADS, 0, st>>>(db->v, sv, bv, S->d_scratch.as<uint32_t>(), stride_words, (uint32_t)C.nitems);
         CUDA_TRY(cudaGetLastError());
         launches++;
     }
     CUDA_TRY(cudaEventRecord(S->ev[3], st));
 
     // ---- candidate scoring + feature assembly
-    CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_score<<<n, SCORE_THREADS, smem, st>>>(db->v, sv, bv, S->d_features.as<FeatureOut>(), S->d_counts.as<uint32_t>(), pmax,
-                                           dbg ? S->d_dbgk.as<uint64_t>() : nullptr, dbg ? S->d_dbgm.as<uint32_t>() : nullptr);
+    CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));
+    k_score<<<n, SCORE_THREADS, C.smem, st>>>(db->v, sv, bv, S->d_features.as<FeatureOut>(), S->d_counts.as<uint32_t>(), C.pmax,
+                                             dbg ? S->d_dbgk.as<uint64_t>() : nullptr, dbg ? S->d_dbgm.as<uint32_t>() : nullptr);
     CUDA_TRY(cudaGetLastError());
     launches++;
     CUDA_TRY(cudaEventRecord(S->ev[4], st));
+    CUDA_TRY(cudaMemcpyAsync(hc, S->d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
 
-    // ---- D2H
+    sage_b200_counters& L = S->last;
+    float ms;
+    cudaEventElapsedTime(&ms, S->ev[1], S->ev[2]); L.ms_setup += ms;
+    cudaEventElapsedTime(&ms, S->ev[2], S->ev[3]); L.ms_prelim += ms;
+    cudaEventElapsedTime(&ms, S->ev[3], S->ev[4]); L.ms_score += ms;
+    cudaEventElapsedTime(&ms, S->ev[1], S->ev[4]); L.ms_total += ms;
+    L.spectra += n; L.peaks += C.npk; L.queries += hc[C_QUERIES]; L.tasks += hc[C_TASKS]; L.pages += hc[C_PAGES]; L.entries_scanned += hc[C_ENTRIES];
+    L.matched_fragments += hc[C_MATCHED]; L.candidates_scored += hc[C_CANDS]; L.peptide_record_floats += hc[C_PEPFLOATS]; L.psms += hc[C_PSMS];
+    L.wide_queries += hc[C_WIDE];
+    L.d2h_bytes += 2 * 8 * C_COUNT;
+    L.kernel_launches += launches;
+    return 0;
+}
+
+static int chunk_download(sage_b200_scorer* S, sage_b200_feature* fdst, uint32_t* cdst) {
+    const ScorerView& sv = S->sv;
+    cudaStream_t st = S->stream;
+    ChunkState& C = S->chunk;
+    if (!C.loaded) return fail(SAGE_B200_EINVAL, "no results on the device");
+    const uint32_t n = C.n;
+    int rc;
     const size_t fbytes = (size_t)n * sv.report_psms * sizeof(sage_b200_feature);
-    sage_b200_feature* fdst = features + c0 * sv.report_psms;
-    uint32_t* cdst = counts + c0;
     const bool f_pinned = is_pinned(fdst), c_pinned = is_pinned(cdst);
     if (!f_pinned && (rc = S->h_features.reserve(fbytes))) return rc;
     if (!c_pinned && (rc = S->h_counts.reserve(4 * (size_t)n))) return rc;
+    CUDA_TRY(cudaEventRecord(S->ev[4], st));
     CUDA_TRY(cudaMemcpyAsync(f_pinned ? (void*)fdst : S->h_features.p, S->d_features.p, fbytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(c_pinned ? (void*)cdst : S->h_counts.p, S->d_counts.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(hc, S->d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(S->ev[5], st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (!f_pinned) memcpy(fdst, S->h_features.p, fbytes);
     if (!c_pinned) memcpy(cdst, S->h_counts.p, 4 * (size_t)n);
-
-    // ---- counters
-    sage_b200_counters& L = S->last;
     float ms;
-    cudaEventElapsedTime(&ms, S->ev[0], S->ev[1]); L.ms_h2d += ms;
-    cudaEventElapsedTime(&ms, S->ev[1], S->ev[2]); L.ms_setup += ms;
-    cudaEventElapsedTime(&ms, S->ev[2], S->ev[3]); L.ms_prelim += ms;
-    cudaEventElapsedTime(&ms, S->ev[3], S->ev[4]); L.ms_score += ms;
-    cudaEventElapsedTime(&ms, S->ev[4], S->ev[5]); L.ms_d2h += ms;
-    cudaEventElapsedTime(&ms, S->ev[0], S->ev[5]); L.ms_total += ms;
-    L.spectra += n; L.peaks += npk; L.queries += hc[C_QUERIES]; L.tasks += hc[C_TASKS]; L.pages += hc[C_PAGES]; L.entries_scanned += hc[C_ENTRIES];
-    L.matched_fragments += hc[C_MATCHED]; L.candidates_scored += hc[C_CANDS]; L.peptide_record_floats += hc[C_PEPFLOATS]; L.psms += hc[C_PSMS];
-    L.wide_queries += hc[C_WIDE];
-    L.h2d_bytes += small_bytes + 8 * npk;
-    L.d2h_bytes += fbytes + 4 * (size_t)n + 2 * 8 * C_COUNT;
-    L.kernel_launches += launches;
+    cudaEventElapsedTime(&ms, S->ev[4], S->ev[5]);
+    S->last.ms_d2h += ms;
+    S->last.ms_total += ms;
+    S->last.d2h_bytes += fbytes + 4 * (size_t)n;
     return 0;
+}
+
+static int run_chunk(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64_t c0, uint64_t c1, sage_b200_feature* features, uint32_t* counts, bool dbg) {
+    int rc;
+    if ((rc = chunk_upload(S, sp, c0, c1))) return rc;
+    if ((rc = chunk_run(S, dbg))) return rc;
+    return chunk_download(S, features + c0 * S->sv.report_psms, counts + c0);
 }
 
 static void finish_counters(sage_b200_scorer* S) {
@@ -631,6 +675,38 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
     }
     finish_counters(S);
     return 0;
+}
+
+// Device-resident variant of score_batch, split in phases (single chunk): upload once, run the kernels any number of
+// times (bench.py times this with the inputs already in HBM), download the Feature rows.
+extern "C" int sage_b200_batch_upload(sage_b200_scorer* S, const sage_b200_spectra* sp) {
+    if (!S) return fail(SAGE_B200_EINVAL, "batch_upload: null scorer");
+    int rc = check_spectra(sp);
+    if (rc) return rc;
+    if (sp->n == 0 || sp->n > (1u << 17) || sp->peak_offsets[sp->n] - sp->peak_offsets[0] > (1ull << 25))
+        return fail(SAGE_B200_ELIMIT, "batch_upload takes 1..131072 spectra and at most 2^25 peaks (use score_batch for larger batches)");
+    std::lock_guard<std::mutex> lock(S->mu);
+    CUDA_TRY(cudaSetDevice(S->db->device));
+    S->last = sage_b200_counters{};
+    return chunk_upload(S, sp, 0, sp->n);
+}
+extern "C" int sage_b200_batch_run(sage_b200_scorer* S) {
+    if (!S) return fail(SAGE_B200_EINVAL, "batch_run: null scorer");
+    std::lock_guard<std::mutex> lock(S->mu);
+    CUDA_TRY(cudaSetDevice(S->db->device));
+    const uint64_t h2d = S->last.h2d_bytes;
+    S->last = sage_b200_counters{};
+    S->last.h2d_bytes = h2d;
+    int rc = chunk_run(S, false);
+    if (rc) return rc;
+    finish_counters(S);
+    return 0;
+}
+extern "C" int sage_b200_batch_download(sage_b200_scorer* S, sage_b200_feature* features, uint32_t* counts) {
+    if (!S || !features || !counts) return fail(SAGE_B200_EINVAL, "batch_download: null argument");
+    std::lock_guard<std::mutex> lock(S->mu);
+    CUDA_TRY(cudaSetDevice(S->db->device));
+    return chunk_download(S, features, counts);
 }
 
 extern "C" int64_t sage_b200_initial_hits(sage_b200_scorer* S, const sage_b200_spectra* sp, uint16_t* matched, uint32_t* peptide, uint8_t* charge,
