@@ -126,7 +126,8 @@ typedef struct { int32_t kind, charge, ordinal; float intensity, mz_calculated, 
 /* Work counters of the last score_batch (SURVEY.md §8d algorithmic-bytes terms) + device timings (CUDA events, ms). */
 typedef struct {
     uint64_t spectra, peaks, queries, tasks /* (peak,fragment-charge) probes */, pages, entries_scanned, matched_fragments,
-        candidates_scored, peptide_record_floats, psms, wide_queries;
+        candidates_scored, peptide_record_floats, psms, wide_queries,
+        pep_queries /* narrow queries counted peptide-centrically (pages/entries_scanned are then not visited) */, pep_fallbacks;
     uint64_t algorithmic_bytes;    /* SURVEY.md §8d formula, whole batch */
     uint64_t prelim_bytes;         /* the part of it the preliminary-scoring kernel(s) move */
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied across PCIe for the batch */
@@ -151,6 +152,9 @@ void sage_b200_db_destroy(sage_b200_db* db);
 
 int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_scorer_params* params, sage_b200_scorer** out);
 void sage_b200_scorer_destroy(sage_b200_scorer* scorer);
+/* Tuning knobs that do not change results. "pep_cap": precursor windows with at most this many peptides are counted by streaming
+ * the candidates' ion tables instead of probing the fragment index (0 = always probe the index, the reference's loop order). */
+int sage_b200_scorer_set_option(sage_b200_scorer* scorer, const char* name, int64_t value);
 
 /* Scorer::score over a batch (runner.rs:311-325 `par_iter().flat_map(|s| scorer.score(s))`).
  * features: caller-allocated, n * report_psms entries; spectrum i's PSMs are features[i*report_psms .. +counts[i]).

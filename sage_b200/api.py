@@ -63,7 +63,7 @@ class CSpectra(C.Structure):
 
 
 COUNTER_U64 = ["spectra", "peaks", "queries", "tasks", "pages", "entries_scanned", "matched_fragments", "candidates_scored", "peptide_record_floats",
-               "psms", "wide_queries", "algorithmic_bytes", "prelim_bytes", "h2d_bytes", "d2h_bytes", "kernel_launches"]
+               "psms", "wide_queries", "pep_queries", "pep_fallbacks", "algorithmic_bytes", "prelim_bytes", "h2d_bytes", "d2h_bytes", "kernel_launches"]
 COUNTER_F32 = ["ms_total", "ms_h2d", "ms_setup", "ms_prelim", "ms_score", "ms_d2h"]
 
 
@@ -83,7 +83,7 @@ assert FEATURE_DTYPE.itemsize == 128
 
 EXPORTED_SYMBOLS = [
     "sage_b200_device_count", "sage_b200_db_create", "sage_b200_db_build", "sage_b200_db_get_info", "sage_b200_db_export_index", "sage_b200_db_destroy",
-    "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_score_batch", "sage_b200_batch_upload", "sage_b200_batch_run",
+    "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_scorer_set_option", "sage_b200_score_batch", "sage_b200_batch_upload", "sage_b200_batch_run",
     "sage_b200_batch_download", "sage_b200_initial_hits", "sage_b200_counters_get",
     "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
 ]
@@ -392,6 +392,9 @@ class Scorer:
         h = C.c_void_p()
         _check(load_library().sage_b200_scorer_create(db._h, C.byref(p), C.byref(h)))
         self._h = h
+
+    def set_option(self, name: str, value: int):
+        _check(load_library().sage_b200_scorer_set_option(self._h, name.encode(), C.c_int64(int(value))))
 
     def __del__(self):
         try:

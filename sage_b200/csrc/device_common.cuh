@@ -111,7 +111,7 @@ struct QueryDesc {
     uint8_t charge;      // precursor charge of this query
     int8_t iso;          // isotope error recorded in PreScore
     uint8_t nfc;         // fragment charges searched = max_fragment_charge - 1
-    uint8_t mode;        // 0 unused, 1 narrow (smem counts), 2 wide (global counts)
+    uint8_t mode;        // 0 unused, 1 narrow/index (smem counts), 2 wide (global counts), 3 narrow/peptide-centric
 };
 
 struct QueryHits {
@@ -122,7 +122,7 @@ struct QueryHits {
 };
 
 // Device counters (u64 slots)
-enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_COUNT };
+enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_PEPQ, C_PEPFALLBACK, C_COUNT };
 
 struct DbView {
     const uint2* frag;        // {peptide_index, fragment_mz bits}, reference bucket layout
@@ -134,6 +134,9 @@ struct DbView {
     const uint8_t* pep_flags; // bit0 decoy
     const uint8_t* pep_missed;
     uint32_t n_pep, n_bucket, bucket_size, n_kinds;
+    uint32_t min_ion_index;   // fragments in the index are ions with index > min_ion_index (database.rs:281-291)
+    uint32_t pep_centric_ok;  // index content verified == ions filtered by min_ion_index (peptide-centric counting allowed)
+    uint32_t nterm_mask;      // bit k set when ion kind k is an N-terminal series (a/b/c)
     uint64_t n_frag;
     uint8_t kinds[MAX_KINDS];
 };
@@ -150,6 +153,7 @@ struct ScorerView {
     uint32_t n_ch_max; // charges folded per spectrum (upper bound)
     uint32_t qmax;     // n_iso * n_ch_max query slots per spectrum
     uint32_t lcap;     // list capacity for merges
+    uint32_t pep_cap;  // precursor windows up to this many peptides use the peptide-centric kernel path (0 = never)
 };
 
 struct BatchView {

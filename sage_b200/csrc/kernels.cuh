@@ -25,7 +25,7 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b) {
     uint32_t c1 = fold ? sc.max_charge : known;
     QueryDesc* out = b.queries + (size_t)s * sc.qmax;
     uint32_t qi = 0;
-    unsigned long long nq = 0, nwide = 0, maxpot = 0;
+    unsigned long long nq = 0, nwide = 0, maxpot = 0, npepq = 0;
     for (uint32_t z = c0; z <= c1 && qi < sc.qmax; z++) {
         const float precursor_mass = __fmul_rn(mz, (float)z);
         Tol ptol = sc.precursor_tol;
@@ -59,10 +59,11 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b) {
             q.charge = (uint8_t)z;
             q.iso = (int8_t)iso;
             q.nfc = (uint8_t)(mfc - 1);
-            q.mode = q.potential > NARROW_CAP ? 2 : 1;
+            q.mode = q.potential > NARROW_CAP ? 2 : ((db.pep_centric_ok && q.potential <= sc.pep_cap) ? 3 : 1);
             out[qi] = q;
             nq++;
             if (q.mode == 2) nwide++;
+            if (q.mode == 3) npepq++;
             if (q.potential > maxpot) maxpot = q.potential;
         }
     }
@@ -72,6 +73,7 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b) {
     }
     if (nq) atomicAdd(b.counters + C_QUERIES, nq);
     if (nwide) atomicAdd(b.counters + C_WIDE, nwide);
+    if (npepq) atomicAdd(b.counters + C_PEPQ, npepq);
     atomicMax(b.counters + C_MAXPOT, maxpot);
 }
 
@@ -158,55 +160,177 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* s_warp) 
     return t;
 }
 
+// ------------------------------------------------------------------------------------------- sorted-array bucket LUT
+// Membership tests against a sorted f32 array (spectrum peaks, or per-charge tolerance bounds) dominate the instruction count
+// of this path. A 256-cell LUT over the array's value range gives a conservative lower bound of lower_bound(arr, x) in O(1);
+// callers then advance linearly comparing the ACTUAL array values, so results stay exact.  start[c] = #{i : arr[i] < edge(c)},
+// edge(c) = base + c*w (c >= 1), start[0] = 0.
+constexpr uint32_t LUT_CELLS = 256;
+struct LutParams { float base, inv_w; };
+
+__device__ __forceinline__ LutParams lut_params(float first, float last) {
+    LutParams L;
+    L.base = first;
+    const float w = (last - first) / (float)LUT_CELLS;
+    L.inv_w = (w > 0.0f && w < 3.0e38f) ? 1.0f / w : 0.0f;
+    return L;
+}
+__device__ __forceinline__ float lut_edge(const LutParams& L, uint32_t c) { return L.inv_w > 0.0f ? L.base + (float)c * (1.0f / L.inv_w) : L.base; }
+// Cooperative build: threads [t0, t0+stride, ...) fill start[0..LUT_CELLS)
+__device__ __forceinline__ void lut_build(const float* arr, uint32_t n, const LutParams& L, uint16_t* start, uint32_t t0, uint32_t stride) {
+    for (uint32_t c = t0; c < LUT_CELLS; c += stride) {
+        uint32_t lo = 0;
+        if (c > 0 && L.inv_w > 0.0f) {
+            const float e = lut_edge(L, c);
+            uint32_t hi = n;
+            while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (arr[m] < e) lo = m + 1; else hi = m; }
+        }
+        start[c] = (uint16_t)lo;
+    }
+}
+// A position s with arr[i] < x for all i < s (conservative: one cell early to absorb float rounding of the cell index).
+__device__ __forceinline__ uint32_t lut_start(const LutParams& L, const uint16_t* start, float x) {
+    const float t = (x - L.base) * L.inv_w;
+    int c = t > 1.0f ? (int)fminf(t, (float)(LUT_CELLS - 1)) - 1 : 0;
+    return start[c];
+}
+
 // ------------------------------------------------------------------------------------- preliminary scoring, narrow
-// One CTA per (spectrum, query). Each thread owns (peak, fragment charge) probes: bucket binary search over
-// min_value, per-page binary search over PeptideIx, exact filter, shared-memory count increment.
-__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b) {
+// One CTA per (spectrum, query); the dense per-window counts live in shared memory. Two interchangeable ways to fill them
+// (identical counts: the matched set is {fragment in index : mz in [flo,fhi](peak*charge), PeptideIx in [eff_lo,eff_hi]}):
+//
+//  * index path (mode 1) — the reference's loop order: each thread owns (peak, fragment charge) probes: bucket binary search
+//    over min_value, per-page binary search over PeptideIx, exact filter, shared-memory count increment.
+//  * peptide-centric path (mode 3) — for small windows: the window's peptides are contiguous in the per-peptide ion table,
+//    so one warp per peptide streams its ions (coalesced), and each lane counts the (peak, charge) pairs whose tolerance
+//    interval contains its fragment with two binary searches over per-charge LO/HI bound arrays staged in shared memory
+//    (bounds computed with the reference's f32 ops; both arrays are monotone in the peak mass, which is verified per
+//    spectrum — otherwise the CTA falls back to the index path).
+__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b, uint32_t pmax) {
     __shared__ uint32_t cnt32[NARROW_CAP / 2 + 1];
     __shared__ uint64_t heap[K_MAX];
     __shared__ uint64_t queue[PRELIM_THREADS];
     __shared__ uint32_t s_warp[40];
     __shared__ uint32_t s_nonzero;
+    extern __shared__ float bounds_smem[];  // LO[nfc][np] then HI[nfc][np] (peptide-centric path only)
 
     const uint32_t item = blockIdx.x;
     const QueryDesc q = b.queries[item];
-    if (q.mode != 1) return;
+    if (q.mode != 1 && q.mode != 3) return;
     const uint32_t s = item / sc.qmax;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = PRELIM_THREADS / 32;
     const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
     const uint32_t nwords = (q.potential + 1) >> 1;
     for (uint32_t i = tid; i < nwords; i += PRELIM_THREADS) cnt32[i] = 0;
-    __syncthreads();
 
     const uint32_t nfc = q.nfc;
     const uint32_t ntask = np * nfc;
     uint32_t my_matched = 0, my_pages = 0, my_entries = 0;
-    for (uint32_t t = tid; t < ntask; t += PRELIM_THREADS) {
-        const uint32_t p = t / nfc, fc = t - p * nfc + 1;
-        const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
-        float flo, fhi;
-        tol_bounds(sc.fragment_tol, mass, flo, fhi);
-        const int klo = f32_key(flo), khi = f32_key(fhi);
-        uint32_t bl, br;
-        binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
-                            [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
-        for (uint32_t page = bl; page < br; page++) {
-            const uint64_t pbase = (uint64_t)page * db.bucket_size;
-            const uint64_t pend = min(pbase + db.bucket_size, db.n_frag);
-            const uint2* slice = db.frag + pbase;
-            const uint32_t pn = (uint32_t)(pend - pbase);
-            uint32_t il, ir;
-            binary_search_slice(pn, [&](uint32_t i) { return __ldg(&slice[i].x) < q.pre_lo; }, [&](uint32_t i) { return __ldg(&slice[i].x) <= q.pre_hi; },
-                                il, ir);
-            my_pages++;
-            my_entries += ir - il;
-            for (uint32_t e = il; e < ir; e++) {
-                const uint2 f = __ldg(&slice[e]);
-                const float fmz = __uint_as_float(f.y);
-                if (f.x >= q.eff_lo && f.x <= q.eff_hi && fmz >= flo && fmz <= fhi) {
-                    const uint32_t idx = f.x - q.pre_lo;
-                    atomicAdd(&cnt32[idx >> 1], 1u << ((idx & 1) * 16));
-                    my_matched++;
+    __shared__ LutParams s_lp[8];
+    bool pep_path = q.mode == 3 && np > 0 && np < 65536 && nfc <= 8;
+    // dynamic smem layout per fragment charge c: LO_c[pmax] HI_c[pmax] (floats) | sA_c[256] sB_c[256] (u16)
+    float* const bnd = bounds_smem;
+    uint16_t* const luts = reinterpret_cast<uint16_t*>(bounds_smem + 2 * (size_t)nfc * pmax);
+    if (pep_path) {
+        for (uint32_t t = tid; t < ntask; t += PRELIM_THREADS) {
+            const uint32_t c = t / np, p = t - c * np;
+            const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)(c + 1));  // scoring.rs:360
+            float flo, fhi;
+            tol_bounds(sc.fragment_tol, mass, flo, fhi);
+            bnd[(2 * c) * pmax + p] = flo;
+            bnd[(2 * c + 1) * pmax + p] = fhi;
+        }
+        __syncthreads();
+        bool bad = false;
+        for (uint32_t t = tid; t < ntask; t += PRELIM_THREADS) {
+            const uint32_t c = t / np, p = t - c * np;
+            const float* lo_c = bnd + (2 * c) * pmax;
+            const float* hi_c = lo_c + pmax;
+            if (p > 0) bad |= !(lo_c[p] >= lo_c[p - 1]) || !(hi_c[p] >= hi_c[p - 1]);
+            bad |= !(lo_c[p] == lo_c[p]) || !(hi_c[p] == hi_c[p]);
+        }
+        if (__syncthreads_or(bad)) {
+            pep_path = false;
+            if (tid == 0) atomicAdd(b.counters + C_PEPFALLBACK, 1ull);
+        } else {
+            for (uint32_t c = 0; c < nfc; c++) {
+                const float* lo_c = bnd + (2 * c) * pmax;
+                const float* hi_c = lo_c + pmax;
+                const LutParams L = lut_params(lo_c[0], hi_c[np - 1]);
+                if (tid == 0) s_lp[c] = L;
+                lut_build(lo_c, np, L, luts + (2 * c) * LUT_CELLS, tid, PRELIM_THREADS);
+                lut_build(hi_c, np, L, luts + (2 * c + 1) * LUT_CELLS, tid, PRELIM_THREADS);
+            }
+            __syncthreads();
+        }
+    } else {
+        __syncthreads();
+    }
+
+    if (pep_path) {
+        if (q.eff_lo <= q.eff_hi) {
+            for (uint32_t pep = q.eff_lo + warp; pep <= q.eff_hi; pep += nwarps) {
+                const uint32_t L = __ldg(db.pep_len + pep);
+                const uint32_t nions = L - 1, tot = nions * db.n_kinds;
+                const float* src = db.ions + __ldg(db.ion_off + pep);
+                uint32_t c_here = 0;
+                for (uint32_t j0 = 0; j0 < tot; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    if (j < tot) {
+                        const uint32_t k = j / nions, i = j - k * nions;
+                        const bool keep = ((db.nterm_mask >> k) & 1) ? (i + 1) > db.min_ion_index : (nions - i) > db.min_ion_index;
+                        if (keep) {
+                            const float f = __ldg(src + j);
+                            for (uint32_t c = 0; c < nfc; c++) {
+                                const float* lo_c = bnd + (2 * c) * pmax;
+                                const float* hi_c = lo_c + pmax;
+                                const LutParams LP = s_lp[c];
+                                // a = #{p : LO[p] <= f},  bb = #{p : HI[p] < f} (within [0,a)); pairs matched = a - bb
+                                uint32_t a = lut_start(LP, luts + (2 * c) * LUT_CELLS, f);
+                                while (a < np && lo_c[a] <= f) a++;
+                                uint32_t bb = lut_start(LP, luts + (2 * c + 1) * LUT_CELLS, f);
+                                while (bb < a && hi_c[bb] < f) bb++;
+                                c_here += a - min(bb, a);
+                            }
+                        }
+                    }
+                }
+                for (int o = 16; o > 0; o >>= 1) c_here += __shfl_down_sync(0xffffffffu, c_here, o);
+                if (lane == 0 && c_here) {
+                    const uint32_t idx = pep - q.pre_lo;
+                    atomicAdd(&cnt32[idx >> 1], (c_here & 0xFFFFu) << ((idx & 1) * 16));
+                    my_matched += c_here;
+                }
+            }
+        }
+    } else {
+        for (uint32_t t = tid; t < ntask; t += PRELIM_THREADS) {
+            const uint32_t p = t / nfc, fc = t - p * nfc + 1;
+            const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
+            float flo, fhi;
+            tol_bounds(sc.fragment_tol, mass, flo, fhi);
+            const int klo = f32_key(flo), khi = f32_key(fhi);
+            uint32_t bl, br;
+            binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
+                                [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
+            for (uint32_t page = bl; page < br; page++) {
+                const uint64_t pbase = (uint64_t)page * db.bucket_size;
+                const uint64_t pend = min(pbase + db.bucket_size, db.n_frag);
+                const uint2* slice = db.frag + pbase;
+                const uint32_t pn = (uint32_t)(pend - pbase);
+                uint32_t il, ir;
+                binary_search_slice(pn, [&](uint32_t i) { return __ldg(&slice[i].x) < q.pre_lo; }, [&](uint32_t i) { return __ldg(&slice[i].x) <= q.pre_hi; },
+                                    il, ir);
+                my_pages++;
+                my_entries += ir - il;
+                for (uint32_t e = il; e < ir; e++) {
+                    const uint2 f = __ldg(&slice[e]);
+                    const float fmz = __uint_as_float(f.y);
+                    if (f.x >= q.eff_lo && f.x <= q.eff_hi && fmz >= flo && fmz <= fhi) {
+                        const uint32_t idx = f.x - q.pre_lo;
+                        atomicAdd(&cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                        my_matched++;
+                    }
                 }
             }
         }
@@ -216,8 +340,8 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
     const uint32_t entries_total = block_sum_u32(my_entries, s_warp);
     if (tid == 0) {
         atomicAdd(b.counters + C_TASKS, (unsigned long long)ntask);
-        atomicAdd(b.counters + C_PAGES, (unsigned long long)pages_total);
-        atomicAdd(b.counters + C_ENTRIES, (unsigned long long)entries_total);
+        if (pages_total) atomicAdd(b.counters + C_PAGES, (unsigned long long)pages_total);
+        if (entries_total) atomicAdd(b.counters + C_ENTRIES, (unsigned long long)entries_total);
         atomicAdd(b.counters + C_MATCHED, (unsigned long long)matched_total);
     }
     QueryHits* h = b.hits + item;
@@ -363,9 +487,10 @@ struct ScoreRec {
     uint32_t charge;
     int iso;
     uint32_t valid;
+    uint32_t plen;
 };
 
-// select_most_intense_peak (spectrum.rs:134-159), offset None
+// select_most_intense_peak (spectrum.rs:134-159), offset None — exact binary_search_slice emulation (any input)
 __device__ __forceinline__ int select_most_intense_peak(const float* masses, const float* intens, uint32_t n, float center, const Tol& tol) {
     float lo, hi;
     tol_bounds(tol, center, lo, hi);
@@ -382,6 +507,27 @@ __device__ __forceinline__ int select_most_intense_peak(const float* masses, con
             const float it = intens[idx];
             if (it >= max_int) { max_int = it; best = (int)idx; }
         }
+    }
+    return best;
+}
+// Same result for spectra whose masses are verified ascending, positive and non-NaN: the in-window peaks are then one contiguous
+// run, found from the bucket LUT and scanned in index order with the reference's comparisons (>= keeps the last of equal maxima).
+__device__ __forceinline__ int select_most_intense_peak_lut(const float* masses, const float* intens, uint32_t n, float center, const Tol& tol,
+                                                            const LutParams& LP, const uint16_t* lut) {
+    float lo, hi;
+    tol_bounds(tol, center, lo, hi);
+    lo = __fadd_rn(lo, 0.0f);
+    hi = __fadd_rn(hi, 0.0f);
+    uint32_t idx = lut_start(LP, lut, lo);
+    while (idx < n && masses[idx] < lo) idx++;
+    int best = -1;
+    float max_int = 0.0f;
+    while (idx < n) {
+        const float m = masses[idx];
+        if (!(m <= hi)) break;
+        const float it = intens[idx];
+        if (it >= max_int) { max_int = it; best = (int)idx; }
+        idx++;
     }
     return best;
 }
@@ -416,11 +562,13 @@ struct Run {
     }
 };
 
-// One warp scores one candidate (score_candidate, scoring.rs:675-767). Lanes look up theoretical fragments in
-// parallel (ions precomputed per peptide), then matched fragments are folded in the reference's order
-// (kind, ion index, charge) with a ballot loop so the f32 accumulations are bit-identical.
-__device__ __forceinline__ void score_candidate_warp(const DbView& db, const ScorerView& sc, uint64_t key, const float* masses, const float* intens,
-                                                     uint32_t np, ScoreRec* out, uint8_t* mark /*nullable: remove_matched_peaks marks*/) {
+// One warp scores one candidate (score_candidate, scoring.rs:675-767). Lanes look up theoretical fragments in parallel (ions
+// precomputed per peptide) and each computes its own ppm term; matched fragments are then folded in the reference's order
+// (kind, ion index, charge) with a ballot loop so the f32 accumulations (summed_b/y, ppm_difference) are bit-identical.
+struct SpecView { const float* masses; const float* intens; uint32_t np; bool use_lut; LutParams lp; const uint16_t* lut; };
+
+__device__ __forceinline__ void score_candidate_warp(const DbView& db, const ScorerView& sc, uint64_t key, const SpecView& sp, ScoreRec* out,
+                                                     uint8_t* mark /*nullable: remove_matched_peaks marks*/) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t pep = key_peptide(key), charge = key_charge(key);
     const uint32_t L = __ldg(db.pep_len + pep);
@@ -434,33 +582,42 @@ __device__ __forceinline__ void score_candidate_warp(const DbView& db, const Sco
     for (uint32_t base = 0; base < total; base += 32) {
         const uint32_t f = base + lane;
         int pk = -1;
-        float mz = 0.f;
-        uint32_t kind_i = 0, idx = 0;
+        float term = 0.f, inten = 0.f;
+        uint32_t idx = 0;
+        bool is_n = false;
         if (f < total) {
-            kind_i = f / per_kind;
+            const uint32_t kind_i = f / per_kind;
             const uint32_t rem = f - kind_i * per_kind;
             idx = rem / nfc;
             const uint32_t fc = rem - idx * nfc + 1;
-            mz = __fdiv_rn(__ldg(ions + kind_i * nions + idx), (float)fc);  // scoring.rs:707
-            pk = select_most_intense_peak(masses, intens, np, mz, sc.fragment_tol);
+            is_n = (db.nterm_mask >> kind_i) & 1;
+            const float mz = __fdiv_rn(__ldg(ions + kind_i * nions + idx), (float)fc);  // scoring.rs:707
+            pk = sp.use_lut ? select_most_intense_peak_lut(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol, sp.lp, sp.lut)
+                            : select_most_intense_peak(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol);
+            if (pk >= 0 && mark == nullptr) {
+                const float peak_mass = sp.masses[pk];
+                inten = sp.intens[pk];
+                // scoring.rs:719-720: peak_intensity * (mz - peak_mass).abs() * 2E6 / (mz + peak_mass)
+                term = __fdiv_rn(__fmul_rn(__fmul_rn(inten, fabsf(__fsub_rn(mz, peak_mass))), 2E6f), __fadd_rn(mz, peak_mass));
+            }
         }
-        uint32_t mask = __ballot_sync(0xffffffffu, pk >= 0);
         if (mark != nullptr) {
             if (pk >= 0) mark[pk] = 1;
             continue;
         }
+        uint32_t mask = __ballot_sync(0xffffffffu, pk >= 0);
+        const uint32_t maskn = __ballot_sync(0xffffffffu, pk >= 0 && is_n);
+        mb += __popc(maskn);
+        my += __popc(mask & ~maskn);
         while (mask) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;
-            const int pkb = __shfl_sync(0xffffffffu, pk, src);
-            const float mzb = __shfl_sync(0xffffffffu, mz, src);
-            const uint32_t kb = __shfl_sync(0xffffffffu, kind_i, src);
+            const float t = __shfl_sync(0xffffffffu, term, src);
+            const float it = __shfl_sync(0xffffffffu, inten, src);
             const uint32_t ib = __shfl_sync(0xffffffffu, idx, src);
-            const float peak_mass = masses[pkb], peak_int = intens[pkb];
-            // scoring.rs:719-720: peak_intensity * (mz - peak_mass).abs() * 2E6 / (mz + peak_mass)
-            ppm = __fadd_rn(ppm, __fdiv_rn(__fmul_rn(__fmul_rn(peak_int, fabsf(__fsub_rn(mzb, peak_mass))), 2E6f), __fadd_rn(mzb, peak_mass)));
-            if (db.kinds[kb] <= 2) { mb++; sb = __fadd_rn(sb, peak_int); brun.matched(ib); }
-            else { my++; sy = __fadd_rn(sy, peak_int); yrun.matched(ib); }
+            ppm = __fadd_rn(ppm, t);
+            if ((maskn >> src) & 1) { sb = __fadd_rn(sb, it); brun.matched(ib); }
+            else { sy = __fadd_rn(sy, it); yrun.matched(ib); }
         }
     }
     if (mark == nullptr && lane == 0) {
@@ -471,6 +628,7 @@ __device__ __forceinline__ void score_candidate_warp(const DbView& db, const Sco
         r.hyperscore = hyperscore_of(sc.score_type, r.matched_b, r.matched_y, sb, sy);
         r.ppm_difference = __fdiv_rn(ppm, __fadd_rn(sb, sy));  // scoring.rs:759
         r.valid = ((r.matched_b + r.matched_y) & 0xFFFF) >= sc.min_matched_peaks;
+        r.plen = L;
         *out = r;
     }
 }
@@ -506,18 +664,34 @@ __device__ __forceinline__ uint32_t append_hits(uint64_t* buf, uint32_t len, uin
     return len;
 }
 
+// Validates that the (possibly peak-depleted) spectrum is ascending, positive and NaN-free and builds the bucket LUT; otherwise the
+// exact binary-search emulation is used for this spectrum.
+__device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t np, uint16_t* lut, LutParams& lp) {
+    bool bad = np == 0 || np >= 65536;
+    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
+        const float m = masses[i];
+        bad |= !(m > 0.0f) || (i > 0 && !(m >= masses[i - 1]));
+    }
+    if (__syncthreads_or(bad)) return false;
+    lp = lut_params(masses[0], masses[np - 1]);
+    lut_build(masses, np, lp, lut, threadIdx.x, blockDim.x);
+    __syncthreads();
+    return true;
+}
+
 // One CTA per spectrum.
 __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
                                                          uint64_t* dbg_keys /*nullable: initial_hits dump*/, uint32_t* dbg_meta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: masses[pmax] intens[pmax] cur[lcap] tot[lcap] recs[kparam] order[kparam] mark[pmax]
+    // layout: masses[pmax] intens[pmax] cur[lcap] tot[lcap] recs[kparam] order[kparam] lut[256] mark[pmax]     (pmax is even)
     float* masses = reinterpret_cast<float*>(smem_raw);
     float* intens = masses + pmax;
-    uint64_t* cur = reinterpret_cast<uint64_t*>(intens + pmax + (pmax & 1));
+    uint64_t* cur = reinterpret_cast<uint64_t*>(intens + pmax);
     uint64_t* tot = cur + sc.lcap;
     ScoreRec* recs = reinterpret_cast<ScoreRec*>(tot + sc.lcap);
     uint32_t* order = reinterpret_cast<uint32_t*>(recs + sc.kparam);
-    uint8_t* mark = reinterpret_cast<uint8_t*>(order + sc.kparam);
+    uint16_t* lut = reinterpret_cast<uint16_t*>(order + sc.kparam);
+    uint8_t* mark = reinterpret_cast<uint8_t*>(lut + LUT_CELLS);
     __shared__ uint32_t s_ntot, s_ncand, s_np, s_nvalid;
     __shared__ unsigned long long s_matched_peaks, s_scored;
     __shared__ float s_tic;
@@ -527,14 +701,34 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
     uint32_t np = b.peak_off[s + 1] - p0;
     for (uint32_t i = tid; i < np; i += SCORE_THREADS) { masses[i] = b.masses[p0 + i]; intens[i] = b.intens[p0 + i]; }
 
-    // ---- fold the per-query hits: matched_peaks (isotope fold, scoring.rs:384-416) then initial_hits (charge fold, :418-462)
-    if (tid == 0) {
-        const QueryDesc* qd = b.queries + (size_t)s * sc.qmax;
-        const QueryHits* qh = b.hits + (size_t)s * sc.qmax;
-        const uint64_t* qk = b.hit_keys + (size_t)s * sc.qmax * sc.kparam;
+    const QueryDesc* qd = b.queries + (size_t)s * sc.qmax;
+    const QueryHits* qh = b.hits + (size_t)s * sc.qmax;
+    const uint64_t* qk = b.hit_keys + (size_t)s * sc.qmax * sc.kparam;
+    const bool iso_fold = sc.min_iso != sc.max_iso;
+    const bool single = !iso_fold && (sc.qmax == 1 || qd[1].mode == 0) && qd[0].mode != 0;
+    if (single) {
+        // one query, nothing to fold: trim_hits on a list of <= k entries is the identity (scoring.rs:460 after :380). Parallel copy,
+        // then an order-preserving filter of PreScore::default() entries (scoring.rs:489).
+        const QueryHits h = qh[0];
+        const uint32_t n = h.n ? h.n : min(h.default_run, sc.kparam);
+        for (uint32_t i = tid; i < n; i += SCORE_THREADS) tot[i] = h.n ? qk[i] : PRESCORE_DEFAULT;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = 0;
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t i = base + lane;
+                const uint64_t k = i < n ? tot[i] : PRESCORE_DEFAULT;
+                const bool keep = i < n && key_peptide(k) != 0xFFFFFFFFu;
+                const uint32_t ball = __ballot_sync(0xffffffffu, keep);
+                if (keep) cur[w + __popc(ball & ((1u << lane) - 1))] = k;
+                w += __popc(ball);
+            }
+            if (lane == 0) { s_ntot = n; s_ncand = w; s_matched_peaks = h.matched_peaks; s_scored = h.scored_candidates; s_np = np; s_tic = b.tic[s]; }
+        }
+    } else if (tid == 0) {
+        // ---- fold the per-query hits: matched_peaks (isotope fold, scoring.rs:384-416) then initial_hits (charge fold, :418-462)
         unsigned long long mp = 0, scd = 0;
         uint32_t ntot = 0;
-        const bool iso_fold = sc.min_iso != sc.max_iso;
         uint32_t nq = 0;
         while (nq < sc.qmax && qd[nq].mode != 0) nq++;
         const uint32_t nch = sc.n_iso ? nq / sc.n_iso : 0;
@@ -580,30 +774,36 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
     const uint32_t rounds = sc.chimera ? sc.report_psms : 1;
     const uint32_t per_round = sc.chimera ? 1 : sc.report_psms;
     uint32_t nout = 0;
-    if (tid == 0 && ncand) {
-        unsigned long long fl = 0;
-        for (uint32_t c = 0; c < ncand; c++) fl += 2ull * db.pep_len[key_peptide(cur[c])] + 2ull;
-        atomicAdd(b.counters + C_CANDS, (unsigned long long)ncand * rounds);
-        atomicAdd(b.counters + C_PEPFLOATS, fl * rounds);
-    }
-    for (uint32_t round = 0; round < rounds; round++) {
+    SpecView sv;
+    sv.masses = masses; sv.intens = intens; sv.lut = lut;
+    for (uint32_t round = 0; round < rounds && ncand; round++) {
         np = s_np;
-        for (uint32_t c = warp; c < ncand; c += nwarps) score_candidate_warp(db, sc, cur[c], masses, intens, np, recs + c, nullptr);
-        __syncthreads();
-        // stable sort by hyperscore descending (scoring.rs:495) via rank counting
+        sv.np = np;
+        sv.use_lut = spectrum_lut_setup(masses, np, lut, sv.lp);
+        for (uint32_t c = warp; c < ncand; c += nwarps) score_candidate_warp(db, sc, cur[c], sv, recs + c, nullptr);
         if (tid == 0) s_nvalid = 0;
         __syncthreads();
-        if (tid < ncand && recs[tid].valid) {
-            const double h = recs[tid].hyperscore;
-            uint32_t pos = 0;
-            for (uint32_t j = 0; j < ncand; j++) {
-                if (!recs[j].valid) continue;
-                const double hj = recs[j].hyperscore;
-                pos += (hj > h) || (hj == h && j < tid);
+        // stable sort by hyperscore descending (scoring.rs:495) via rank counting
+        uint32_t my_floats = 0;
+        if (tid < ncand) {
+            my_floats = 2 * recs[tid].plen + 2;
+            if (recs[tid].valid) {
+                const double h = recs[tid].hyperscore;
+                uint32_t pos = 0;
+                for (uint32_t j = 0; j < ncand; j++) {
+                    if (!recs[j].valid) continue;
+                    const double hj = recs[j].hyperscore;
+                    pos += (hj > h) || (hj == h && j < tid);
+                }
+                order[pos] = tid;
+                atomicAdd(&s_nvalid, 1u);
             }
-            order[pos] = tid;
-            atomicAdd(&s_nvalid, 1u);
         }
+        if (tid < ((ncand + 31) & ~31u)) {  // SURVEY.md §8d peptide-record term: 2L+2 floats per scored candidate
+            for (int o = 16; o > 0; o >>= 1) my_floats += __shfl_down_sync(0xffffffffu, my_floats, o);
+            if (lane == 0 && my_floats) atomicAdd(b.counters + C_PEPFLOATS, (unsigned long long)my_floats);
+        }
+        if (tid == 0) atomicAdd(b.counters + C_CANDS, (unsigned long long)ncand);
         __syncthreads();
         const uint32_t nvalid = s_nvalid;
         const uint32_t emit = min(per_round, nvalid);
@@ -618,7 +818,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
             const float mono = db.pep_mono[r.peptide];
             // scoring.rs:530-531
             const float delta_mass = __fdiv_rn(__fmul_rn(__fsub_rn(__fsub_rn(precursor_mass, mono), iso), 2E6f), __fadd_rn(__fsub_rn(precursor_mass, iso), mono));
-            const uint32_t plen = db.pep_len[r.peptide];
+            const uint32_t plen = r.plen;
             const float sum = __fadd_rn(r.summed_b, r.summed_y);
             FeatureOut f;
             f.spectrum = s; f.peptide_idx = r.peptide; f.peptide_len = plen;
@@ -646,7 +846,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
         __syncthreads();
         if (warp == 0) {
             const ScoreRec r = recs[order[0]];
-            score_candidate_warp(db, sc, prescore_key(0, r.peptide, r.charge, r.iso), masses, intens, np, nullptr, mark);
+            score_candidate_warp(db, sc, prescore_key(0, r.peptide, r.charge, r.iso), sv, nullptr, mark);
         }
         __syncthreads();
         // a peak is removed when its (mass, intensity) pair equals a marked one (Vec::contains on (f32,f32))
@@ -761,6 +961,30 @@ __global__ void k_bucket_keys(uint64_t n_frag, uint32_t bucket_shift, const uint
     const uint64_t bucket = i >> bucket_shift;
     key64[i] = (bucket << 32) | pep_sorted[i];
     if ((i & ((1ull << bucket_shift) - 1)) == 0) bucket_min[bucket] = __uint_as_float(bits);
+}
+// Verifies that an uploaded index is exactly {ions with index > min_ion_index}: per peptide, fragment count and the wrapped sum
+// of m/z bit patterns must match what k_gen would emit. acc[2p] = count, acc[2p+1] = sum.
+__global__ void k_index_signature(uint64_t n_frag, const uint2* frag, uint32_t n_pep, uint32_t* acc) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frag) return;
+    const uint2 f = frag[i];
+    if (f.x >= n_pep) return;
+    atomicAdd(acc + 2ull * f.x, 1u);
+    atomicAdd(acc + 2ull * f.x + 1, f.y);
+}
+__global__ void k_index_verify(uint32_t n_pep, const uint8_t* pep_len, const uint32_t* ion_off, const float* ions, uint32_t n_kinds, DbView kinds_src,
+                               uint32_t min_ion_index, const uint32_t* acc, uint32_t* mismatch) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pep) return;
+    const uint32_t L = pep_len[p];
+    const float* src = ions + ion_off[p];
+    uint32_t c = 0, sum = 0;
+    for (uint32_t k = 0; k < n_kinds; k++)
+        for (uint32_t i = 0; i + 1 < L; i++) {
+            const bool keep = kinds_src.kinds[k] <= 2 ? (i + 1) > min_ion_index : ((L - 1) - i) > min_ion_index;
+            if (keep) { c++; sum += __float_as_uint(src[k * (L - 1) + i]); }
+        }
+    if (c != acc[2ull * p] || sum != acc[2ull * p + 1]) atomicAdd(mismatch, 1u);
 }
 __global__ void k_pack_fragments(uint64_t n_frag, const uint64_t* key64, const uint32_t* mzbits, uint2* frag) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

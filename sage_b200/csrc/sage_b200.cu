@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -131,6 +132,7 @@ static int db_upload_peptides(sage_b200_db* db, const sage_b200_peptides* P, con
     for (uint64_t k = 0; k < n_kinds; k++) {
         if (kinds[k] > 5) return fail(SAGE_B200_EINVAL, "ion kind %u out of range", kinds[k]);
         db->v.kinds[k] = kinds[k];
+        if (kinds[k] <= 2) db->v.nterm_mask |= 1u << k;
     }
     const uint64_t nres = n ? P->residue_offsets[n] : 0;
     db->total_residues = nres;
@@ -253,6 +255,39 @@ extern "C" int sage_b200_db_create(const sage_b200_peptides* peptides, const sag
     if (e != cudaSuccess) { sage_b200_db_destroy(db); return fail(SAGE_B200_ECUDA, "index upload failed: %s", cudaGetErrorString(e)); }
     db->v.frag = (const uint2*)db->d_frag;
     db->v.bucket_min = (const float*)db->d_bucket_min;
+    // IndexedDatabase does not carry min_ion_index (it lives in Parameters, database.rs:128): infer it from the fragment count and
+    // verify the index content against the ion table; only then may narrow windows be counted peptide-centrically.
+    db->v.pep_centric_ok = 0;
+    db->v.min_ion_index = 0;
+    if (peptides->n_peptides && nf) {
+        const uint64_t n = peptides->n_peptides;
+        int found = -1;
+        for (uint32_t m = 0; m <= 64 && found < 0; m++) {
+            uint64_t tot = 0;
+            for (uint64_t i = 0; i < n; i++) {
+                const uint64_t L = peptides->residue_offsets[i + 1] - peptides->residue_offsets[i];
+                tot += index->n_ion_kinds * ((L - 1) > m ? (L - 1) - m : 0);
+            }
+            if (tot == nf) found = (int)m;
+            if (tot < nf) break;
+        }
+        if (found >= 0) {
+            void *acc = nullptr, *mis = nullptr;
+            uint32_t mismatch = 1;
+            if (cudaMalloc(&acc, 8 * n) == cudaSuccess && cudaMalloc(&mis, 4) == cudaSuccess) {
+                cudaMemset(acc, 0, 8 * n);
+                cudaMemset(mis, 0, 4);
+                k_index_signature<<<(unsigned)((nf + 255) / 256), 256>>>(nf, db->v.frag, (uint32_t)n, (uint32_t*)acc);
+                k_index_verify<<<(unsigned)((n + 127) / 128), 128>>>((uint32_t)n, db->v.pep_len, db->v.ion_off, db->v.ions, db->v.n_kinds, db->v, (uint32_t)found,
+                                                                    (const uint32_t*)acc, (uint32_t*)mis);
+                if (cudaMemcpy(&mismatch, mis, 4, cudaMemcpyDeviceToHost) != cudaSuccess) mismatch = 1;
+            }
+            if (acc) cudaFree(acc);
+            if (mis) cudaFree(mis);
+            cudaGetLastError();
+            if (mismatch == 0) { db->v.min_ion_index = (uint32_t)found; db->v.pep_centric_ok = 1; }
+        }
+    }
     *out = db;
     return 0;
 }
@@ -283,6 +318,8 @@ extern "C" int sage_b200_db_build(const sage_b200_peptides* peptides, uint64_t b
     db->v.n_frag = nf;
     db->v.n_bucket = (uint32_t)nb;
     db->v.bucket_size = (uint32_t)bucket_size;
+    db->v.min_ion_index = (uint32_t)std::min<uint64_t>(min_ion_index, 0xFFFFFFFFull);
+    db->v.pep_centric_ok = 1;  // the index is generated from the ion table with this filter by construction
     if ((rc = dmalloc(db, &db->d_frag, 8 * nf))) { sage_b200_db_destroy(db); return rc; }
     if ((rc = dmalloc(db, &db->d_bucket_min, 4 * nb))) { sage_b200_db_destroy(db); return rc; }
     db->v.frag = (const uint2*)db->d_frag;
@@ -358,7 +395,7 @@ extern "C" int sage_b200_db_export_index(const sage_b200_db* db, uint32_t* fragm
 // ------------------------------------------------------------------------------------------------ scorer
 struct ChunkState {
     bool loaded = false;
-    uint32_t n = 0, pmax = 2;
+    uint32_t n = 0, pmax = 2, zmax = 1;
     uint64_t npk = 0;
     size_t nitems = 0, smem = 0, small_bytes = 0;
     size_t o_off = 0, o_pmz = 0, o_tic = 0, o_ilo = 0, o_ihi = 0, o_rt = 0, o_ims = 0, o_chg = 0;
@@ -407,11 +444,24 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     if (v.n_iso > 32 || v.n_ch_max > 16) { delete s; return fail(SAGE_B200_ELIMIT, "isotope range > 32 or charge range > 16 not supported"); }
     v.qmax = std::max<uint32_t>(1, v.n_iso) * v.n_ch_max;
     v.lcap = std::max<uint32_t>(std::max<uint32_t>(v.n_iso, v.n_ch_max), 1) * v.kparam;
+    v.pep_cap = 2048;
+    if (const char* e = getenv("SAGE_B200_PEP_CAP")) v.pep_cap = (uint32_t)std::min<long>(std::max<long>(atol(e), 0), (long)NARROW_CAP);
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
     s->wide_ctas = db->sm_count * 2;
     *out = s;
     return 0;
+}
+
+extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name, int64_t value) {
+    if (!s || !name) return fail(SAGE_B200_EINVAL, "scorer_set_option: null argument");
+    std::lock_guard<std::mutex> lock(s->mu);
+    if (!strcmp(name, "pep_cap")) {  // 0 = always probe the fragment index (reference loop order); default 2048
+        if (value < 0 || value > (int64_t)NARROW_CAP) return fail(SAGE_B200_EINVAL, "pep_cap must be 0..%u", NARROW_CAP);
+        s->sv.pep_cap = (uint32_t)value;
+        return 0;
+    }
+    return fail(SAGE_B200_EINVAL, "unknown option '%s'", name);
 }
 
 extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
@@ -455,9 +505,10 @@ static int chunk_upload(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64
     if ((rc = S->d_small.reserve(C.small_bytes))) return rc;
     unsigned char* hs = (unsigned char*)S->h_small.p;
     uint32_t* h_off = (uint32_t*)(hs + C.o_off);
-    uint32_t pmax = 2;
+    uint32_t pmax = 2, zmax = sv.max_charge;
     for (uint32_t i = 0; i <= n; i++) h_off[i] = (uint32_t)(sp->peak_offsets[c0 + i] - pk0);
     for (uint32_t i = 0; i < n; i++) {
+        zmax = std::max<uint32_t>(zmax, sp->precursor_charge[c0 + i]);
         if (sp->peak_offsets[c0 + i + 1] < sp->peak_offsets[c0 + i]) return fail(SAGE_B200_EINVAL, "peak_offsets not monotone at spectrum %llu", (unsigned long long)(c0 + i));
         pmax = std::max(pmax, h_off[i + 1] - h_off[i]);
         if (sp->level && sp->level[c0 + i] != 2)
@@ -465,6 +516,7 @@ static int chunk_upload(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64
         if (std::isnan(sp->precursor_mz[c0 + i])) return fail(SAGE_B200_ENOPRECURSOR, "missing MS1 precursor for spectrum %llu", (unsigned long long)(c0 + i));
     }
     C.pmax = (pmax + 1) & ~1u;
+    C.zmax = zmax;
     memcpy(hs + C.o_pmz, sp->precursor_mz + c0, 4 * (size_t)n);
     memcpy(hs + C.o_tic, sp->total_ion_current + c0, 4 * (size_t)n);
     float* h_ilo = (float*)(hs + C.o_ilo);
@@ -478,7 +530,7 @@ static int chunk_upload(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64
         h_ims[i] = sp->inverse_ion_mobility ? sp->inverse_ion_mobility[c0 + i] : NAN;
     }
     memcpy(hs + C.o_chg, sp->precursor_charge + c0, n);
-    C.smem = (size_t)C.pmax * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + C.pmax + 16;
+    C.smem = (size_t)C.pmax * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + 2 * LUT_CELLS + C.pmax + 16;
     if (C.smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", C.pmax);
     C.nitems = (size_t)n * sv.qmax;
     if (C.nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
@@ -553,8 +605,16 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
 
     CUDA_TRY(cudaEventRecord(S->ev[1], st));
     CUDA_TRY(cudaMemsetAsync(S->d_counters.p, 0, 8 * C_COUNT, st));
-    // ---- setup: resolve precursor windows
-    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, sv, bv);
+    // ---- setup: resolve precursor windows. Peptide-centric counting needs LO/HI bound arrays of nfc_max * pmax floats in smem.
+    ScorerView svq = sv;
+    uint32_t mfc = sv.max_fragment_charge_opt >= 0 ? std::min<uint32_t>(C.zmax, (uint32_t)(sv.max_fragment_charge_opt + 1) & 0xFF) : C.zmax;
+    if (mfc < 2) mfc = 2;
+    size_t pep_smem = (size_t)(mfc - 1) * (2 * (size_t)C.pmax * sizeof(float) + 2 * LUT_CELLS * sizeof(uint16_t));
+    if (mfc - 1 > 8) pep_smem = 200 * 1024;
+    if (pep_smem > 96 * 1024) { svq.pep_cap = 0; pep_smem = 0; }
+    if (svq.pep_cap == 0) pep_smem = 0;
+    if (pep_smem > 24 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_prelim_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pep_smem));
+    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(S->ev[2], st));
     unsigned long long* hc = (unsigned long long*)S->h_counters.p;
@@ -565,7 +625,7 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
 
     // ---- preliminary scoring
     if (n_queries > n_wide) {
-        k_prelim_narrow<<<(unsigned)C.nitems, PRELIM_THREADS, 0, st>>>(db->v, sv, bv);
+        k_prelim_narrow<<<(unsigned)C.nitems, PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax);
         CUDA_TRY(cudaGetLastError());
         launches++;
     }
@@ -598,6 +658,8 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
     L.spectra += n; L.peaks += C.npk; L.queries += hc[C_QUERIES]; L.tasks += hc[C_TASKS]; L.pages += hc[C_PAGES]; L.entries_scanned += hc[C_ENTRIES];
     L.matched_fragments += hc[C_MATCHED]; L.candidates_scored += hc[C_CANDS]; L.peptide_record_floats += hc[C_PEPFLOATS]; L.psms += hc[C_PSMS];
     L.wide_queries += hc[C_WIDE];
+    L.pep_queries += hc[C_PEPQ];
+    L.pep_fallbacks += hc[C_PEPFALLBACK];
     L.d2h_bytes += 2 * 8 * C_COUNT;
     L.kernel_launches += launches;
     return 0;

@@ -20,11 +20,16 @@ def small():
     return pep, odb, gdb, spectra
 
 
-def run_both(odb, gdb, spectra, **kw):
-    sc = Scorer(gdb, **kw)
-    gf, gc = sc.score_batch(spectra)
+def run_both(odb, gdb, spectra, pep_caps=(None, 0), **kw):
+    """Scores with the CUDA path under each prelim strategy (default = peptide-centric for small windows, 0 = always probe the
+    fragment index in the reference's loop order) and requires both to equal the oracle."""
     of, oc, _, octr = odb.score_batch(oracle_cfg(**kw), spectra.as_dict(), counters=True)
-    n = assert_features_equal(gf, gc, of, oc, kw.get("report_psms", 1), what=str({k: v for k, v in kw.items() if "tol" not in k}))
+    for cap in pep_caps:
+        sc = Scorer(gdb, **kw)
+        if cap is not None:
+            sc.set_option("pep_cap", cap)
+        gf, gc = sc.score_batch(spectra)
+        n = assert_features_equal(gf, gc, of, oc, kw.get("report_psms", 1), what=str({"pep_cap": cap, **{k: v for k, v in kw.items() if "tol" not in k}}))
     return sc, n, octr
 
 
@@ -71,10 +76,14 @@ def test_narrow_search(small):
     pep, odb, gdb, spectra = small
     sc, n, octr = run_both(odb, gdb, spectra, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20))
     assert n > 1000
-    c = sc.counters()
+    c = sc.counters()  # last run: pep_cap = 0, i.e. the reference's loop order -> identical work counters
     for k in ("queries", "pages", "entries_scanned", "candidates_scored", "psms"):
         assert c[k] == octr[k], (k, c[k], octr[k])
-    assert c["peptide_record_floats"] == octr["peptide_record_floats"]
+    assert c["peptide_record_floats"] == octr["peptide_record_floats"] and c["pep_queries"] == 0
+    sc2 = Scorer(gdb, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20))
+    sc2.score_batch(spectra)
+    c2 = sc2.counters()
+    assert c2["pep_queries"] == c2["queries"] and c2["pep_fallbacks"] == 0 and c2["matched_fragments"] == c["matched_fragments"]
 
 
 def test_narrow_report5_fragcharge1(small):
@@ -164,6 +173,21 @@ def test_edge_cases(small):
     run_both(odb, gdb, batch, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=2)
     run_both(odb, gdb, batch, precursor_tol=Tolerance.da(-500, 500), fragment_tol=Tolerance.ppm(-20, 20), min_isotope_err=-1, max_isotope_err=1, chimera=True,
              report_psms=2)
+
+
+def test_unsorted_peaks_fall_back_to_index_path(small):
+    # the reference never assumes sorted peaks in the preliminary pass; the peptide-centric path does, so it must detect and fall back
+    pep, odb, gdb, spectra = small
+    sub = spectra.slice(0, 64)
+    rng = np.random.default_rng(5)
+    m = sub.masses.reshape(64, 200).copy()
+    it = sub.intensities.reshape(64, 200).copy()
+    for r in range(0, 64, 2):
+        perm = rng.permutation(200)
+        m[r], it[r] = m[r][perm], it[r][perm]
+    shuffled = SpectraBatch(**{**sub.__dict__, "masses": m.ravel(), "intensities": it.ravel()})
+    sc, _, _ = run_both(odb, gdb, shuffled, pep_caps=(None,), precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), min_matched_peaks=1)
+    assert sc.counters()["pep_fallbacks"] == 32
 
 
 def test_reference_panics_become_errors(small):
