@@ -154,6 +154,8 @@ struct ScorerView {
     uint32_t qmax;     // n_iso * n_ch_max query slots per spectrum
     uint32_t lcap;     // list capacity for merges
     uint32_t pep_cap;  // precursor windows up to this many peptides use the peptide-centric kernel path (0 = never)
+    const double* lnfact_tab;  // lnfact(n) for n < lnfact_n, computed on the host with libm log (scoring.rs:170-177)
+    uint32_t lnfact_n;
 };
 
 struct BatchView {
@@ -168,6 +170,7 @@ struct BatchView {
     const float* tic;
     const float* rt;            // nullable
     const float* ims;           // nullable
+    const uint32_t* order;      // spectrum processing order (ascending precursor window) for L2 locality; nullable = identity
     QueryDesc* queries;         // n * qmax
     QueryHits* hits;            // n * qmax
     uint64_t* hit_keys;         // n * qmax * kparam

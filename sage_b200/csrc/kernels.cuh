@@ -14,7 +14,7 @@ namespace sb {
 // ------------------------------------------------------------------------------------------------ setup
 // One thread per spectrum: enumerate the (charge, isotope) queries of Scorer::initial_hits and resolve each
 // precursor window to a PeptideIx range (two binary searches over peptides[].monoisotopic).
-__global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b) {
+__global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t* sort_key, uint32_t* sort_val) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n) return;
     const float pmz = b.prec_mz[s];
@@ -71,6 +71,7 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b) {
         QueryDesc q = {};
         out[qi] = q;
     }
+    if (sort_key) { sort_key[s] = out[0].mode ? out[0].pre_lo : 0xFFFFFFFFu; sort_val[s] = s; }
     if (nq) atomicAdd(b.counters + C_QUERIES, nq);
     if (nwide) atomicAdd(b.counters + C_WIDE, nwide);
     if (npepq) atomicAdd(b.counters + C_PEPQ, npepq);
@@ -214,10 +215,10 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
     __shared__ uint32_t s_nonzero;
     extern __shared__ float bounds_smem[];  // LO[nfc][np] then HI[nfc][np] (peptide-centric path only)
 
-    const uint32_t item = blockIdx.x;
+    const uint32_t s = b.order ? b.order[blockIdx.x / sc.qmax] : blockIdx.x / sc.qmax;
+    const uint32_t item = s * sc.qmax + blockIdx.x % sc.qmax;
     const QueryDesc q = b.queries[item];
     if (q.mode != 1 && q.mode != 3) return;
-    const uint32_t s = item / sc.qmax;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = PRELIM_THREADS / 32;
     const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
     const uint32_t nwords = (q.potential + 1) >> 1;
@@ -533,20 +534,21 @@ __device__ __forceinline__ int select_most_intense_peak_lut(const float* masses,
 }
 
 // lnfact (scoring.rs:170-177)
-__device__ __forceinline__ double lnfact(uint32_t n) {
+__device__ __forceinline__ double lnfact(const ScorerView& sc, uint32_t n) {
+    if (n < sc.lnfact_n) return __ldg(sc.lnfact_tab + n);
     if (n == 0) return 1.0;
     const double x = (double)n;
     return x * log(x) - x + 0.5 * log(x) + 0.5 * log(3.14159265358979323846 * 2.0 * x);
 }
 // ScoreType::score (scoring.rs:179-201)
-__device__ __forceinline__ double hyperscore_of(int score_type, uint32_t mb, uint32_t my, float sb, float sy) {
+__device__ __forceinline__ double hyperscore_of(const ScorerView& sc, uint32_t mb, uint32_t my, float sb, float sy) {
     double s;
-    if (score_type == 0) {
+    if (sc.score_type == 0) {
         const double i = (double)__fadd_rn(sb, 1.0f) * (double)__fadd_rn(sy, 1.0f);
-        s = log(i) + lnfact(mb) + lnfact(my);
+        s = log(i) + lnfact(sc, mb) + lnfact(sc, my);
     } else {
         const float si = __fadd_rn(sb, sy);
-        s = (double)(float)log1p((double)si) + lnfact(mb) + lnfact(my);
+        s = (double)(float)log1p((double)si) + lnfact(sc, mb) + lnfact(sc, my);
     }
     return isfinite(s) ? s : 255.0;
 }
@@ -625,12 +627,18 @@ __device__ __forceinline__ void score_candidate_warp(const DbView& db, const Sco
         r.peptide = pep; r.charge = charge; r.iso = key_iso(key);
         r.matched_b = mb & 0xFFFF; r.matched_y = my & 0xFFFF; r.summed_b = sb; r.summed_y = sy;
         r.longest_b = brun.longest; r.longest_y = yrun.longest;
-        r.hyperscore = hyperscore_of(sc.score_type, r.matched_b, r.matched_y, sb, sy);
-        r.ppm_difference = __fdiv_rn(ppm, __fadd_rn(sb, sy));  // scoring.rs:759
-        r.valid = ((r.matched_b + r.matched_y) & 0xFFFF) >= sc.min_matched_peaks;
+        r.hyperscore = 0.0;          // finalised one candidate per thread (finalize_rec): keeps the f64 log off the warp-serial path
+        r.ppm_difference = ppm;
+        r.valid = 0;
         r.plen = L;
         *out = r;
     }
+}
+
+__device__ __forceinline__ void finalize_rec(const ScorerView& sc, ScoreRec& r) {
+    r.hyperscore = hyperscore_of(sc, r.matched_b, r.matched_y, r.summed_b, r.summed_y);               // scoring.rs:756
+    r.ppm_difference = __fdiv_rn(r.ppm_difference, __fadd_rn(r.summed_b, r.summed_y));                // scoring.rs:759
+    r.valid = ((r.matched_b + r.matched_y) & 0xFFFF) >= sc.min_matched_peaks;                          // scoring.rs:491
 }
 
 struct FeatureOut {  // layout == sage_b200_feature
@@ -692,14 +700,15 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
     uint32_t* order = reinterpret_cast<uint32_t*>(recs + sc.kparam);
     uint16_t* lut = reinterpret_cast<uint16_t*>(order + sc.kparam);
     uint8_t* mark = reinterpret_cast<uint8_t*>(lut + LUT_CELLS);
-    __shared__ uint32_t s_ntot, s_ncand, s_np, s_nvalid;
+    __shared__ uint32_t s_ntot, s_ncand, s_np, s_nvalid, s_next;
     __shared__ unsigned long long s_matched_peaks, s_scored;
     __shared__ float s_tic;
 
-    const uint32_t s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SCORE_THREADS / 32;
+    const uint32_t s = b.order ? b.order[blockIdx.x] : blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SCORE_THREADS / 32;
     const uint32_t p0 = b.peak_off[s];
     uint32_t np = b.peak_off[s + 1] - p0;
     for (uint32_t i = tid; i < np; i += SCORE_THREADS) { masses[i] = b.masses[p0 + i]; intens[i] = b.intens[p0 + i]; }
+    if (tid == 0) s_next = 0;
 
     const QueryDesc* qd = b.queries + (size_t)s * sc.qmax;
     const QueryHits* qh = b.hits + (size_t)s * sc.qmax;
@@ -780,8 +789,16 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
         np = s_np;
         sv.np = np;
         sv.use_lut = spectrum_lut_setup(masses, np, lut, sv.lp);
-        for (uint32_t c = warp; c < ncand; c += nwarps) score_candidate_warp(db, sc, cur[c], sv, recs + c, nullptr);
+        for (;;) {  // warps pull candidates dynamically (their cost varies with peptide length / charge / matches)
+            uint32_t c = lane == 0 ? atomicAdd(&s_next, 1u) : 0u;
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= ncand) break;
+            score_candidate_warp(db, sc, cur[c], sv, recs + c, nullptr);
+        }
         if (tid == 0) s_nvalid = 0;
+        __syncthreads();
+        if (tid < ncand) finalize_rec(sc, recs[tid]);
+        if (tid == 0) s_next = 0;
         __syncthreads();
         // stable sort by hyperscore descending (scoring.rs:495) via rank counting
         uint32_t my_floats = 0;
@@ -812,7 +829,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
             const double next = tid + 1 < nvalid ? recs[order[tid + 1]].hyperscore : 0.0;
             const double best = recs[order[0]].hyperscore;
             const uint32_t k = (r.matched_b + r.matched_y) & 0xFFFF;
-            const double log10_poisson = ((double)k * log(lambda) - lambda - lnfact(k)) / 2.302585092994045684;
+            const double log10_poisson = ((double)k * log(lambda) - lambda - lnfact(sc, k)) / 2.302585092994045684;
             const float precursor_mass = __fmul_rn(mzp, (float)r.charge);
             const float iso = __fmul_rn((float)r.iso, NEUTRON);
             const float mono = db.pep_mono[r.peptide];

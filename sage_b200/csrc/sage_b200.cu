@@ -409,7 +409,8 @@ struct sage_b200_scorer {
     cudaEvent_t ev[8] = {};
     std::mutex mu;
     // device
-    DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_scratch, d_dbgk, d_dbgm;
+    DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_scratch, d_dbgk, d_dbgm, d_lnfact, d_sort, d_sorttmp;
+    int sort_spectra = 1;
     // pinned staging
     PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
     sage_b200_counters last{};
@@ -444,8 +445,23 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     if (v.n_iso > 32 || v.n_ch_max > 16) { delete s; return fail(SAGE_B200_ELIMIT, "isotope range > 32 or charge range > 16 not supported"); }
     v.qmax = std::max<uint32_t>(1, v.n_iso) * v.n_ch_max;
     v.lcap = std::max<uint32_t>(std::max<uint32_t>(v.n_iso, v.n_ch_max), 1) * v.kparam;
-    v.pep_cap = 2048;
+    v.pep_cap = 64;  // measured crossover on cfg2 (mean window 177 peptides): index probing wins above ~100 candidates
     if (const char* e = getenv("SAGE_B200_PEP_CAP")) v.pep_cap = (uint32_t)std::min<long>(std::max<long>(atol(e), 0), (long)NARROW_CAP);
+    {   // lnfact table with the host libm (the reference's f64::ln): Stirling form of scoring.rs:170-177
+        const uint32_t N = 4096;
+        std::vector<double> tab(N);
+        tab[0] = 1.0;
+        for (uint32_t n = 1; n < N; n++) {
+            const double x = (double)n;
+            tab[n] = x * std::log(x) - x + 0.5 * std::log(x) + 0.5 * std::log(3.14159265358979323846 * 2.0 * x);
+        }
+        int rc2 = s->d_lnfact.reserve(8 * N);
+        if (rc2) { delete s; return rc2; }
+        CUDA_TRY(cudaMemcpy(s->d_lnfact.p, tab.data(), 8 * N, cudaMemcpyHostToDevice));
+        v.lnfact_tab = s->d_lnfact.as<double>();
+        v.lnfact_n = N;
+    }
+    if (const char* e = getenv("SAGE_B200_SORT")) s->sort_spectra = atoi(e);
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
     s->wide_ctas = db->sm_count * 2;
@@ -456,7 +472,8 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
 extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name, int64_t value) {
     if (!s || !name) return fail(SAGE_B200_EINVAL, "scorer_set_option: null argument");
     std::lock_guard<std::mutex> lock(s->mu);
-    if (!strcmp(name, "pep_cap")) {  // 0 = always probe the fragment index (reference loop order); default 2048
+    if (!strcmp(name, "sort_spectra")) { s->sort_spectra = value != 0; return 0; }
+    if (!strcmp(name, "pep_cap")) {  // 0 = always probe the fragment index (reference loop order); default 64
         if (value < 0 || value > (int64_t)NARROW_CAP) return fail(SAGE_B200_EINVAL, "pep_cap must be 0..%u", NARROW_CAP);
         s->sv.pep_cap = (uint32_t)value;
         return 0;
@@ -467,7 +484,7 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
 extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
     if (!s) return;
     cudaSetDevice(s->db->device);
-    for (DevBuf* b : {&s->d_small, &s->d_masses, &s->d_intens, &s->d_queries, &s->d_hits, &s->d_keys, &s->d_features, &s->d_counts, &s->d_counters, &s->d_scratch, &s->d_dbgk, &s->d_dbgm}) b->release();
+    for (DevBuf* b : {&s->d_small, &s->d_masses, &s->d_intens, &s->d_queries, &s->d_hits, &s->d_keys, &s->d_features, &s->d_counts, &s->d_counters, &s->d_scratch, &s->d_dbgk, &s->d_dbgm, &s->d_lnfact, &s->d_sort, &s->d_sorttmp}) b->release();
     for (PinBuf* b : {&s->h_small, &s->h_masses, &s->h_intens, &s->h_features, &s->h_counts, &s->h_counters}) b->release();
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -614,8 +631,20 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
     if (pep_smem > 96 * 1024) { svq.pep_cap = 0; pep_smem = 0; }
     if (svq.pep_cap == 0) pep_smem = 0;
     if (pep_smem > 24 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_prelim_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pep_smem));
-    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv);
+    uint32_t *sk_in = nullptr, *sk_out = nullptr, *sv_in = nullptr, *sv_out = nullptr;
+    size_t sort_tmp = 0;
+    if (S->sort_spectra && n > 1) {  // process spectra in ascending precursor-window order: neighbouring CTAs then touch the same index lines
+        if ((rc = S->d_sort.reserve(16 * (size_t)n))) return rc;
+        sk_in = S->d_sort.as<uint32_t>(); sk_out = sk_in + n; sv_in = sk_out + n; sv_out = sv_in + n;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
+        if ((rc = S->d_sorttmp.reserve(sort_tmp + 16))) return rc;
+    }
+    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv, sk_in, sv_in);
     CUDA_TRY(cudaGetLastError());
+    if (sk_in) {
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(S->d_sorttmp.p, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
+        bv.order = sv_out;
+    }
     CUDA_TRY(cudaEventRecord(S->ev[2], st));
     unsigned long long* hc = (unsigned long long*)S->h_counters.p;
     CUDA_TRY(cudaMemcpyAsync(hc, S->d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));

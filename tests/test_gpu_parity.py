@@ -20,7 +20,7 @@ def small():
     return pep, odb, gdb, spectra
 
 
-def run_both(odb, gdb, spectra, pep_caps=(None, 0), **kw):
+def run_both(odb, gdb, spectra, pep_caps=(2048, 0), **kw):
     """Scores with the CUDA path under each prelim strategy (default = peptide-centric for small windows, 0 = always probe the
     fragment index in the reference's loop order) and requires both to equal the oracle."""
     of, oc, _, octr = odb.score_batch(oracle_cfg(**kw), spectra.as_dict(), counters=True)
@@ -81,6 +81,7 @@ def test_narrow_search(small):
         assert c[k] == octr[k], (k, c[k], octr[k])
     assert c["peptide_record_floats"] == octr["peptide_record_floats"] and c["pep_queries"] == 0
     sc2 = Scorer(gdb, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20))
+    sc2.set_option("pep_cap", 8192)
     sc2.score_batch(spectra)
     c2 = sc2.counters()
     assert c2["pep_queries"] == c2["queries"] and c2["pep_fallbacks"] == 0 and c2["matched_fragments"] == c["matched_fragments"]
@@ -186,7 +187,7 @@ def test_unsorted_peaks_fall_back_to_index_path(small):
         perm = rng.permutation(200)
         m[r], it[r] = m[r][perm], it[r][perm]
     shuffled = SpectraBatch(**{**sub.__dict__, "masses": m.ravel(), "intensities": it.ravel()})
-    sc, _, _ = run_both(odb, gdb, shuffled, pep_caps=(None,), precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), min_matched_peaks=1)
+    sc, _, _ = run_both(odb, gdb, shuffled, pep_caps=(2048,), precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), min_matched_peaks=1)
     assert sc.counters()["pep_fallbacks"] == 32
 
 
