@@ -153,11 +153,15 @@ def main():
     ap.add_argument("--impl", default="sage_b200", choices=["sage_b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spectra", type=int, default=0, help="override the number of spectra per GPU (profiling only; invalidates the metric)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.spectra:
+        wl["n_spectra"] = args.spectra
+        wl["desc"] += f" [PROFILING RUN: {args.spectra} spectra]"
     warmup = max(3, args.warmup)
     config = {"workload": f"{args.workload}: {wl['desc']}", "spectra_per_gpu": wl["n_spectra"], "peaks_per_spectrum": 200,
               "sharding": f"spectra sharded across {args.gpus} GPU(s), index replicated, no collective",

@@ -127,7 +127,8 @@ typedef struct { int32_t kind, charge, ordinal; float intensity, mz_calculated, 
 typedef struct {
     uint64_t spectra, peaks, queries, tasks /* (peak,fragment-charge) probes */, pages, entries_scanned, matched_fragments,
         candidates_scored, peptide_record_floats, psms, wide_queries,
-        pep_queries /* narrow queries counted peptide-centrically (pages/entries_scanned are then not visited) */, pep_fallbacks;
+        pep_queries /* narrow queries counted peptide-centrically (pages/entries_scanned are then not visited) */, pep_fallbacks,
+        wide_overflows /* open-search queries whose survivor list overflowed (replayed inside the counting kernel) */;
     uint64_t algorithmic_bytes;    /* SURVEY.md §8d formula, whole batch */
     uint64_t prelim_bytes;         /* the part of it the preliminary-scoring kernel(s) move */
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied across PCIe for the batch */

@@ -122,7 +122,7 @@ struct QueryHits {
 };
 
 // Device counters (u64 slots)
-enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_PEPQ, C_PEPFALLBACK, C_COUNT };
+enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_PEPQ, C_PEPFALLBACK, C_WSLOT, C_WOVERFLOW, C_COUNT };
 
 struct DbView {
     const uint2* frag;        // {peptide_index, fragment_mz bits}, reference bucket layout
@@ -154,6 +154,8 @@ struct ScorerView {
     uint32_t qmax;     // n_iso * n_ch_max query slots per spectrum
     uint32_t lcap;     // list capacity for merges
     uint32_t pep_cap;  // precursor windows up to this many peptides use the peptide-centric kernel path (0 = never)
+    uint32_t wide_tile;        // peptides per shared-memory tile of the wide kernel
+    uint32_t wide_lmax;        // survivor-list capacity per query (<= WIDE_LMAX; smaller only in tests)
     const double* lnfact_tab;  // lnfact(n) for n < lnfact_n, computed on the host with libm log (scoring.rs:170-177)
     uint32_t lnfact_n;
 };

@@ -359,22 +359,49 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
 }
 
 // --------------------------------------------------------------------------------------- preliminary scoring, wide
-// Persistent CTAs (one scratch slot each) pull wide queries from a work counter. Per query: zero the dense u16 count
-// array in the CTA's scratch (L2-resident for human-scale windows), resolve the page ranges of 256 probes at a time
-// (one per thread), then stream each [inner_left, inner_right) page slice with whole warps (coalesced 8-byte
-// loads, 4 in flight per lane), filter and count with half-word atomics, finally run the exact trim.
+// Open-search windows (> NARROW_CAP peptides; ±500 Da spans ~40 % of a human index) make the dense count array megabytes long.
+// Instead of a global scratch + L2/DRAM atomics, the window is processed in TILES of WIDE_TILE consecutive PeptideIx whose u16
+// counts live in shared memory (1 CTA / SM, ~200 KB). Inside a page entries are sorted by PeptideIx, so the part of a page slice
+// that belongs to a tile is a contiguous sub-slice: every page visit (peak, fragment charge, page) carries its position from
+// tile to tile (one binary search per visit and tile), whole warps stream the sub-slices with coalesced 8-byte loads (4 in
+// flight per lane), matches become shared-memory atomics, and after each tile the exact trim (heap replay in index order)
+// consumes the tile's counts straight from shared memory. Every index entry of [inner_left, inner_right) is read exactly once.
+constexpr int WIDE_THREADS = 512;
+constexpr uint32_t WIDE_TILE = 80 * 1024;    // peptides per tile (u16 counts: 160 KB)
+constexpr uint32_t WIDE_VMAX = 2048;         // page visits whose running position is cached in smem
+constexpr uint32_t WIDE_TCACHE = 2048;       // (peak, charge) probes whose bucket range is cached in smem
+constexpr uint32_t WIDE_LMAX = 12288;        // survivor keys kept per query for the replay kernel (overflow -> in-kernel serial replay)
+constexpr uint32_t WIDE_HLEV = 64;           // matched-count histogram levels (last level = ">= 63")
+struct WideSlot { uint32_t item, n_list, state /*0 = replay pending, 1 = finished in k_prelim_wide*/, k; };
 struct WideRange { uint64_t start; uint32_t len; float flo, fhi; };
 
-__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_wide(DbView db, ScorerView sc, BatchView b, uint32_t* scratch, uint64_t scratch_stride_words,
-                                                                 uint32_t n_items) {
-    __shared__ WideRange ranges[PRELIM_THREADS];
-    __shared__ uint64_t heap[K_MAX];
-    __shared__ uint64_t queue[PRELIM_THREADS];
-    __shared__ uint32_t s_warp[40];
-    __shared__ uint32_t s_nonzero, s_item;
+struct WideSmem {
+    uint32_t cnt32[WIDE_TILE / 2];
+    uint32_t cur[WIDE_VMAX];
+    uint32_t task_bl[WIDE_TCACHE];
+    uint16_t task_nb[WIDE_TCACHE];
+    WideRange ranges[WIDE_THREADS];
+    uint64_t heap[K_MAX];
+    uint64_t queue[2 * WIDE_THREADS];
+    uint32_t s_warp[40];
+    uint32_t hist[WIDE_HLEV];   // entries seen in earlier tiles with matched == level (level 63 = >= 63)
+    uint32_t s_item, s_slot, s_level, s_listn, s_serial;
+};
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = PRELIM_THREADS / 32;
-    uint32_t* cnt = scratch + (size_t)blockIdx.x * scratch_stride_words;
+// lower_bound over the PeptideIx column of a page sub-range: first e in [lo, hi) with slice[e].x >= key
+__device__ __forceinline__ uint32_t page_lower_bound(const uint2* slice, uint32_t lo, uint32_t hi, uint32_t key) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(&slice[mid].x) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, ScorerView sc, BatchView b, uint32_t n_items, uint64_t* wlist,
+                                                                   WideSlot* wslots) {
+    extern __shared__ __align__(16) unsigned char wide_raw[];
+    WideSmem& S = *reinterpret_cast<WideSmem*>(wide_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = WIDE_THREADS / 32;
     for (;;) {
         __syncthreads();
         if (tid == 0) {
@@ -383,98 +410,327 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_wide(DbView db, Score
                 it = (uint32_t)atomicAdd(b.counters + C_WORK, 1ull);
                 if (it >= n_items || b.queries[it].mode == 2) break;
             }
-            s_item = it;
+            S.s_item = it;
+            if (it < n_items) {
+                S.s_slot = (uint32_t)atomicAdd(b.counters + C_WSLOT, 1ull);
+                S.s_level = 1; S.s_listn = 0; S.s_serial = 0;
+            }
         }
+        if (tid < WIDE_HLEV) S.hist[tid] = 0;
         __syncthreads();
-        const uint32_t item = s_item;
+        const uint32_t item = S.s_item;
         if (item >= n_items) return;
+        uint64_t* const list = wlist + (size_t)S.s_slot * WIDE_LMAX;
         const QueryDesc q = b.queries[item];
         const uint32_t s = item / sc.qmax;
         const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
-        const uint32_t nwords = (q.potential + 1) >> 1;
-        for (uint32_t i = tid; i < nwords; i += PRELIM_THREADS) cnt[i] = 0;
-        __syncthreads();
-
         const uint32_t nfc = q.nfc, ntask = np * nfc;
-        uint32_t my_matched = 0, my_pages = 0, my_entries = 0;
-        for (uint32_t tbase = 0; tbase < ntask; tbase += PRELIM_THREADS) {
-            const uint32_t t = tbase + tid;
-            uint32_t bl = 0, br = 0;
-            float flo = 0.f, fhi = 0.f;
-            if (t < ntask) {
-                const uint32_t p = t / nfc, fc = t - p * nfc + 1;
-                const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);
-                tol_bounds(sc.fragment_tol, mass, flo, fhi);
-                const int klo = f32_key(flo), khi = f32_key(fhi);
-                binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
-                                    [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
-            }
-            for (uint32_t round = 0;; round++) {
-                const bool have = bl + round < br;
-                if (!__syncthreads_or(have)) break;
-                WideRange r;
-                r.start = 0; r.len = 0; r.flo = flo; r.fhi = fhi;
-                if (have) {
-                    const uint32_t page = bl + round;
-                    const uint64_t pbase = (uint64_t)page * db.bucket_size;
-                    const uint64_t pend = min(pbase + db.bucket_size, db.n_frag);
-                    const uint2* slice = db.frag + pbase;
-                    uint32_t il, ir;
-                    binary_search_slice((uint32_t)(pend - pbase), [&](uint32_t i) { return __ldg(&slice[i].x) < q.pre_lo; },
-                                        [&](uint32_t i) { return __ldg(&slice[i].x) <= q.pre_hi; }, il, ir);
-                    r.start = pbase + il;
-                    r.len = ir - il;
-                    my_pages++;
-                    my_entries += ir - il;
-                }
-                ranges[tid] = r;
-                __syncthreads();
-                for (uint32_t ri = warp; ri < PRELIM_THREADS; ri += nwarps) {
-                    const WideRange rr = ranges[ri];
-                    if (rr.len == 0) continue;
-                    const uint2* src = db.frag + rr.start;
-                    for (uint32_t e0 = 0; e0 < rr.len; e0 += 128) {
-                        uint2 f[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const uint32_t e = e0 + u * 32 + lane;
-                            f[u] = e < rr.len ? __ldg(src + e) : make_uint2(0xFFFFFFFFu, 0x7FC00000u);
+        const uint32_t n = q.potential;                       // dense slots of this window
+        const uint32_t k = min(n, sc.kparam);                 // n > NARROW_CAP > k here
+        const uint32_t TILE = sc.wide_tile;                   // <= WIDE_TILE (smaller only in tests, to exercise the multi-tile logic)
+        const uint32_t ntiles = (n + TILE - 1) / TILE;
+        uint32_t my_matched = 0, my_pages = 0, nz = 0;
+        long long my_entries = 0;
+
+        for (uint32_t tile = 0; tile < ntiles; tile++) {
+            const uint32_t d0 = tile * TILE;                               // first dense slot of the tile
+            const uint32_t dn = min(TILE, n - d0);                         // slots in the tile
+            const uint32_t pep_lo = q.pre_lo + d0;                         // PeptideIx of slot d0
+            const bool last_tile = tile + 1 == ntiles;
+            const bool tile_entered_serial = S.s_serial != 0;  // uniform: s_serial only changes between barriers at the end of a tile
+            // exclusive PeptideIx bound of the tile; the last tile ends at pre_hi + 1 so that its end == inner_right (database.rs:506-511)
+            const uint32_t pep_hi_excl = last_tile ? q.pre_hi + 1 : pep_lo + dn;
+            for (uint32_t i = tid; i < (dn + 1) / 2; i += WIDE_THREADS) S.cnt32[i] = 0;
+            __syncthreads();
+            for (uint32_t tbase = 0; tbase < ntask; tbase += WIDE_THREADS) {
+                const uint32_t t = tbase + tid;
+                uint32_t bl = 0, nb = 0;
+                float flo = 0.f, fhi = 0.f;
+                if (t < ntask) {
+                    const uint32_t p = t / nfc, fc = t - p * nfc + 1;
+                    const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
+                    tol_bounds(sc.fragment_tol, mass, flo, fhi);
+                    if (tile == 0 || t >= WIDE_TCACHE) {
+                        const int klo = f32_key(flo), khi = f32_key(fhi);
+                        uint32_t br;
+                        binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
+                                            [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
+                        nb = br - bl;
+                        if (t < WIDE_TCACHE) { S.task_bl[t] = bl; S.task_nb[t] = (uint16_t)min(nb, 0xFFFFu); }
+                        if (nb > 0xFFFFu && t < WIDE_TCACHE) S.task_nb[t] = 0xFFFF;  // (absurd tolerances) recomputed below
+                    } else {
+                        bl = S.task_bl[t];
+                        nb = S.task_nb[t];
+                        if (nb == 0xFFFFu) {
+                            const int klo = f32_key(flo), khi = f32_key(fhi);
+                            uint32_t br;
+                            binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
+                                                [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
+                            nb = br - bl;
                         }
+                    }
+                }
+                for (uint32_t round = 0;; round++) {
+                    const bool have = round < nb;
+                    if (!__syncthreads_or(have)) break;
+                    WideRange r;
+                    r.start = 0; r.len = 0; r.flo = flo; r.fhi = fhi;
+                    if (have) {
+                        const uint32_t page = bl + round;
+                        const uint64_t pbase = (uint64_t)page * db.bucket_size;
+                        const uint32_t pn = (uint32_t)(min(pbase + db.bucket_size, db.n_frag) - pbase);
+                        const uint2* slice = db.frag + pbase;
+                        const uint64_t vid64 = (uint64_t)round * ntask + t;
+                        const bool cached = vid64 < WIDE_VMAX;
+                        uint32_t start;
+                        if (tile == 0) {
+                            start = page_lower_bound(slice, 0, pn, q.pre_lo);            // partition_point(pep < pre_idx_lo)
+                            my_pages++;
+                            my_entries -= (long long)(start == 0 ? 0 : start - 1);       // inner_left = saturating_sub(.., 1)
+                        } else {
+                            start = cached ? S.cur[(uint32_t)vid64] : page_lower_bound(slice, 0, pn, pep_lo);
+                        }
+                        const uint32_t end = page_lower_bound(slice, start, pn, pep_hi_excl);
+                        if (cached) S.cur[(uint32_t)vid64] = end;
+                        if (last_tile) my_entries += (long long)end;                     // inner_right
+                        r.start = pbase + start;
+                        r.len = end - start;
+                    }
+                    S.ranges[tid] = r;
+                    __syncthreads();
+                    for (uint32_t ri = warp; ri < WIDE_THREADS; ri += nwarps) {
+                        const WideRange rr = S.ranges[ri];
+                        if (rr.len == 0) continue;
+                        const uint2* src = db.frag + rr.start;
+                        for (uint32_t e0 = 0; e0 < rr.len; e0 += 128) {
+                            uint2 f[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const float fmz = __uint_as_float(f[u].y);
-                            if (f[u].x >= q.eff_lo && f[u].x <= q.eff_hi && fmz >= rr.flo && fmz <= rr.fhi) {
-                                const uint32_t idx = f[u].x - q.pre_lo;
-                                atomicAdd(&cnt[idx >> 1], 1u << ((idx & 1) * 16));
-                                my_matched++;
+                            for (int u = 0; u < 4; u++) {
+                                const uint32_t e = e0 + u * 32 + lane;
+                                f[u] = e < rr.len ? __ldg(src + e) : make_uint2(0xFFFFFFFFu, 0x7FC00000u);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const float fmz = __uint_as_float(f[u].y);
+                                if (f[u].x >= q.eff_lo && f[u].x <= q.eff_hi && fmz >= rr.flo && fmz <= rr.fhi) {
+                                    const uint32_t idx = f[u].x - pep_lo;   // < dn by construction of the sub-slice
+                                    atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                                    my_matched++;
+                                }
                             }
                         }
+                    }
+                    __syncthreads();
+                }
+            }
+            __syncthreads();
+            // ---- trim, stage 1 (parallel): the heap replay itself is inherently serial (its ORDER is observable), so this CTA only
+            // emits, in dense order, the keys that can still enter the heap: the literal first k slots, then every slot whose matched
+            // count reaches `level` = the largest m with >= k earlier slots (previous tiles) having matched >= m  (such a key is
+            // preceded by k strictly greater keys, so bounded_min_heapify can never take it). k_replay_wide replays them, one
+            // thread per query. If a list overflows, this CTA replays it itself and continues serially (s_serial).
+            auto cnt = [&](uint32_t i) -> uint32_t { return (S.cnt32[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu; };
+            uint32_t scan_from = 0;
+            if (tile == 0) {
+                for (uint32_t i = tid; i < k; i += WIDE_THREADS) {
+                    const uint32_t c = cnt(i);
+                    nz += c != 0;
+                    if (c) atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
+                    list[i] = c ? prescore_key(c, q.pre_lo + i, q.charge, q.iso) : PRESCORE_DEFAULT;
+                }
+                if (tid == 0) S.s_listn = k;
+                scan_from = k;
+                __syncthreads();
+            }
+            if (!S.s_serial) {
+                const uint32_t level = S.s_level;
+                // each warp owns a contiguous segment (multiple of 64 slots); pass 1 counts survivors, pass 2 writes them in order
+                const uint32_t span = dn - scan_from;
+                const uint32_t seg = ((span + nwarps - 1) / nwarps + 63) & ~63u;
+                const uint32_t w_lo = scan_from + warp * seg, w_hi = min(dn, w_lo + seg);
+                uint32_t wcount = 0;
+                uint32_t lev[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 64) {
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const uint32_t i = i0 + 2 * lane + u;
+                        const uint32_t c = i < w_hi ? cnt(i) : 0;
+                        if (c) {
+                            nz++;
+                            if (c < 8) lev[c]++; else atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
+                            wcount += c >= level;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int l = 1; l < 8; l++) {
+                    uint32_t v = lev[l];
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                    if (lane == 0 && v) atomicAdd(&S.hist[l], v);
+                }
+                for (int o = 16; o > 0; o >>= 1) wcount += __shfl_down_sync(0xffffffffu, wcount, o);
+                if (lane == 0) S.s_warp[warp] = wcount;
+                __syncthreads();
+                uint32_t woff = S.s_listn, total = 0;
+                for (uint32_t w = 0; w < nwarps; w++) {
+                    const uint32_t x = S.s_warp[w];
+                    if (w < warp) woff += x;
+                    total += x;
+                }
+                const bool overflow = S.s_listn + total > sc.wide_lmax;
+                if (!overflow) {
+                    for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 64) {
+                        uint32_t c2[2];
+                        uint32_t mine = 0;
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            const uint32_t i = i0 + 2 * lane + u;
+                            c2[u] = i < w_hi ? cnt(i) : 0;
+                            if (c2[u] < level || c2[u] == 0) c2[u] = 0;
+                            mine += c2[u] != 0;
+                        }
+                        uint32_t incl = mine;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= (uint32_t)o) incl += v;
+                        }
+                        uint32_t pos = woff + incl - mine;
+#pragma unroll
+                        for (int u = 0; u < 2; u++)
+                            if (c2[u]) list[pos++] = prescore_key(c2[u], q.pre_lo + d0 + i0 + 2 * lane + u, q.charge, q.iso);
+                        woff += __shfl_sync(0xffffffffu, incl, 31);
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    if (!overflow) {
+                        S.s_listn += total;
+                        uint32_t acc = 0, lv = 1;  // new level: largest m >= 1 with #(matched >= m) >= k among the slots seen so far
+                        for (int l = WIDE_HLEV - 1; l >= 1; l--) {
+                            acc += S.hist[l];
+                            if (acc >= k) { lv = (uint32_t)l; break; }
+                        }
+                        S.s_level = lv;
+                    } else {
+                        // replay what was listed so far (heap.rs:7-28), then go serial for this tile and the rest of the query
+                        const uint32_t nl = S.s_listn;
+                        for (uint32_t i = 0; i < k; i++) S.heap[i] = list[i];
+                        for (uint32_t i = k / 2; i-- > 0;) sift_down(S.heap, k, i);
+                        for (uint32_t j = k; j < nl; j++) {
+                            const uint64_t kq = list[j];
+                            if (kq > S.heap[0]) { S.heap[0] = kq; sift_down(S.heap, k, 0); }
+                        }
+                        S.s_serial = 1;
+                        atomicAdd(b.counters + C_WOVERFLOW, 1ull);
                     }
                 }
                 __syncthreads();
             }
+            if (S.s_serial) {
+                const bool count_nz = tile_entered_serial;  // pass 1 above already counted this tile's non-zero slots otherwise
+                for (uint32_t base = scan_from; base < dn; base += 2 * WIDE_THREADS) {
+                    uint64_t key[2];
+                    uint32_t ncand = 0;
+                    const uint64_t hmin = S.heap[0];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const uint32_t i = base + 2 * tid + u;
+                        const uint32_t c = i < dn ? cnt(i) : 0;
+                        if (count_nz) nz += c != 0;
+                        const uint64_t kk = prescore_key(c, q.pre_lo + d0 + i, q.charge, q.iso);
+                        if (c != 0 && kk > hmin) key[ncand++] = kk;
+                    }
+                    if (__syncthreads_or(ncand != 0)) {
+                        uint32_t incl = ncand;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= (uint32_t)o) incl += v;
+                        }
+                        if (lane == 31) S.s_warp[warp] = incl;
+                        __syncthreads();
+                        uint32_t off = 0, total = 0;
+                        for (uint32_t w = 0; w < nwarps; w++) {
+                            const uint32_t x = S.s_warp[w];
+                            if (w < warp) off += x;
+                            total += x;
+                        }
+                        off += incl - ncand;
+                        for (uint32_t u = 0; u < ncand; u++) S.queue[off + u] = key[u];
+                        __syncthreads();
+                        if (tid == 0) {
+                            for (uint32_t j = 0; j < total; j++) {
+                                const uint64_t kq = S.queue[j];
+                                if (kq > S.heap[0]) { S.heap[0] = kq; sift_down(S.heap, k, 0); }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+            }
+            __syncthreads();
         }
-        const uint32_t matched_total = block_sum_u32(my_matched, s_warp);
-        const uint32_t pages_total = block_sum_u32(my_pages, s_warp);
-        const uint32_t entries_total = block_sum_u32(my_entries, s_warp);
+        const uint32_t matched_total = block_sum_u32(my_matched, S.s_warp);
+        const uint32_t pages_total = block_sum_u32(my_pages, S.s_warp);
+        const uint32_t nonzero_total = block_sum_u32(nz, S.s_warp);
+        // entries: sum of (inner_right - inner_left) over page visits; per-thread partial sums can be negative, total is not
+        long long ent = my_entries;
+        for (int o = 16; o > 0; o >>= 1) ent += __shfl_down_sync(0xffffffffu, ent, o);
+        if (lane == 0 && ent) atomicAdd(b.counters + C_ENTRIES, (unsigned long long)ent);
         if (tid == 0) {
             atomicAdd(b.counters + C_TASKS, (unsigned long long)ntask);
             atomicAdd(b.counters + C_PAGES, (unsigned long long)pages_total);
-            atomicAdd(b.counters + C_ENTRIES, (unsigned long long)entries_total);
             atomicAdd(b.counters + C_MATCHED, (unsigned long long)matched_total);
         }
         QueryHits* h = b.hits + item;
+        WideSlot* slot = wslots + S.s_slot;
         if (matched_total == 0) {
-            if (tid == 0) { h->n = 0; h->default_run = q.potential; h->matched_peaks = 0; h->scored_candidates = 0; }
+            if (tid == 0) {
+                h->n = 0; h->default_run = q.potential; h->matched_peaks = 0; h->scored_candidates = 0;
+                slot->item = item; slot->n_list = 0; slot->state = 1; slot->k = k;
+            }
             continue;
         }
-        const uint32_t k = min(q.potential, sc.kparam);
-        auto cntf = [&](uint32_t i) -> uint32_t { return (__ldcg(cnt + (i >> 1)) >> ((i & 1) * 16)) & 0xFFFFu; };
-        const uint32_t nout = trim_dense(cntf, q.potential, k, q.pre_lo, q.charge, q.iso, heap, queue, s_warp, &s_nonzero);
-        uint64_t* keys = b.hit_keys + (size_t)item * sc.kparam;
-        for (uint32_t i = tid; i < nout; i += PRELIM_THREADS) keys[i] = heap[i];
-        if (tid == 0) { h->n = nout; h->default_run = 0; h->matched_peaks = matched_total; h->scored_candidates = s_nonzero; }
+        if (S.s_serial) {
+            uint64_t* keys = b.hit_keys + (size_t)item * sc.kparam;
+            for (uint32_t i = tid; i < k; i += WIDE_THREADS) keys[i] = S.heap[i];
+        }
+        if (tid == 0) {
+            h->n = k; h->default_run = 0; h->matched_peaks = matched_total; h->scored_candidates = nonzero_total;
+            slot->item = item; slot->n_list = S.s_listn; slot->state = S.s_serial ? 1 : 0; slot->k = k;
+        }
     }
+}
+
+// trim, stage 2: bounded_min_heapify (heap.rs:7-28) over each query's survivor list, ONE THREAD PER QUERY so that the serial
+// replays of all open-search queries of the batch run concurrently. Heaps live in shared memory, interleaved by thread.
+constexpr int REPLAY_THREADS = 128;
+__global__ void __launch_bounds__(REPLAY_THREADS) k_replay_wide(ScorerView sc, BatchView b, const uint64_t* wlist, const WideSlot* wslots, uint32_t n_slots) {
+    extern __shared__ uint64_t rheap[];  // [kparam][REPLAY_THREADS]
+    const uint32_t slot = blockIdx.x * REPLAY_THREADS + threadIdx.x;
+    if (slot >= n_slots) return;
+    const WideSlot ws = wslots[slot];
+    if (ws.state != 0) return;
+    const uint64_t* list = wlist + (size_t)slot * WIDE_LMAX;
+    const uint32_t k = ws.k, tid = threadIdx.x;
+    auto H = [&](uint32_t i) -> uint64_t& { return rheap[i * REPLAY_THREADS + tid]; };
+    auto sift = [&](uint32_t index) {
+        while (index * 2 + 1 < k) {
+            uint32_t smallest = index, l = index * 2 + 1, r = index * 2 + 2;
+            if (H(l) < H(smallest)) smallest = l;
+            if (r < k && H(r) < H(smallest)) smallest = r;
+            if (smallest != index) { const uint64_t t = H(smallest); H(smallest) = H(index); H(index) = t; index = smallest; }
+            else break;
+        }
+    };
+    for (uint32_t i = 0; i < k; i++) H(i) = list[i];
+    for (uint32_t i = k / 2; i-- > 0;) sift(i);
+    uint64_t root = H(0);
+    for (uint32_t j = k; j < ws.n_list; j++) {
+        const uint64_t kq = __ldg(list + j);
+        if (kq > root) { H(0) = kq; sift(0); root = H(0); }
+    }
+    uint64_t* keys = b.hit_keys + (size_t)ws.item * sc.kparam;
+    for (uint32_t i = 0; i < k; i++) keys[i] = H(i);
 }
 
 // ------------------------------------------------------------------------------------------------ scoring

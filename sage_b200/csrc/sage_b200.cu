@@ -409,7 +409,7 @@ struct sage_b200_scorer {
     cudaEvent_t ev[8] = {};
     std::mutex mu;
     // device
-    DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_scratch, d_dbgk, d_dbgm, d_lnfact, d_sort, d_sorttmp;
+    DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_scratch, d_dbgk, d_dbgm, d_lnfact, d_sort, d_sorttmp, d_wlist, d_wslots;
     int sort_spectra = 1;
     // pinned staging
     PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
@@ -445,6 +445,8 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     if (v.n_iso > 32 || v.n_ch_max > 16) { delete s; return fail(SAGE_B200_ELIMIT, "isotope range > 32 or charge range > 16 not supported"); }
     v.qmax = std::max<uint32_t>(1, v.n_iso) * v.n_ch_max;
     v.lcap = std::max<uint32_t>(std::max<uint32_t>(v.n_iso, v.n_ch_max), 1) * v.kparam;
+    v.wide_tile = WIDE_TILE;
+    v.wide_lmax = WIDE_LMAX;
     v.pep_cap = 64;  // measured crossover on cfg2 (mean window 177 peptides): index probing wins above ~100 candidates
     if (const char* e = getenv("SAGE_B200_PEP_CAP")) v.pep_cap = (uint32_t)std::min<long>(std::max<long>(atol(e), 0), (long)NARROW_CAP);
     {   // lnfact table with the host libm (the reference's f64::ln): Stirling form of scoring.rs:170-177
@@ -473,6 +475,16 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
     if (!s || !name) return fail(SAGE_B200_EINVAL, "scorer_set_option: null argument");
     std::lock_guard<std::mutex> lock(s->mu);
     if (!strcmp(name, "sort_spectra")) { s->sort_spectra = value != 0; return 0; }
+    if (!strcmp(name, "wide_lmax")) {  // test hook: a tiny survivor list forces the overflow -> in-kernel serial replay path
+        if (value < (int64_t)K_MAX || value > (int64_t)WIDE_LMAX) return fail(SAGE_B200_EINVAL, "wide_lmax must be in %d..%u", K_MAX, WIDE_LMAX);
+        s->sv.wide_lmax = (uint32_t)value;
+        return 0;
+    }
+    if (!strcmp(name, "wide_tile")) {  // test hook: smaller tiles exercise the multi-tile path on small databases
+        if (value < 256 || value > (int64_t)WIDE_TILE || (value & 1)) return fail(SAGE_B200_EINVAL, "wide_tile must be even and in 256..%u", WIDE_TILE);
+        s->sv.wide_tile = (uint32_t)value;
+        return 0;
+    }
     if (!strcmp(name, "pep_cap")) {  // 0 = always probe the fragment index (reference loop order); default 64
         if (value < 0 || value > (int64_t)NARROW_CAP) return fail(SAGE_B200_EINVAL, "pep_cap must be 0..%u", NARROW_CAP);
         s->sv.pep_cap = (uint32_t)value;
@@ -484,7 +496,7 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
 extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
     if (!s) return;
     cudaSetDevice(s->db->device);
-    for (DevBuf* b : {&s->d_small, &s->d_masses, &s->d_intens, &s->d_queries, &s->d_hits, &s->d_keys, &s->d_features, &s->d_counts, &s->d_counters, &s->d_scratch, &s->d_dbgk, &s->d_dbgm, &s->d_lnfact, &s->d_sort, &s->d_sorttmp}) b->release();
+    for (DevBuf* b : {&s->d_small, &s->d_masses, &s->d_intens, &s->d_queries, &s->d_hits, &s->d_keys, &s->d_features, &s->d_counts, &s->d_counters, &s->d_scratch, &s->d_dbgk, &s->d_dbgm, &s->d_lnfact, &s->d_sort, &s->d_sorttmp, &s->d_wlist, &s->d_wslots}) b->release();
     for (PinBuf* b : {&s->h_small, &s->h_masses, &s->h_intens, &s->h_features, &s->h_counts, &s->h_counters}) b->release();
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -659,12 +671,19 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
         launches++;
     }
     if (n_wide) {
-        const uint64_t stride_words = align_up((max_pot + 2) / 2 + 1, 64);
-        const int ctas = (int)std::min<uint64_t>((uint64_t)S->wide_ctas, n_wide);
-        if ((rc = S->d_scratch.reserve(stride_words * 4 * (uint64_t)S->wide_ctas))) return rc;
-        k_prelim_wide<<<ctas, PRELIM_THREADS, 0, st>>>(db->v, sv, bv, S->d_scratch.as<uint32_t>(), stride_words, (uint32_t)C.nitems);
+        (void)max_pot;
+        const int ctas = (int)std::min<uint64_t>((uint64_t)db->sm_count, n_wide);
+        CUDA_TRY(cudaFuncSetAttribute(k_prelim_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WideSmem)));
+        if ((rc = S->d_wlist.reserve((size_t)n_wide * WIDE_LMAX * 8))) return rc;
+        if ((rc = S->d_wslots.reserve((size_t)n_wide * sizeof(WideSlot)))) return rc;
+        k_prelim_wide<<<ctas, WIDE_THREADS, sizeof(WideSmem), st>>>(db->v, sv, bv, (uint32_t)C.nitems, S->d_wlist.as<uint64_t>(), S->d_wslots.as<WideSlot>());
         CUDA_TRY(cudaGetLastError());
-        launches++;
+        const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
+        CUDA_TRY(cudaFuncSetAttribute(k_replay_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+        k_replay_wide<<<(unsigned)((n_wide + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, S->d_wlist.as<uint64_t>(),
+                                                                                                              S->d_wslots.as<WideSlot>(), (uint32_t)n_wide);
+        CUDA_TRY(cudaGetLastError());
+        launches += 2;
     }
     CUDA_TRY(cudaEventRecord(S->ev[3], st));
 
@@ -689,6 +708,7 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
     L.wide_queries += hc[C_WIDE];
     L.pep_queries += hc[C_PEPQ];
     L.pep_fallbacks += hc[C_PEPFALLBACK];
+    L.wide_overflows += hc[C_WOVERFLOW];
     L.d2h_bytes += 2 * 8 * C_COUNT;
     L.kernel_launches += launches;
     return 0;

