@@ -291,7 +291,7 @@ def main():
               "phases_ms_per_step": {"setup": setup_ms / args.steps, "prelim": prelim_ms / args.steps, "score": score_ms / args.steps,
                                      "resident_wall": wall_resident * 1000.0 / args.steps, "e2e_h2d": e2e_c["ms_h2d"], "e2e_d2h": e2e_c["ms_d2h"]},
               "work_per_step": {k: int(last[k]) for k in ("queries", "tasks", "pages", "entries_scanned", "matched_fragments", "candidates_scored", "psms",
-                                                          "algorithmic_bytes")},
+                                                          "algorithmic_bytes", "wide_queries", "wide_overflows", "pep_queries", "pep_fallbacks")},
               "psms_per_step_rank0": psms}
 
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:

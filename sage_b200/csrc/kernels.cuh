@@ -385,7 +385,7 @@ struct WideSmem {
     uint64_t queue[2 * WIDE_THREADS];
     uint32_t s_warp[40];
     uint32_t hist[WIDE_HLEV];   // entries seen in earlier tiles with matched == level (level 63 = >= 63)
-    uint32_t s_item, s_slot, s_level, s_listn, s_serial;
+    uint32_t s_item, s_slot, s_level, s_listn, s_serial, s_nranges;
 };
 
 // lower_bound over the PeptideIx column of a page sub-range: first e in [lo, hi) with slice[e].x >= key
@@ -428,13 +428,15 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         const uint32_t n = q.potential;                       // dense slots of this window
         const uint32_t k = min(n, sc.kparam);                 // n > NARROW_CAP > k here
         const uint32_t TILE = sc.wide_tile;                   // <= WIDE_TILE (smaller only in tests, to exercise the multi-tile logic)
-        const uint32_t ntiles = (n + TILE - 1) / TILE;
+        // two short leading tiles tighten the matched-count bound early (keeps the survivor lists short), then full tiles
+        const uint32_t T0 = max(TILE / 8, 256u) & ~7u, T1 = max(TILE / 4, 256u) & ~7u;
+        const uint32_t ntiles = n <= T0 ? 1 : (n <= T0 + T1 ? 2 : 2 + (n - T0 - T1 + TILE - 1) / TILE);
         uint32_t my_matched = 0, my_pages = 0, nz = 0;
         long long my_entries = 0;
 
         for (uint32_t tile = 0; tile < ntiles; tile++) {
-            const uint32_t d0 = tile * TILE;                               // first dense slot of the tile
-            const uint32_t dn = min(TILE, n - d0);                         // slots in the tile
+            const uint32_t d0 = tile == 0 ? 0 : (tile == 1 ? T0 : T0 + T1 + (tile - 2) * TILE);   // first dense slot of the tile
+            const uint32_t dn = min(tile == 0 ? T0 : (tile == 1 ? T1 : TILE), n - d0);            // slots in the tile
             const uint32_t pep_lo = q.pre_lo + d0;                         // PeptideIx of slot d0
             const bool last_tile = tile + 1 == ntiles;
             const bool tile_entered_serial = S.s_serial != 0;  // uniform: s_serial only changes between barriers at the end of a tile
@@ -496,26 +498,34 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                         r.start = pbase + start;
                         r.len = end - start;
                     }
-                    S.ranges[tid] = r;
+                    if (tid == 0) S.s_nranges = 0;
                     __syncthreads();
-                    for (uint32_t ri = warp; ri < WIDE_THREADS; ri += nwarps) {
-                        const WideRange rr = S.ranges[ri];
-                        if (rr.len == 0) continue;
-                        const uint2* src = db.frag + rr.start;
-                        for (uint32_t e0 = 0; e0 < rr.len; e0 += 128) {
-                            uint2 f[4];
+                    if (r.len) S.ranges[atomicAdd(&S.s_nranges, 1u)] = r;   // order is irrelevant for counting
+                    __syncthreads();
+                    // all threads walk the ranges together; 8 independent ranges (one 8-byte entry each per thread) are in flight at a
+                    // time, so a 512-thread CTA keeps 32 KB of index loads outstanding
+                    const uint32_t nr = S.s_nranges;
+                    for (uint32_t r0 = 0; r0 < nr; r0 += 8) {
+                        uint32_t maxlen = 0;
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const uint32_t e = e0 + u * 32 + lane;
-                                f[u] = e < rr.len ? __ldg(src + e) : make_uint2(0xFFFFFFFFu, 0x7FC00000u);
+                        for (int u = 0; u < 8; u++) maxlen = max(maxlen, r0 + u < nr ? S.ranges[r0 + u].len : 0u);
+                        for (uint32_t e = tid; e < maxlen; e += WIDE_THREADS) {
+                            uint2 f[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const bool ok = r0 + u < nr && e < S.ranges[r0 + u].len;
+                                f[u] = ok ? __ldg(db.frag + S.ranges[r0 + u].start + e) : make_uint2(0xFFFFFFFFu, 0x7FC00000u);
                             }
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
+                            for (int u = 0; u < 8; u++) {
                                 const float fmz = __uint_as_float(f[u].y);
-                                if (f[u].x >= q.eff_lo && f[u].x <= q.eff_hi && fmz >= rr.flo && fmz <= rr.fhi) {
-                                    const uint32_t idx = f[u].x - pep_lo;   // < dn by construction of the sub-slice
-                                    atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16));
-                                    my_matched++;
+                                if (f[u].x >= q.eff_lo && f[u].x <= q.eff_hi) {
+                                    const WideRange& rr = S.ranges[min(r0 + u, nr - 1)];
+                                    if (fmz >= rr.flo && fmz <= rr.fhi) {
+                                        const uint32_t idx = f[u].x - pep_lo;   // < dn by construction of the sub-slice
+                                        atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                                        my_matched++;
+                                    }
                                 }
                             }
                         }
@@ -544,18 +554,25 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
             }
             if (!S.s_serial) {
                 const uint32_t level = S.s_level;
-                // each warp owns a contiguous segment (multiple of 64 slots); pass 1 counts survivors, pass 2 writes them in order
-                const uint32_t span = dn - scan_from;
-                const uint32_t seg = ((span + nwarps - 1) / nwarps + 63) & ~63u;
-                const uint32_t w_lo = scan_from + warp * seg, w_hi = min(dn, w_lo + seg);
+                // each warp owns a contiguous segment (multiple of 256 slots, 8-aligned); a lane reads 8 slots with one 16-byte load.
+                // pass 1 counts survivors and feeds the histogram, pass 2 writes them in dense order
+                const uint32_t base0 = scan_from & ~7u;
+                const uint32_t span = dn - base0;
+                const uint32_t seg = ((span + nwarps - 1) / nwarps + 255) & ~255u;
+                const uint32_t w_lo = base0 + warp * seg, w_hi = min(dn, w_lo + seg);
+                const uint4* cnt128 = reinterpret_cast<const uint4*>(S.cnt32);
                 uint32_t wcount = 0;
                 uint32_t lev[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 64) {
+                for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 256) {
+                    const uint32_t i = i0 + 8 * lane;
+                    if (i >= w_hi) continue;
+                    const uint4 w4 = cnt128[i >> 3];
+                    if ((w4.x | w4.y | w4.z | w4.w) == 0) continue;
+                    const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const uint32_t i = i0 + 2 * lane + u;
-                        const uint32_t c = i < w_hi ? cnt(i) : 0;
-                        if (c) {
+                    for (int u = 0; u < 8; u++) {
+                        const uint32_t c = (ww[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu;
+                        if (c && i + u >= scan_from && i + u < dn) {
                             nz++;
                             if (c < 8) lev[c]++; else atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
                             wcount += c >= level;
@@ -578,17 +595,21 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                     total += x;
                 }
                 const bool overflow = S.s_listn + total > sc.wide_lmax;
-                if (!overflow) {
-                    for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 64) {
-                        uint32_t c2[2];
+                if (!overflow && S.s_warp[warp] != 0) {
+                    for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 256) {
+                        const uint32_t i = i0 + 8 * lane;
+                        uint32_t cc[8];
                         uint32_t mine = 0;
+                        uint4 w4 = make_uint4(0, 0, 0, 0);
+                        if (i < w_hi) w4 = cnt128[i >> 3];
+                        const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                        for (int u = 0; u < 2; u++) {
-                            const uint32_t i = i0 + 2 * lane + u;
-                            c2[u] = i < w_hi ? cnt(i) : 0;
-                            if (c2[u] < level || c2[u] == 0) c2[u] = 0;
-                            mine += c2[u] != 0;
+                        for (int u = 0; u < 8; u++) {
+                            const uint32_t c = (ww[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu;
+                            cc[u] = (c >= level && c != 0 && i + u >= scan_from && i + u < dn) ? c : 0;
+                            mine += cc[u] != 0;
                         }
+                        if (!__any_sync(0xffffffffu, mine != 0)) continue;
                         uint32_t incl = mine;
                         for (int o = 1; o < 32; o <<= 1) {
                             const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -596,8 +617,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                         }
                         uint32_t pos = woff + incl - mine;
 #pragma unroll
-                        for (int u = 0; u < 2; u++)
-                            if (c2[u]) list[pos++] = prescore_key(c2[u], q.pre_lo + d0 + i0 + 2 * lane + u, q.charge, q.iso);
+                        for (int u = 0; u < 8; u++)
+                            if (cc[u]) list[pos++] = prescore_key(cc[u], q.pre_lo + d0 + i + u, q.charge, q.iso);
                         woff += __shfl_sync(0xffffffffu, incl, 31);
                     }
                 }
