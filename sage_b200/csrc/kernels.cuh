@@ -375,17 +375,27 @@ constexpr uint32_t WIDE_HLEV = 64;           // matched-count histogram levels (
 struct WideSlot { uint32_t item, n_list, state /*0 = replay pending, 1 = finished in k_prelim_wide*/, k; };
 struct WideRange { uint64_t start; uint32_t len; float flo, fhi; };
 
-struct WideSmem {
-    uint32_t cnt32[WIDE_TILE / 2];
+constexpr uint32_t WIDE_VCAP = 1024;         // page visits per query handled by the boundary-table fast path
+constexpr uint32_t WIDE_BT = 16;             // boundary columns (tiles + 1) of the fast path
+struct WideSlow {                            // fallback: one search per (visit, tile), positions carried in `cur`
     uint32_t cur[WIDE_VMAX];
     uint32_t task_bl[WIDE_TCACHE];
     uint16_t task_nb[WIDE_TCACHE];
     WideRange ranges[WIDE_THREADS];
+};
+struct WideFast {                            // fast path: all tile boundaries of all page visits resolved once per query
+    uint16_t B[WIDE_VCAP * WIDE_BT];         // B[v*nb1 + t] = lower_bound(page(v), first PeptideIx of tile t); column ntiles = inner_right
+    uint32_t vpage[WIDE_VCAP];
+    float vflo[WIDE_VCAP], vfhi[WIDE_VCAP];
+};
+struct WideSmem {
+    uint32_t cnt32[WIDE_TILE / 2];
+    union { WideSlow slow; WideFast fast; } u;
     uint64_t heap[K_MAX];
     uint64_t queue[2 * WIDE_THREADS];
     uint32_t s_warp[40];
     uint32_t hist[WIDE_HLEV];   // entries seen in earlier tiles with matched == level (level 63 = >= 63)
-    uint32_t s_item, s_slot, s_level, s_listn, s_serial, s_nranges;
+    uint32_t s_item, s_slot, s_level, s_listn, s_serial, s_nranges, s_nvis, s_fast;
 };
 
 // lower_bound over the PeptideIx column of a page sub-range: first e in [lo, hi) with slice[e].x >= key
@@ -433,6 +443,51 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         const uint32_t ntiles = n <= T0 ? 1 : (n <= T0 + T1 ? 2 : 2 + (n - T0 - T1 + TILE - 1) / TILE);
         uint32_t my_matched = 0, my_pages = 0, nz = 0;
         long long my_entries = 0;
+        auto tile_d0 = [&](uint32_t t) -> uint32_t { return t == 0 ? 0 : (t == 1 ? T0 : T0 + T1 + (t - 2) * TILE); };
+
+        // ---- fast path setup: enumerate the page visits of every (peak, charge) probe and resolve all tile boundaries at once
+        const uint32_t nb1 = ntiles + 1;
+        if (tid == 0) { S.s_nvis = 0; S.s_fast = (nb1 <= WIDE_BT && db.bucket_size <= 65535u) ? 1u : 0u; }
+        __syncthreads();
+        if (S.s_fast) {
+            WideFast& F = S.u.fast;
+            for (uint32_t t = tid; t < ntask; t += WIDE_THREADS) {
+                const uint32_t p = t / nfc, fc = t - p * nfc + 1;
+                const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
+                float flo, fhi;
+                tol_bounds(sc.fragment_tol, mass, flo, fhi);
+                const int klo = f32_key(flo), khi = f32_key(fhi);
+                uint32_t bl, br;
+                binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
+                                    [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
+                const uint32_t nbk = br - bl;
+                if (nbk) {
+                    const uint32_t v0 = atomicAdd(&S.s_nvis, nbk);   // visit order is irrelevant for counting
+                    if (v0 + nbk <= WIDE_VCAP) {
+                        for (uint32_t r = 0; r < nbk; r++) { F.vpage[v0 + r] = bl + r; F.vflo[v0 + r] = flo; F.vfhi[v0 + r] = fhi; }
+                    } else S.s_fast = 0;
+                }
+            }
+            __syncthreads();
+        }
+        if (S.s_fast) {
+            WideFast& F = S.u.fast;
+            const uint32_t nvis = S.s_nvis;
+            for (uint32_t j = tid; j < nvis * nb1; j += WIDE_THREADS) {
+                const uint32_t v = j / nb1, t = j - v * nb1;
+                const uint64_t pbase = (uint64_t)F.vpage[v] * db.bucket_size;
+                const uint32_t pn = (uint32_t)(min(pbase + db.bucket_size, db.n_frag) - pbase);
+                const uint32_t key = t == ntiles ? q.pre_hi + 1 : q.pre_lo + tile_d0(t);
+                F.B[j] = (uint16_t)page_lower_bound(db.frag + pbase, 0, pn, key);
+            }
+            __syncthreads();
+            for (uint32_t v = tid; v < nvis; v += WIDE_THREADS) {   // SURVEY §8d counters: inner_right - inner_left per page visit
+                const uint32_t st = F.B[v * nb1], en = F.B[v * nb1 + ntiles];
+                my_entries += (long long)en - (long long)(st == 0 ? 0 : st - 1);
+                my_pages++;
+            }
+        }
+        const bool fast = S.s_fast != 0;
 
         for (uint32_t tile = 0; tile < ntiles; tile++) {
             const uint32_t d0 = tile == 0 ? 0 : (tile == 1 ? T0 : T0 + T1 + (tile - 2) * TILE);   // first dense slot of the tile
@@ -444,6 +499,44 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
             const uint32_t pep_hi_excl = last_tile ? q.pre_hi + 1 : pep_lo + dn;
             for (uint32_t i = tid; i < (dn + 1) / 2; i += WIDE_THREADS) S.cnt32[i] = 0;
             __syncthreads();
+            if (fast) {
+                // stream every visit's sub-slice of this tile: one warp walks two visits at a time, 4 coalesced 8-byte entries per lane
+                // from each (8 loads = 2 KB in flight per warp, 32 KB per CTA)
+                const WideFast& F = S.u.fast;
+                const uint32_t nvis = S.s_nvis;
+                for (uint32_t v0 = warp * 2; v0 < nvis; v0 += nwarps * 2) {
+                    const uint32_t v1 = min(v0 + 1, nvis - 1);
+                    const uint32_t stA = F.B[v0 * nb1 + tile], lnA = F.B[v0 * nb1 + tile + 1] - stA;
+                    const uint32_t stB = F.B[v1 * nb1 + tile], lnB = v0 + 1 < nvis ? F.B[v1 * nb1 + tile + 1] - stB : 0;
+                    const uint2* srcA = db.frag + (uint64_t)F.vpage[v0] * db.bucket_size + stA;
+                    const uint2* srcB = db.frag + (uint64_t)F.vpage[v1] * db.bucket_size + stB;
+                    const float floA = F.vflo[v0], fhiA = F.vfhi[v0], floB = F.vflo[v1], fhiB = F.vfhi[v1];
+                    const uint32_t mx = max(lnA, lnB);
+                    for (uint32_t e0 = 0; e0 < mx; e0 += 128) {
+                        uint2 fa[4], fb[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t e = e0 + u * 32 + lane;
+                            fa[u] = e < lnA ? __ldg(srcA + e) : make_uint2(0xFFFFFFFFu, 0x7FC00000u);
+                            fb[u] = e < lnB ? __ldg(srcB + e) : make_uint2(0xFFFFFFFFu, 0x7FC00000u);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const float ma = __uint_as_float(fa[u].y), mb = __uint_as_float(fb[u].y);
+                            if (fa[u].x >= q.eff_lo && fa[u].x <= q.eff_hi && ma >= floA && ma <= fhiA) {
+                                const uint32_t idx = fa[u].x - pep_lo;   // < dn by construction of the sub-slice
+                                atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                                my_matched++;
+                            }
+                            if (fb[u].x >= q.eff_lo && fb[u].x <= q.eff_hi && mb >= floB && mb <= fhiB) {
+                                const uint32_t idx = fb[u].x - pep_lo;
+                                atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                                my_matched++;
+                            }
+                        }
+                    }
+                }
+            } else
             for (uint32_t tbase = 0; tbase < ntask; tbase += WIDE_THREADS) {
                 const uint32_t t = tbase + tid;
                 uint32_t bl = 0, nb = 0;
@@ -458,11 +551,11 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                         binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
                                             [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
                         nb = br - bl;
-                        if (t < WIDE_TCACHE) { S.task_bl[t] = bl; S.task_nb[t] = (uint16_t)min(nb, 0xFFFFu); }
-                        if (nb > 0xFFFFu && t < WIDE_TCACHE) S.task_nb[t] = 0xFFFF;  // (absurd tolerances) recomputed below
+                        if (t < WIDE_TCACHE) { S.u.slow.task_bl[t] = bl; S.u.slow.task_nb[t] = (uint16_t)min(nb, 0xFFFFu); }
+                        if (nb > 0xFFFFu && t < WIDE_TCACHE) S.u.slow.task_nb[t] = 0xFFFF;  // (absurd tolerances) recomputed below
                     } else {
-                        bl = S.task_bl[t];
-                        nb = S.task_nb[t];
+                        bl = S.u.slow.task_bl[t];
+                        nb = S.u.slow.task_nb[t];
                         if (nb == 0xFFFFu) {
                             const int klo = f32_key(flo), khi = f32_key(fhi);
                             uint32_t br;
@@ -490,17 +583,17 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                             my_pages++;
                             my_entries -= (long long)(start == 0 ? 0 : start - 1);       // inner_left = saturating_sub(.., 1)
                         } else {
-                            start = cached ? S.cur[(uint32_t)vid64] : page_lower_bound(slice, 0, pn, pep_lo);
+                            start = cached ? S.u.slow.cur[(uint32_t)vid64] : page_lower_bound(slice, 0, pn, pep_lo);
                         }
                         const uint32_t end = page_lower_bound(slice, start, pn, pep_hi_excl);
-                        if (cached) S.cur[(uint32_t)vid64] = end;
+                        if (cached) S.u.slow.cur[(uint32_t)vid64] = end;
                         if (last_tile) my_entries += (long long)end;                     // inner_right
                         r.start = pbase + start;
                         r.len = end - start;
                     }
                     if (tid == 0) S.s_nranges = 0;
                     __syncthreads();
-                    if (r.len) S.ranges[atomicAdd(&S.s_nranges, 1u)] = r;   // order is irrelevant for counting
+                    if (r.len) S.u.slow.ranges[atomicAdd(&S.s_nranges, 1u)] = r;   // order is irrelevant for counting
                     __syncthreads();
                     // all threads walk the ranges together; 8 independent ranges (one 8-byte entry each per thread) are in flight at a
                     // time, so a 512-thread CTA keeps 32 KB of index loads outstanding
@@ -508,19 +601,19 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                     for (uint32_t r0 = 0; r0 < nr; r0 += 8) {
                         uint32_t maxlen = 0;
 #pragma unroll
-                        for (int u = 0; u < 8; u++) maxlen = max(maxlen, r0 + u < nr ? S.ranges[r0 + u].len : 0u);
+                        for (int u = 0; u < 8; u++) maxlen = max(maxlen, r0 + u < nr ? S.u.slow.ranges[r0 + u].len : 0u);
                         for (uint32_t e = tid; e < maxlen; e += WIDE_THREADS) {
                             uint2 f[8];
 #pragma unroll
                             for (int u = 0; u < 8; u++) {
-                                const bool ok = r0 + u < nr && e < S.ranges[r0 + u].len;
-                                f[u] = ok ? __ldg(db.frag + S.ranges[r0 + u].start + e) : make_uint2(0xFFFFFFFFu, 0x7FC00000u);
+                                const bool ok = r0 + u < nr && e < S.u.slow.ranges[r0 + u].len;
+                                f[u] = ok ? __ldg(db.frag + S.u.slow.ranges[r0 + u].start + e) : make_uint2(0xFFFFFFFFu, 0x7FC00000u);
                             }
 #pragma unroll
                             for (int u = 0; u < 8; u++) {
                                 const float fmz = __uint_as_float(f[u].y);
                                 if (f[u].x >= q.eff_lo && f[u].x <= q.eff_hi) {
-                                    const WideRange& rr = S.ranges[min(r0 + u, nr - 1)];
+                                    const WideRange& rr = S.u.slow.ranges[min(r0 + u, nr - 1)];
                                     if (fmz >= rr.flo && fmz <= rr.fhi) {
                                         const uint32_t idx = f[u].x - pep_lo;   // < dn by construction of the sub-slice
                                         atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16));
