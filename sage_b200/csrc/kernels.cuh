@@ -655,28 +655,35 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                 const uint32_t w_lo = base0 + warp * seg, w_hi = min(dn, w_lo + seg);
                 const uint4* cnt128 = reinterpret_cast<const uint4*>(S.cnt32);
                 uint32_t wcount = 0;
-                uint32_t lev[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                // branch-free SIMD-in-register pass over packed u16 pairs: non-zero slots (scored_candidates) and survivors (matched >= level).
+                // Only survivors feed the histogram: slots below `level` cannot raise it (level is monotone), so skipping them keeps the bound valid.
+                const uint32_t lvl2 = level | (level << 16);
                 for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 256) {
                     const uint32_t i = i0 + 8 * lane;
                     if (i >= w_hi) continue;
                     const uint4 w4 = cnt128[i >> 3];
                     if ((w4.x | w4.y | w4.z | w4.w) == 0) continue;
                     const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+                    const bool edge = i < scan_from || i + 8 > dn;   // first / last 16-byte group of the scanned range: mask slot by slot
+                    if (!edge) {
+                        uint32_t nzm = 0, svm = 0;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            nzm += __popc(__vcmpne2(ww[u], 0u));
+                            svm += __popc(__vcmpgeu2(ww[u], lvl2) & __vcmpne2(ww[u], 0u));
+                        }
+                        nz += nzm >> 4;
+                        wcount += svm >> 4;
+                        if (svm == 0) continue;
+                    }
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         const uint32_t c = (ww[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu;
                         if (c && i + u >= scan_from && i + u < dn) {
-                            nz++;
-                            if (c < 8) lev[c]++; else atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
-                            wcount += c >= level;
+                            if (edge) { nz++; wcount += c >= level; }
+                            if (c >= level) atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
                         }
                     }
-                }
-#pragma unroll
-                for (int l = 1; l < 8; l++) {
-                    uint32_t v = lev[l];
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                    if (lane == 0 && v) atomicAdd(&S.hist[l], v);
                 }
                 for (int o = 16; o > 0; o >>= 1) wcount += __shfl_down_sync(0xffffffffu, wcount, o);
                 if (lane == 0) S.s_warp[warp] = wcount;
@@ -696,6 +703,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                         uint4 w4 = make_uint4(0, 0, 0, 0);
                         if (i < w_hi) w4 = cnt128[i >> 3];
                         const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+                        uint32_t pre = 0;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) pre |= __vcmpgeu2(ww[u], lvl2) & __vcmpne2(ww[u], 0u);
+                        if (!__any_sync(0xffffffffu, pre != 0)) continue;
 #pragma unroll
                         for (int u = 0; u < 8; u++) {
                             const uint32_t c = (ww[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu;
