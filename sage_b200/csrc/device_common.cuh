@@ -14,6 +14,7 @@ constexpr uint32_t NARROW_CAP = 8192; // precursor windows up to this many pepti
 constexpr int PRELIM_THREADS = 256;
 constexpr int SCORE_THREADS = 256;
 constexpr int MAX_KINDS = 6;
+constexpr uint32_t BUCKET_LUT_CELLS = 4096;
 
 // mass.rs:5-8
 constexpr float PROTON = 1.0072764f;
@@ -137,6 +138,11 @@ struct DbView {
     uint32_t min_ion_index;   // fragments in the index are ions with index > min_ion_index (database.rs:281-291)
     uint32_t pep_centric_ok;  // index content verified == ions filtered by min_ion_index (peptide-centric counting allowed)
     uint32_t nterm_mask;      // bit k set when ion kind k is an N-terminal series (a/b/c)
+    // search directories (results identical to the plain binary searches; nullptr = not built)
+    const uint16_t* page_grid;  // [n_bucket][grid_n + 1]: page_grid[p][g] = #{entries of page p with PeptideIx < (g << grid_shift)}
+    uint32_t grid_shift, grid_n;
+    const uint32_t* bucket_lut; // [BUCKET_LUT_CELLS]: #{bucket_min < edge(c)}, conservative start for the bucket search
+    float blut_base, blut_inv_w;
     uint64_t n_frag;
     uint8_t kinds[MAX_KINDS];
 };

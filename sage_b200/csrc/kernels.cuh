@@ -196,6 +196,41 @@ __device__ __forceinline__ uint32_t lut_start(const LutParams& L, const uint16_t
     return start[c];
 }
 
+// binary_search_slice(min_value, flo, fhi) (database.rs:487-492) -> [left, right) pages; uses the m/z LUT when built.
+__device__ __forceinline__ void bucket_range(const DbView& db, float flo, float fhi, uint32_t& left, uint32_t& right) {
+    if (db.bucket_lut == nullptr) {
+        const int klo = f32_key(flo), khi = f32_key(fhi);
+        binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
+                            [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, left, right);
+        return;
+    }
+    // bucket_min holds positive finite m/z values, so float compares equal total_cmp here
+    const float t = (flo - db.blut_base) * db.blut_inv_w;
+    const int c = t > 1.0f ? (int)fminf(t, (float)(BUCKET_LUT_CELLS - 1)) - 1 : 0;
+    uint32_t pp = __ldg(db.bucket_lut + c);                               // <= partition_point(min < flo)
+    while (pp < db.n_bucket && __ldg(db.bucket_min + pp) < flo) pp++;
+    left = pp == 0 ? 0 : pp - 1;
+    uint32_t r = left;
+    while (r < db.n_bucket && __ldg(db.bucket_min + r) <= fhi) r++;
+    right = r;
+}
+
+// partition_point(|e| e.peptide_index < key) inside one page; uses the per-page PeptideIx grid when built.
+__device__ __forceinline__ uint32_t page_lower_bound_dir(const DbView& db, uint32_t page, const uint2* slice, uint32_t pn, uint32_t key) {
+    uint32_t lo = 0, hi = pn;
+    if (db.page_grid != nullptr) {
+        const uint32_t g = min(key >> db.grid_shift, db.grid_n - 1);
+        const uint16_t* G = db.page_grid + (size_t)page * (db.grid_n + 1) + g;
+        lo = __ldg(G);
+        hi = (key >> db.grid_shift) >= db.grid_n ? pn : (uint32_t)__ldg(G + 1);
+    }
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(&slice[mid].x) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 // ------------------------------------------------------------------------------------- preliminary scoring, narrow
 // One CTA per (spectrum, query); the dense per-window counts live in shared memory. Two interchangeable ways to fill them
 // (identical counts: the matched set is {fragment in index : mz in [flo,fhi](peak*charge), PeptideIx in [eff_lo,eff_hi]}):
@@ -310,22 +345,21 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
             const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
             float flo, fhi;
             tol_bounds(sc.fragment_tol, mass, flo, fhi);
-            const int klo = f32_key(flo), khi = f32_key(fhi);
             uint32_t bl, br;
-            binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
-                                [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
+            bucket_range(db, flo, fhi, bl, br);
             for (uint32_t page = bl; page < br; page++) {
                 const uint64_t pbase = (uint64_t)page * db.bucket_size;
                 const uint64_t pend = min(pbase + db.bucket_size, db.n_frag);
                 const uint2* slice = db.frag + pbase;
                 const uint32_t pn = (uint32_t)(pend - pbase);
-                uint32_t il, ir;
-                binary_search_slice(pn, [&](uint32_t i) { return __ldg(&slice[i].x) < q.pre_lo; }, [&](uint32_t i) { return __ldg(&slice[i].x) <= q.pre_hi; },
-                                    il, ir);
-                my_pages++;
-                my_entries += ir - il;
-                for (uint32_t e = il; e < ir; e++) {
+                // inner_left = partition_point(pep < pre_lo).saturating_sub(1); then walk forward: the walk ends exactly at
+                // inner_right = inner_left + partition_point(pep <= pre_hi) (database.rs:506-511), no second search needed
+                const uint32_t pp = page_lower_bound_dir(db, page, slice, pn, q.pre_lo);
+                const uint32_t il = pp == 0 ? 0 : pp - 1;
+                uint32_t e = il;
+                for (; e < pn; e++) {
                     const uint2 f = __ldg(&slice[e]);
+                    if (f.x > q.pre_hi) break;
                     const float fmz = __uint_as_float(f.y);
                     if (f.x >= q.eff_lo && f.x <= q.eff_hi && fmz >= flo && fmz <= fhi) {
                         const uint32_t idx = f.x - q.pre_lo;
@@ -333,6 +367,8 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
                         my_matched++;
                     }
                 }
+                my_pages++;
+                my_entries += e - il;
             }
         }
     }
@@ -456,10 +492,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                 const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
                 float flo, fhi;
                 tol_bounds(sc.fragment_tol, mass, flo, fhi);
-                const int klo = f32_key(flo), khi = f32_key(fhi);
                 uint32_t bl, br;
-                binary_search_slice(db.n_bucket, [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) < klo; },
-                                    [&](uint32_t i) { return f32_key(__ldg(db.bucket_min + i)) <= khi; }, bl, br);
+                bucket_range(db, flo, fhi, bl, br);
                 const uint32_t nbk = br - bl;
                 if (nbk) {
                     const uint32_t v0 = atomicAdd(&S.s_nvis, nbk);   // visit order is irrelevant for counting
@@ -478,7 +512,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                 const uint64_t pbase = (uint64_t)F.vpage[v] * db.bucket_size;
                 const uint32_t pn = (uint32_t)(min(pbase + db.bucket_size, db.n_frag) - pbase);
                 const uint32_t key = t == ntiles ? q.pre_hi + 1 : q.pre_lo + tile_d0(t);
-                F.B[j] = (uint16_t)page_lower_bound(db.frag + pbase, 0, pn, key);
+                F.B[j] = (uint16_t)page_lower_bound_dir(db, F.vpage[v], db.frag + pbase, pn, key);
             }
             __syncthreads();
             for (uint32_t v = tid; v < nvis; v += WIDE_THREADS) {   // SURVEY §8d counters: inner_right - inner_left per page visit
@@ -1360,6 +1394,31 @@ __global__ void k_bucket_keys(uint64_t n_frag, uint32_t bucket_shift, const uint
     key64[i] = (bucket << 32) | pep_sorted[i];
     if ((i & ((1ull << bucket_shift) - 1)) == 0) bucket_min[bucket] = __uint_as_float(bits);
 }
+// Search directories. page_grid[p][g] = #{entries of page p with PeptideIx < g << shift} (g = 0..grid_n), bucket_lut[c] = #{bucket_min < edge(c)}.
+__global__ void k_build_page_grid(DbView db, uint32_t grid_shift, uint32_t grid_n, uint16_t* grid) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)db.n_bucket * (grid_n + 1);
+    if (j >= total) return;
+    const uint32_t page = (uint32_t)(j / (grid_n + 1)), g = (uint32_t)(j - (uint64_t)page * (grid_n + 1));
+    const uint64_t pbase = (uint64_t)page * db.bucket_size;
+    const uint32_t pn = (uint32_t)(min(pbase + db.bucket_size, db.n_frag) - pbase);
+    const uint64_t key64 = (uint64_t)g << grid_shift;
+    uint32_t pos = pn;
+    if (key64 <= 0xFFFFFFFFull) pos = page_lower_bound(db.frag + pbase, 0, pn, (uint32_t)key64);
+    grid[j] = (uint16_t)pos;
+}
+__global__ void k_build_bucket_lut(DbView db, float base, float inv_w, uint32_t* lut) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= BUCKET_LUT_CELLS) return;
+    uint32_t lo = 0;
+    if (c > 0 && inv_w > 0.0f) {
+        const float e = base + (float)c * (1.0f / inv_w);
+        uint32_t hi = db.n_bucket;
+        while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (db.bucket_min[m] < e) lo = m + 1; else hi = m; }
+    }
+    lut[c] = lo;
+}
+
 // Verifies that an uploaded index is exactly {ions with index > min_ion_index}: per peptide, fragment count and the wrapped sum
 // of m/z bit patterns must match what k_gen would emit. acc[2p] = count, acc[2p+1] = sum.
 __global__ void k_index_signature(uint64_t n_frag, const uint2* frag, uint32_t n_pep, uint32_t* acc) {

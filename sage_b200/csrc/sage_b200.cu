@@ -101,6 +101,7 @@ static bool is_pinned(const void* p) {
 struct sage_b200_db {
     int device = 0;
     DbView v{};
+    void *d_page_grid = nullptr, *d_bucket_lut = nullptr;
     void *d_frag = nullptr, *d_bucket_min = nullptr, *d_pep_mono = nullptr, *d_ion_off = nullptr, *d_ions = nullptr, *d_pep_len = nullptr,
          *d_pep_flags = nullptr, *d_pep_missed = nullptr;
     uint64_t total_residues = 0, device_bytes = 0;
@@ -219,10 +220,44 @@ extern "C" int sage_b200_device_count(void) {
 extern "C" void sage_b200_db_destroy(sage_b200_db* db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    void* ps[] = {db->d_frag, db->d_bucket_min, db->d_pep_mono, db->d_ion_off, db->d_ions, db->d_pep_len, db->d_pep_flags, db->d_pep_missed};
+    void* ps[] = {db->d_page_grid, db->d_bucket_lut, db->d_frag, db->d_bucket_min, db->d_pep_mono, db->d_ion_off, db->d_ions, db->d_pep_len, db->d_pep_flags, db->d_pep_missed};
     for (void* p : ps)
         if (p) cudaFree(p);
     delete db;
+}
+
+// Search directories over the finished index (see DbView). Skipped (plain binary searches are used) when the shapes do not fit.
+static int db_build_directories(sage_b200_db* db) {
+    DbView& v = db->v;
+    v.page_grid = nullptr; v.bucket_lut = nullptr;
+    if (v.n_frag == 0 || v.n_bucket == 0 || v.n_pep == 0 || (getenv("SAGE_B200_NO_DIRECTORIES") && getenv("SAGE_B200_NO_DIRECTORIES")[0] == '1')) return 0;
+    int rc;
+    if (v.bucket_size <= 65535u) {
+        uint32_t shift = 0;
+        while (((uint64_t)v.n_pep >> shift) >= 256) shift++;
+        const uint32_t gn = (uint32_t)(((uint64_t)v.n_pep - 1) >> shift) + 1;   // cells 0..gn-1 cover every PeptideIx
+        const uint64_t total = (uint64_t)v.n_bucket * (gn + 1);
+        if ((rc = dmalloc(db, &db->d_page_grid, 2 * total))) return rc;
+        k_build_page_grid<<<(unsigned)((total + 255) / 256), 256>>>(v, shift, gn, (uint16_t*)db->d_page_grid);
+        CUDA_TRY(cudaGetLastError());
+        v.grid_shift = shift; v.grid_n = gn;
+    }
+    float ends[2] = {0.f, 0.f};
+    CUDA_TRY(cudaMemcpy(&ends[0], db->d_bucket_min, 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&ends[1], (const float*)db->d_bucket_min + (v.n_bucket - 1), 4, cudaMemcpyDeviceToHost));
+    bool lut_ok = ends[0] > 0.0f && std::isfinite(ends[0]) && std::isfinite(ends[1]);   // positive finite m/z: float order == total_cmp order
+    if (lut_ok) {
+        const float w = (ends[1] - ends[0]) / (float)BUCKET_LUT_CELLS;
+        const float inv_w = (w > 0.0f && w < 3.0e38f) ? 1.0f / w : 0.0f;
+        if ((rc = dmalloc(db, &db->d_bucket_lut, 4 * BUCKET_LUT_CELLS))) return rc;
+        k_build_bucket_lut<<<BUCKET_LUT_CELLS / 256, 256>>>(v, ends[0], inv_w, (uint32_t*)db->d_bucket_lut);
+        CUDA_TRY(cudaGetLastError());
+        v.blut_base = ends[0]; v.blut_inv_w = inv_w;
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (db->d_page_grid) v.page_grid = (const uint16_t*)db->d_page_grid;
+    if (lut_ok) v.bucket_lut = (const uint32_t*)db->d_bucket_lut;
+    return 0;
 }
 
 extern "C" int sage_b200_db_create(const sage_b200_peptides* peptides, const sage_b200_index* index, int device, sage_b200_db** out) {
@@ -288,6 +323,7 @@ extern "C" int sage_b200_db_create(const sage_b200_peptides* peptides, const sag
             if (mismatch == 0) { db->v.min_ion_index = (uint32_t)found; db->v.pep_centric_ok = 1; }
         }
     }
+    if ((rc = db_build_directories(db))) { sage_b200_db_destroy(db); return rc; }
     *out = db;
     return 0;
 }
@@ -362,6 +398,7 @@ extern "C" int sage_b200_db_build(const sage_b200_peptides* peptides, uint64_t b
     TRY_BUILD(cudaDeviceSynchronize());
     cleanup();
 #undef TRY_BUILD
+    if ((rc = db_build_directories(db))) { sage_b200_db_destroy(db); return rc; }
     *out = db;
     return 0;
 }
