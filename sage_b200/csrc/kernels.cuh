@@ -14,7 +14,7 @@ namespace sb {
 // ------------------------------------------------------------------------------------------------ setup
 // One thread per spectrum: enumerate the (charge, isotope) queries of Scorer::initial_hits and resolve each
 // precursor window to a PeptideIx range (two binary searches over peptides[].monoisotopic).
-__global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t* sort_key, uint32_t* sort_val) {
+__global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t* sort_key, uint32_t* sort_val, uint32_t* list_cap) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n) return;
     const float pmz = b.prec_mz[s];
@@ -61,6 +61,7 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
             q.nfc = (uint8_t)(mfc - 1);
             q.mode = q.potential > NARROW_CAP ? 2 : ((db.pep_centric_ok && q.potential <= sc.pep_cap) ? 3 : 1);
             out[qi] = q;
+            if (list_cap) list_cap[(size_t)s * sc.qmax + qi] = (q.mode == 1 || q.mode == 3) ? q.potential : 0;
             nq++;
             if (q.mode == 2) nwide++;
             if (q.mode == 3) npepq++;
@@ -70,6 +71,7 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
     for (; qi < sc.qmax; qi++) {
         QueryDesc q = {};
         out[qi] = q;
+        if (list_cap) list_cap[(size_t)s * sc.qmax + qi] = 0;
     }
     if (sort_key) { sort_key[s] = out[0].mode ? out[0].pre_lo : 0xFFFFFFFFu; sort_val[s] = s; }
     if (nq) atomicAdd(b.counters + C_QUERIES, nq);
@@ -242,7 +244,8 @@ __device__ __forceinline__ uint32_t page_lower_bound_dir(const DbView& db, uint3
 //    interval contains its fragment with two binary searches over per-charge LO/HI bound arrays staged in shared memory
 //    (bounds computed with the reference's f32 ops; both arrays are monotone in the peak mass, which is verified per
 //    spectrum — otherwise the CTA falls back to the index path).
-__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b, uint32_t pmax) {
+__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b, uint32_t pmax, uint64_t* nlist,
+                                                                  const uint32_t* nlist_off, ReplaySlot* nslots) {
     __shared__ uint32_t cnt32[NARROW_CAP / 2 + 1];
     __shared__ uint64_t heap[K_MAX];
     __shared__ uint64_t queue[PRELIM_THREADS];
@@ -253,7 +256,10 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
     const uint32_t s = b.order ? b.order[blockIdx.x / sc.qmax] : blockIdx.x / sc.qmax;
     const uint32_t item = s * sc.qmax + blockIdx.x % sc.qmax;
     const QueryDesc q = b.queries[item];
-    if (q.mode != 1 && q.mode != 3) return;
+    if (q.mode != 1 && q.mode != 3) {
+        if (threadIdx.x == 0) { nslots[item].off = 0; nslots[item].item = item; nslots[item].n_list = 0; nslots[item].state = 1; nslots[item].k = 0; }
+        return;
+    }
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = PRELIM_THREADS / 32;
     const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
     const uint32_t nwords = (q.potential + 1) >> 1;
@@ -383,15 +389,61 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
     }
     QueryHits* h = b.hits + item;
     if (matched_total == 0) {  // scoring.rs:376-378 returns the untrimmed all-default Vec
-        if (tid == 0) { h->n = 0; h->default_run = q.potential; h->matched_peaks = 0; h->scored_candidates = 0; }
+        if (tid == 0) {
+            h->n = 0; h->default_run = q.potential; h->matched_peaks = 0; h->scored_candidates = 0;
+            nslots[item].off = 0; nslots[item].item = item; nslots[item].n_list = 0; nslots[item].state = 1; nslots[item].k = 0;
+        }
         return;
     }
-    const uint32_t k = min(q.potential, sc.kparam);
+    // trim_hits (scoring.rs:322-329), stage 1: emit the keys in dense order — the literal first k slots, then every later slot with
+    // matched > 0 (zeros can never displace the heap root). k_replay performs the exact heap replay, one thread per query.
+    const uint32_t n = q.potential, k = min(n, sc.kparam);
     auto cnt = [&](uint32_t i) -> uint32_t { return (cnt32[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu; };
-    const uint32_t nout = trim_dense(cnt, q.potential, k, q.pre_lo, q.charge, q.iso, heap, queue, s_warp, &s_nonzero);
-    uint64_t* keys = b.hit_keys + (size_t)item * sc.kparam;
-    for (uint32_t i = tid; i < nout; i += PRELIM_THREADS) keys[i] = heap[i];
-    if (tid == 0) { h->n = nout; h->default_run = 0; h->matched_peaks = matched_total; h->scored_candidates = s_nonzero; }
+    ReplaySlot* slot = nslots + item;
+    uint32_t nzc = 0;
+    if (n <= k) {   // nothing to trim: the dense order is the result
+        uint64_t* keys = b.hit_keys + (size_t)item * sc.kparam;
+        for (uint32_t i = tid; i < n; i += PRELIM_THREADS) {
+            const uint32_t c = cnt(i);
+            nzc += c != 0;
+            keys[i] = c ? prescore_key(c, q.pre_lo + i, q.charge, q.iso) : PRESCORE_DEFAULT;
+        }
+        const uint32_t nzt = block_sum_u32(nzc, s_warp);
+        if (tid == 0) {
+            h->n = n; h->default_run = 0; h->matched_peaks = matched_total; h->scored_candidates = nzt;
+            slot->off = 0; slot->item = item; slot->n_list = 0; slot->state = 1; slot->k = k;
+        }
+        return;
+    }
+    uint64_t* list = nlist + nlist_off[item];
+    for (uint32_t i = tid; i < k; i += PRELIM_THREADS) {
+        const uint32_t c = cnt(i);
+        nzc += c != 0;
+        list[i] = c ? prescore_key(c, q.pre_lo + i, q.charge, q.iso) : PRESCORE_DEFAULT;
+    }
+    uint32_t wbase = k;   // next free list position (uniform across the CTA)
+    for (uint32_t base = k; base < n; base += PRELIM_THREADS) {
+        const uint32_t i = base + tid;
+        const uint32_t c = i < n ? cnt(i) : 0;
+        nzc += c != 0;
+        const uint32_t ball = __ballot_sync(0xffffffffu, c != 0);
+        if (lane == 0) s_warp[warp] = __popc(ball);
+        __syncthreads();
+        uint32_t off = 0, total = 0;
+        for (uint32_t w = 0; w < nwarps; w++) {
+            const uint32_t x = s_warp[w];
+            if (w < warp) off += x;
+            total += x;
+        }
+        if (c) list[wbase + off + __popc(ball & ((1u << lane) - 1))] = prescore_key(c, q.pre_lo + i, q.charge, q.iso);
+        wbase += total;
+        __syncthreads();
+    }
+    const uint32_t nzt = block_sum_u32(nzc, s_warp);
+    if (tid == 0) {
+        h->n = k; h->default_run = 0; h->matched_peaks = matched_total; h->scored_candidates = nzt;
+        slot->off = nlist_off[item]; slot->item = item; slot->n_list = wbase; slot->state = 0; slot->k = k;
+    }
 }
 
 // --------------------------------------------------------------------------------------- preliminary scoring, wide
@@ -408,7 +460,7 @@ constexpr uint32_t WIDE_VMAX = 2048;         // page visits whose running positi
 constexpr uint32_t WIDE_TCACHE = 2048;       // (peak, charge) probes whose bucket range is cached in smem
 constexpr uint32_t WIDE_LMAX = 12288;        // survivor keys kept per query for the replay kernel (overflow -> in-kernel serial replay)
 constexpr uint32_t WIDE_HLEV = 64;           // matched-count histogram levels (last level = ">= 63")
-struct WideSlot { uint32_t item, n_list, state /*0 = replay pending, 1 = finished in k_prelim_wide*/, k; };
+typedef ReplaySlot WideSlot;
 struct WideRange { uint64_t start; uint32_t len; float flo, fhi; };
 
 constexpr uint32_t WIDE_VCAP = 1024;         // page visits per query handled by the boundary-table fast path
@@ -467,6 +519,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         const uint32_t item = S.s_item;
         if (item >= n_items) return;
         uint64_t* const list = wlist + (size_t)S.s_slot * WIDE_LMAX;
+        const unsigned long long list_off = (unsigned long long)S.s_slot * WIDE_LMAX;
         const QueryDesc q = b.queries[item];
         const uint32_t s = item / sc.qmax;
         const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
@@ -845,7 +898,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         if (matched_total == 0) {
             if (tid == 0) {
                 h->n = 0; h->default_run = q.potential; h->matched_peaks = 0; h->scored_candidates = 0;
-                slot->item = item; slot->n_list = 0; slot->state = 1; slot->k = k;
+                slot->off = list_off; slot->item = item; slot->n_list = 0; slot->state = 1; slot->k = k;
             }
             continue;
         }
@@ -855,21 +908,22 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         }
         if (tid == 0) {
             h->n = k; h->default_run = 0; h->matched_peaks = matched_total; h->scored_candidates = nonzero_total;
-            slot->item = item; slot->n_list = S.s_listn; slot->state = S.s_serial ? 1 : 0; slot->k = k;
+            slot->off = list_off; slot->item = item; slot->n_list = S.s_listn; slot->state = S.s_serial ? 1 : 0; slot->k = k;
         }
     }
 }
 
-// trim, stage 2: bounded_min_heapify (heap.rs:7-28) over each query's survivor list, ONE THREAD PER QUERY so that the serial
-// replays of all open-search queries of the batch run concurrently. Heaps live in shared memory, interleaved by thread.
+// trim, stage 2: bounded_min_heapify (heap.rs:7-28) over each query's ordered key list, ONE THREAD PER QUERY, so that the inherently
+// serial replays (their result ORDER is observable) of all queries of the batch run concurrently instead of stalling a whole CTA each.
+// Heaps live in shared memory, interleaved by thread. Used by both preliminary-scoring kernels.
 constexpr int REPLAY_THREADS = 128;
-__global__ void __launch_bounds__(REPLAY_THREADS) k_replay_wide(ScorerView sc, BatchView b, const uint64_t* wlist, const WideSlot* wslots, uint32_t n_slots) {
+__global__ void __launch_bounds__(REPLAY_THREADS) k_replay(ScorerView sc, BatchView b, const uint64_t* lists, const ReplaySlot* slots, uint32_t n_slots) {
     extern __shared__ uint64_t rheap[];  // [kparam][REPLAY_THREADS]
     const uint32_t slot = blockIdx.x * REPLAY_THREADS + threadIdx.x;
     if (slot >= n_slots) return;
-    const WideSlot ws = wslots[slot];
+    const ReplaySlot ws = slots[slot];
     if (ws.state != 0) return;
-    const uint64_t* list = wlist + (size_t)slot * WIDE_LMAX;
+    const uint64_t* list = lists + ws.off;
     const uint32_t k = ws.k, tid = threadIdx.x;
     auto H = [&](uint32_t i) -> uint64_t& { return rheap[i * REPLAY_THREADS + tid]; };
     auto sift = [&](uint32_t index) {
@@ -881,7 +935,7 @@ __global__ void __launch_bounds__(REPLAY_THREADS) k_replay_wide(ScorerView sc, B
             else break;
         }
     };
-    for (uint32_t i = 0; i < k; i++) H(i) = list[i];
+    for (uint32_t i = 0; i < k; i++) H(i) = __ldg(list + i);
     for (uint32_t i = k / 2; i-- > 0;) sift(i);
     uint64_t root = H(0);
     for (uint32_t j = k; j < ws.n_list; j++) {

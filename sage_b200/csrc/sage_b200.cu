@@ -5,6 +5,7 @@
 // (scoring.rs:210-232) -> sage_b200_scorer, `par_iter().flat_map(|s| scorer.score(s))` (runner.rs:311-325) ->
 // sage_b200_score_batch. No CPU fallback exists: every entry point fails loudly when CUDA is unavailable.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -446,7 +447,7 @@ struct sage_b200_scorer {
     cudaEvent_t ev[8] = {};
     std::mutex mu;
     // device
-    DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_scratch, d_dbgk, d_dbgm, d_lnfact, d_sort, d_sorttmp, d_wlist, d_wslots;
+    DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_scratch, d_dbgk, d_dbgm, d_lnfact, d_sort, d_sorttmp, d_wlist, d_wslots, d_ncap, d_noff, d_nlist, d_nslots, d_scantmp;
     int sort_spectra = 1;
     // pinned staging
     PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
@@ -533,7 +534,7 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
 extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
     if (!s) return;
     cudaSetDevice(s->db->device);
-    for (DevBuf* b : {&s->d_small, &s->d_masses, &s->d_intens, &s->d_queries, &s->d_hits, &s->d_keys, &s->d_features, &s->d_counts, &s->d_counters, &s->d_scratch, &s->d_dbgk, &s->d_dbgm, &s->d_lnfact, &s->d_sort, &s->d_sorttmp, &s->d_wlist, &s->d_wslots}) b->release();
+    for (DevBuf* b : {&s->d_small, &s->d_masses, &s->d_intens, &s->d_queries, &s->d_hits, &s->d_keys, &s->d_features, &s->d_counts, &s->d_counters, &s->d_scratch, &s->d_dbgk, &s->d_dbgm, &s->d_lnfact, &s->d_sort, &s->d_sorttmp, &s->d_wlist, &s->d_wslots, &s->d_ncap, &s->d_noff, &s->d_nlist, &s->d_nslots, &s->d_scantmp}) b->release();
     for (PinBuf* b : {&s->h_small, &s->h_masses, &s->h_intens, &s->h_features, &s->h_counts, &s->h_counters}) b->release();
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -608,7 +609,7 @@ static int chunk_upload(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64
     if ((rc = S->d_features.reserve((size_t)n * sv.report_psms * sizeof(FeatureOut)))) return rc;
     if ((rc = S->d_counts.reserve(4 * (size_t)n))) return rc;
     if ((rc = S->d_counters.reserve(8 * C_COUNT))) return rc;
-    if ((rc = S->h_counters.reserve(8 * C_COUNT))) return rc;
+    if ((rc = S->h_counters.reserve(8 * C_COUNT + 16))) return rc;
 
     CUDA_TRY(cudaEventRecord(S->ev[0], st));
     CUDA_TRY(cudaMemcpyAsync(S->d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, st));
@@ -688,8 +689,16 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
         if ((rc = S->d_sorttmp.reserve(sort_tmp + 16))) return rc;
     }
-    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv, sk_in, sv_in);
+    // per-item list capacity (window size of narrow queries) -> exclusive scan -> list offsets for the replay kernel
+    if ((rc = S->d_ncap.reserve(4 * (C.nitems + 1)))) return rc;
+    if ((rc = S->d_noff.reserve(4 * (C.nitems + 1)))) return rc;
+    size_t scan_tmp = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, S->d_ncap.as<uint32_t>(), S->d_noff.as<uint32_t>(), (int)(C.nitems + 1), st));
+    if ((rc = S->d_scantmp.reserve(scan_tmp + 16))) return rc;
+    CUDA_TRY(cudaMemsetAsync(S->d_ncap.as<uint32_t>() + C.nitems, 0, 4, st));
+    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv, sk_in, sv_in, S->d_ncap.as<uint32_t>());
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(S->d_scantmp.p, scan_tmp, S->d_ncap.as<uint32_t>(), S->d_noff.as<uint32_t>(), (int)(C.nitems + 1), st));
     if (sk_in) {
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(S->d_sorttmp.p, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
         bv.order = sv_out;
@@ -697,15 +706,26 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
     CUDA_TRY(cudaEventRecord(S->ev[2], st));
     unsigned long long* hc = (unsigned long long*)S->h_counters.p;
     CUDA_TRY(cudaMemcpyAsync(hc, S->d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
+    uint32_t* h_total = (uint32_t*)(hc + C_COUNT);
+    CUDA_TRY(cudaMemcpyAsync(h_total, S->d_noff.as<uint32_t>() + C.nitems, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const uint64_t n_queries = hc[C_QUERIES], n_wide = hc[C_WIDE], max_pot = hc[C_MAXPOT];
+    const uint64_t nlist_total = *h_total;
     uint64_t launches = 1;
 
     // ---- preliminary scoring
     if (n_queries > n_wide) {
-        k_prelim_narrow<<<(unsigned)C.nitems, PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax);
+        if ((rc = S->d_nlist.reserve(8 * (nlist_total + 16)))) return rc;
+        if ((rc = S->d_nslots.reserve(C.nitems * sizeof(ReplaySlot)))) return rc;
+        k_prelim_narrow<<<(unsigned)C.nitems, PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, S->d_nlist.as<uint64_t>(), S->d_noff.as<uint32_t>(),
+                                                                              S->d_nslots.as<ReplaySlot>());
         CUDA_TRY(cudaGetLastError());
-        launches++;
+        const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
+        CUDA_TRY(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+        k_replay<<<(unsigned)((C.nitems + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, S->d_nlist.as<uint64_t>(),
+                                                                                                           S->d_nslots.as<ReplaySlot>(), (uint32_t)C.nitems);
+        CUDA_TRY(cudaGetLastError());
+        launches += 2;
     }
     if (n_wide) {
         (void)max_pot;
@@ -716,8 +736,8 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
         k_prelim_wide<<<ctas, WIDE_THREADS, sizeof(WideSmem), st>>>(db->v, sv, bv, (uint32_t)C.nitems, S->d_wlist.as<uint64_t>(), S->d_wslots.as<WideSlot>());
         CUDA_TRY(cudaGetLastError());
         const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
-        CUDA_TRY(cudaFuncSetAttribute(k_replay_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-        k_replay_wide<<<(unsigned)((n_wide + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, S->d_wlist.as<uint64_t>(),
+        CUDA_TRY(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+        k_replay<<<(unsigned)((n_wide + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, S->d_wlist.as<uint64_t>(),
                                                                                                               S->d_wslots.as<WideSlot>(), (uint32_t)n_wide);
         CUDA_TRY(cudaGetLastError());
         launches += 2;
