@@ -247,10 +247,7 @@ __device__ __forceinline__ uint32_t page_lower_bound_dir(const DbView& db, uint3
 __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b, uint32_t pmax, uint64_t* nlist,
                                                                   const uint32_t* nlist_off, ReplaySlot* nslots) {
     __shared__ uint32_t cnt32[NARROW_CAP / 2 + 1];
-    __shared__ uint64_t heap[K_MAX];
-    __shared__ uint64_t queue[PRELIM_THREADS];
     __shared__ uint32_t s_warp[40];
-    __shared__ uint32_t s_nonzero;
     extern __shared__ float bounds_smem[];  // LO[nfc][np] then HI[nfc][np] (peptide-centric path only)
 
     const uint32_t s = b.order ? b.order[blockIdx.x / sc.qmax] : blockIdx.x / sc.qmax;

@@ -437,23 +437,43 @@ struct ChunkState {
     uint64_t npk = 0;
     size_t nitems = 0, smem = 0, small_bytes = 0;
     size_t o_off = 0, o_pmz = 0, o_tic = 0, o_ilo = 0, o_ihi = 0, o_rt = 0, o_ims = 0, o_chg = 0;
+    bool timed_upload = false;
+};
+
+// One in-flight chunk: its own stream, device buffers, pinned staging and pending-download bookkeeping. score_batch alternates
+// between two lanes so that the H2D copy of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i.
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_dbgk, d_dbgm, d_sort, d_sorttmp, d_wlist, d_wslots,
+        d_ncap, d_noff, d_nlist, d_nslots, d_scantmp;
+    PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
+    ChunkState chunk;
+    // pending work of the chunk in flight
+    bool ran = false, downloading = false;
+    uint64_t launches = 0;
+    sage_b200_feature* fdst = nullptr;
+    uint32_t* cdst = nullptr;
+    bool f_pinned = false, c_pinned = false;
+    void release() {
+        for (DevBuf* b : {&d_small, &d_masses, &d_intens, &d_queries, &d_hits, &d_keys, &d_features, &d_counts, &d_counters, &d_dbgk, &d_dbgm, &d_sort, &d_sorttmp,
+                          &d_wlist, &d_wslots, &d_ncap, &d_noff, &d_nlist, &d_nslots, &d_scantmp}) b->release();
+        for (PinBuf* b : {&h_small, &h_masses, &h_intens, &h_features, &h_counts, &h_counters}) b->release();
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
 };
 
 struct sage_b200_scorer {
     const sage_b200_db* db = nullptr;
     sage_b200_scorer_params params{};
     ScorerView sv{};
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
     std::mutex mu;
-    // device
-    DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_scratch, d_dbgk, d_dbgm, d_lnfact, d_sort, d_sorttmp, d_wlist, d_wslots, d_ncap, d_noff, d_nlist, d_nslots, d_scantmp;
+    Lane lanes[2];
+    DevBuf d_lnfact;
     int sort_spectra = 1;
-    // pinned staging
-    PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
+    int pipeline_chunks = 2;   // score_batch splits large batches into about this many chunks (>= 8192 spectra each)
     sage_b200_counters last{};
-    int wide_ctas = 0;
-    ChunkState chunk;
 };
 
 extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_scorer_params* p, sage_b200_scorer** out) {
@@ -502,9 +522,11 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
         v.lnfact_n = N;
     }
     if (const char* e = getenv("SAGE_B200_SORT")) s->sort_spectra = atoi(e);
-    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    for (auto& e : s->ev) CUDA_TRY(cudaEventCreate(&e));
-    s->wide_ctas = db->sm_count * 2;
+    for (Lane& L : s->lanes) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        for (auto& e : L.ev) CUDA_TRY(cudaEventCreate(&e));
+    }
+    if (const char* e = getenv("SAGE_B200_PIPELINE_CHUNKS")) s->pipeline_chunks = std::max(1, atoi(e));
     *out = s;
     return 0;
 }
@@ -513,6 +535,7 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
     if (!s || !name) return fail(SAGE_B200_EINVAL, "scorer_set_option: null argument");
     std::lock_guard<std::mutex> lock(s->mu);
     if (!strcmp(name, "sort_spectra")) { s->sort_spectra = value != 0; return 0; }
+    if (!strcmp(name, "pipeline_chunks")) { s->pipeline_chunks = (int)std::max<int64_t>(1, value); return 0; }
     if (!strcmp(name, "wide_lmax")) {  // test hook: a tiny survivor list forces the overflow -> in-kernel serial replay path
         if (value < (int64_t)K_MAX || value > (int64_t)WIDE_LMAX) return fail(SAGE_B200_EINVAL, "wide_lmax must be in %d..%u", K_MAX, WIDE_LMAX);
         s->sv.wide_lmax = (uint32_t)value;
@@ -534,10 +557,8 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
 extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
     if (!s) return;
     cudaSetDevice(s->db->device);
-    for (DevBuf* b : {&s->d_small, &s->d_masses, &s->d_intens, &s->d_queries, &s->d_hits, &s->d_keys, &s->d_features, &s->d_counts, &s->d_counters, &s->d_scratch, &s->d_dbgk, &s->d_dbgm, &s->d_lnfact, &s->d_sort, &s->d_sorttmp, &s->d_wlist, &s->d_wslots, &s->d_ncap, &s->d_noff, &s->d_nlist, &s->d_nslots, &s->d_scantmp}) b->release();
-    for (PinBuf* b : {&s->h_small, &s->h_masses, &s->h_intens, &s->h_features, &s->h_counts, &s->h_counters}) b->release();
-    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    for (Lane& L : s->lanes) L.release();
+    s->d_lnfact.release();
     delete s;
 }
 
@@ -547,10 +568,10 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 //   chunk_upload   pack + H2D (spectra become device-resident)
 //   chunk_run      k_setup_queries -> k_prelim_{narrow,wide} -> k_score (results stay on the device)
 //   chunk_download D2H of Feature rows + counts
-static int chunk_upload(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64_t c0, uint64_t c1) {
+static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* sp, uint64_t c0, uint64_t c1) {
     const ScorerView& sv = S->sv;
-    cudaStream_t st = S->stream;
-    ChunkState& C = S->chunk;
+    cudaStream_t st = L.stream;
+    ChunkState& C = L.chunk;
     C.loaded = false;
     const uint32_t n = (uint32_t)(c1 - c0);
     const uint64_t pk0 = sp->peak_offsets[c0], pk1 = sp->peak_offsets[c1];
@@ -568,9 +589,9 @@ static int chunk_upload(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64
     C.o_chg = align_up(C.o_ims + 4 * (size_t)n, 16);
     C.small_bytes = align_up(C.o_chg + n, 16);
     int rc;
-    if ((rc = S->h_small.reserve(C.small_bytes))) return rc;
-    if ((rc = S->d_small.reserve(C.small_bytes))) return rc;
-    unsigned char* hs = (unsigned char*)S->h_small.p;
+    if ((rc = L.h_small.reserve(C.small_bytes))) return rc;
+    if ((rc = L.d_small.reserve(C.small_bytes))) return rc;
+    unsigned char* hs = (unsigned char*)L.h_small.p;
     uint32_t* h_off = (uint32_t*)(hs + C.o_off);
     uint32_t pmax = 2, zmax = sv.max_charge;
     for (uint32_t i = 0; i <= n; i++) h_off[i] = (uint32_t)(sp->peak_offsets[c0 + i] - pk0);
@@ -601,63 +622,61 @@ static int chunk_upload(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64
     if (C.smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", C.pmax);
     C.nitems = (size_t)n * sv.qmax;
     if (C.nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
-    if ((rc = S->d_masses.reserve(4 * npk + 16))) return rc;
-    if ((rc = S->d_intens.reserve(4 * npk + 16))) return rc;
-    if ((rc = S->d_queries.reserve(C.nitems * sizeof(QueryDesc)))) return rc;
-    if ((rc = S->d_hits.reserve(C.nitems * sizeof(QueryHits)))) return rc;
-    if ((rc = S->d_keys.reserve(C.nitems * sv.kparam * 8))) return rc;
-    if ((rc = S->d_features.reserve((size_t)n * sv.report_psms * sizeof(FeatureOut)))) return rc;
-    if ((rc = S->d_counts.reserve(4 * (size_t)n))) return rc;
-    if ((rc = S->d_counters.reserve(8 * C_COUNT))) return rc;
-    if ((rc = S->h_counters.reserve(8 * C_COUNT + 16))) return rc;
+    if ((rc = L.d_masses.reserve(4 * npk + 16))) return rc;
+    if ((rc = L.d_intens.reserve(4 * npk + 16))) return rc;
+    if ((rc = L.d_queries.reserve(C.nitems * sizeof(QueryDesc)))) return rc;
+    if ((rc = L.d_hits.reserve(C.nitems * sizeof(QueryHits)))) return rc;
+    if ((rc = L.d_keys.reserve(C.nitems * sv.kparam * 8))) return rc;
+    if ((rc = L.d_features.reserve((size_t)n * sv.report_psms * sizeof(FeatureOut)))) return rc;
+    if ((rc = L.d_counts.reserve(4 * (size_t)n))) return rc;
+    if ((rc = L.d_counters.reserve(8 * C_COUNT))) return rc;
+    if ((rc = L.h_counters.reserve(8 * C_COUNT + 16))) return rc;
 
-    CUDA_TRY(cudaEventRecord(S->ev[0], st));
-    CUDA_TRY(cudaMemcpyAsync(S->d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(L.ev[0], st));
+    CUDA_TRY(cudaMemcpyAsync(L.d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, st));
     const float* src_m = sp->masses + pk0;
     const float* src_i = sp->intensities + pk0;
     if (npk) {
         if (!is_pinned(src_m)) {
-            if ((rc = S->h_masses.reserve(4 * npk))) return rc;
-            memcpy(S->h_masses.p, src_m, 4 * npk);
-            src_m = (const float*)S->h_masses.p;
+            if ((rc = L.h_masses.reserve(4 * npk))) return rc;
+            memcpy(L.h_masses.p, src_m, 4 * npk);
+            src_m = (const float*)L.h_masses.p;
         }
         if (!is_pinned(src_i)) {
-            if ((rc = S->h_intens.reserve(4 * npk))) return rc;
-            memcpy(S->h_intens.p, src_i, 4 * npk);
-            src_i = (const float*)S->h_intens.p;
+            if ((rc = L.h_intens.reserve(4 * npk))) return rc;
+            memcpy(L.h_intens.p, src_i, 4 * npk);
+            src_i = (const float*)L.h_intens.p;
         }
-        CUDA_TRY(cudaMemcpyAsync(S->d_masses.p, src_m, 4 * npk, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(S->d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(L.d_masses.p, src_m, 4 * npk, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(L.d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, st));
     }
-    CUDA_TRY(cudaEventRecord(S->ev[1], st));
-    CUDA_TRY(cudaStreamSynchronize(st));  // staging buffers are reused by the next chunk
-    float ms;
-    cudaEventElapsedTime(&ms, S->ev[0], S->ev[1]);
-    S->last.ms_h2d += ms;
-    S->last.ms_total += ms;
+    CUDA_TRY(cudaEventRecord(L.ev[1], st));
     S->last.h2d_bytes += C.small_bytes + 8 * npk;
     C.loaded = true;
+    C.timed_upload = true;
+    L.ran = false;
+    L.downloading = false;
     return 0;
 }
 
-static int chunk_run(sage_b200_scorer* S, bool dbg) {
+static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     const sage_b200_db* db = S->db;
     const ScorerView& sv = S->sv;
-    cudaStream_t st = S->stream;
-    ChunkState& C = S->chunk;
+    cudaStream_t st = L.stream;
+    ChunkState& C = L.chunk;
     if (!C.loaded) return fail(SAGE_B200_EINVAL, "no spectra resident on the device (call batch_upload first)");
     const uint32_t n = C.n;
     int rc;
     if (dbg) {
-        if ((rc = S->d_dbgk.reserve((size_t)n * sv.kparam * 8))) return rc;
-        if ((rc = S->d_dbgm.reserve((size_t)n * 16))) return rc;
+        if ((rc = L.d_dbgk.reserve((size_t)n * sv.kparam * 8))) return rc;
+        if ((rc = L.d_dbgm.reserve((size_t)n * 16))) return rc;
     }
     BatchView bv{};
-    unsigned char* ds = (unsigned char*)S->d_small.p;
+    unsigned char* ds = (unsigned char*)L.d_small.p;
     bv.n = n;
     bv.peak_off = (const uint32_t*)(ds + C.o_off);
-    bv.masses = S->d_masses.as<float>();
-    bv.intens = S->d_intens.as<float>();
+    bv.masses = L.d_masses.as<float>();
+    bv.intens = L.d_intens.as<float>();
     bv.prec_mz = (const float*)(ds + C.o_pmz);
     bv.prec_charge = (const uint8_t*)(ds + C.o_chg);
     bv.iso_lo = (const float*)(ds + C.o_ilo);
@@ -665,13 +684,13 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
     bv.tic = (const float*)(ds + C.o_tic);
     bv.rt = (const float*)(ds + C.o_rt);
     bv.ims = (const float*)(ds + C.o_ims);
-    bv.queries = S->d_queries.as<QueryDesc>();
-    bv.hits = S->d_hits.as<QueryHits>();
-    bv.hit_keys = S->d_keys.as<uint64_t>();
-    bv.counters = S->d_counters.as<unsigned long long>();
+    bv.queries = L.d_queries.as<QueryDesc>();
+    bv.hits = L.d_hits.as<QueryHits>();
+    bv.hit_keys = L.d_keys.as<uint64_t>();
+    bv.counters = L.d_counters.as<unsigned long long>();
 
-    CUDA_TRY(cudaEventRecord(S->ev[1], st));
-    CUDA_TRY(cudaMemsetAsync(S->d_counters.p, 0, 8 * C_COUNT, st));
+    CUDA_TRY(cudaEventRecord(L.ev[6], st));
+    CUDA_TRY(cudaMemsetAsync(L.d_counters.p, 0, 8 * C_COUNT, st));
     // ---- setup: resolve precursor windows. Peptide-centric counting needs LO/HI bound arrays of nfc_max * pmax floats in smem.
     ScorerView svq = sv;
     uint32_t mfc = sv.max_fragment_charge_opt >= 0 ? std::min<uint32_t>(C.zmax, (uint32_t)(sv.max_fragment_charge_opt + 1) & 0xFF) : C.zmax;
@@ -684,30 +703,30 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
     uint32_t *sk_in = nullptr, *sk_out = nullptr, *sv_in = nullptr, *sv_out = nullptr;
     size_t sort_tmp = 0;
     if (S->sort_spectra && n > 1) {  // process spectra in ascending precursor-window order: neighbouring CTAs then touch the same index lines
-        if ((rc = S->d_sort.reserve(16 * (size_t)n))) return rc;
-        sk_in = S->d_sort.as<uint32_t>(); sk_out = sk_in + n; sv_in = sk_out + n; sv_out = sv_in + n;
+        if ((rc = L.d_sort.reserve(16 * (size_t)n))) return rc;
+        sk_in = L.d_sort.as<uint32_t>(); sk_out = sk_in + n; sv_in = sk_out + n; sv_out = sv_in + n;
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
-        if ((rc = S->d_sorttmp.reserve(sort_tmp + 16))) return rc;
+        if ((rc = L.d_sorttmp.reserve(sort_tmp + 16))) return rc;
     }
     // per-item list capacity (window size of narrow queries) -> exclusive scan -> list offsets for the replay kernel
-    if ((rc = S->d_ncap.reserve(4 * (C.nitems + 1)))) return rc;
-    if ((rc = S->d_noff.reserve(4 * (C.nitems + 1)))) return rc;
+    if ((rc = L.d_ncap.reserve(4 * (C.nitems + 1)))) return rc;
+    if ((rc = L.d_noff.reserve(4 * (C.nitems + 1)))) return rc;
     size_t scan_tmp = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, S->d_ncap.as<uint32_t>(), S->d_noff.as<uint32_t>(), (int)(C.nitems + 1), st));
-    if ((rc = S->d_scantmp.reserve(scan_tmp + 16))) return rc;
-    CUDA_TRY(cudaMemsetAsync(S->d_ncap.as<uint32_t>() + C.nitems, 0, 4, st));
-    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv, sk_in, sv_in, S->d_ncap.as<uint32_t>());
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, L.d_ncap.as<uint32_t>(), L.d_noff.as<uint32_t>(), (int)(C.nitems + 1), st));
+    if ((rc = L.d_scantmp.reserve(scan_tmp + 16))) return rc;
+    CUDA_TRY(cudaMemsetAsync(L.d_ncap.as<uint32_t>() + C.nitems, 0, 4, st));
+    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv, sk_in, sv_in, L.d_ncap.as<uint32_t>());
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(S->d_scantmp.p, scan_tmp, S->d_ncap.as<uint32_t>(), S->d_noff.as<uint32_t>(), (int)(C.nitems + 1), st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(L.d_scantmp.p, scan_tmp, L.d_ncap.as<uint32_t>(), L.d_noff.as<uint32_t>(), (int)(C.nitems + 1), st));
     if (sk_in) {
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(S->d_sorttmp.p, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(L.d_sorttmp.p, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
         bv.order = sv_out;
     }
-    CUDA_TRY(cudaEventRecord(S->ev[2], st));
-    unsigned long long* hc = (unsigned long long*)S->h_counters.p;
-    CUDA_TRY(cudaMemcpyAsync(hc, S->d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(L.ev[2], st));
+    unsigned long long* hc = (unsigned long long*)L.h_counters.p;
+    CUDA_TRY(cudaMemcpyAsync(hc, L.d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
     uint32_t* h_total = (uint32_t*)(hc + C_COUNT);
-    CUDA_TRY(cudaMemcpyAsync(h_total, S->d_noff.as<uint32_t>() + C.nitems, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_total, L.d_noff.as<uint32_t>() + C.nitems, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const uint64_t n_queries = hc[C_QUERIES], n_wide = hc[C_WIDE], max_pot = hc[C_MAXPOT];
     const uint64_t nlist_total = *h_total;
@@ -715,15 +734,15 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
 
     // ---- preliminary scoring
     if (n_queries > n_wide) {
-        if ((rc = S->d_nlist.reserve(8 * (nlist_total + 16)))) return rc;
-        if ((rc = S->d_nslots.reserve(C.nitems * sizeof(ReplaySlot)))) return rc;
-        k_prelim_narrow<<<(unsigned)C.nitems, PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, S->d_nlist.as<uint64_t>(), S->d_noff.as<uint32_t>(),
-                                                                              S->d_nslots.as<ReplaySlot>());
+        if ((rc = L.d_nlist.reserve(8 * (nlist_total + 16)))) return rc;
+        if ((rc = L.d_nslots.reserve(C.nitems * sizeof(ReplaySlot)))) return rc;
+        k_prelim_narrow<<<(unsigned)C.nitems, PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>(), L.d_noff.as<uint32_t>(),
+                                                                              L.d_nslots.as<ReplaySlot>());
         CUDA_TRY(cudaGetLastError());
         const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
         CUDA_TRY(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-        k_replay<<<(unsigned)((C.nitems + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, S->d_nlist.as<uint64_t>(),
-                                                                                                           S->d_nslots.as<ReplaySlot>(), (uint32_t)C.nitems);
+        k_replay<<<(unsigned)((C.nitems + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, L.d_nlist.as<uint64_t>(),
+                                                                                                           L.d_nslots.as<ReplaySlot>(), (uint32_t)C.nitems);
         CUDA_TRY(cudaGetLastError());
         launches += 2;
     }
@@ -731,77 +750,82 @@ static int chunk_run(sage_b200_scorer* S, bool dbg) {
         (void)max_pot;
         const int ctas = (int)std::min<uint64_t>((uint64_t)db->sm_count, n_wide);
         CUDA_TRY(cudaFuncSetAttribute(k_prelim_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WideSmem)));
-        if ((rc = S->d_wlist.reserve((size_t)n_wide * WIDE_LMAX * 8))) return rc;
-        if ((rc = S->d_wslots.reserve((size_t)n_wide * sizeof(WideSlot)))) return rc;
-        k_prelim_wide<<<ctas, WIDE_THREADS, sizeof(WideSmem), st>>>(db->v, sv, bv, (uint32_t)C.nitems, S->d_wlist.as<uint64_t>(), S->d_wslots.as<WideSlot>());
+        if ((rc = L.d_wlist.reserve((size_t)n_wide * WIDE_LMAX * 8))) return rc;
+        if ((rc = L.d_wslots.reserve((size_t)n_wide * sizeof(WideSlot)))) return rc;
+        k_prelim_wide<<<ctas, WIDE_THREADS, sizeof(WideSmem), st>>>(db->v, sv, bv, (uint32_t)C.nitems, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>());
         CUDA_TRY(cudaGetLastError());
         const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
         CUDA_TRY(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-        k_replay<<<(unsigned)((n_wide + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, S->d_wlist.as<uint64_t>(),
-                                                                                                              S->d_wslots.as<WideSlot>(), (uint32_t)n_wide);
+        k_replay<<<(unsigned)((n_wide + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, L.d_wlist.as<uint64_t>(),
+                                                                                                              L.d_wslots.as<WideSlot>(), (uint32_t)n_wide);
         CUDA_TRY(cudaGetLastError());
         launches += 2;
     }
-    CUDA_TRY(cudaEventRecord(S->ev[3], st));
+    CUDA_TRY(cudaEventRecord(L.ev[3], st));
 
     // ---- candidate scoring + feature assembly
     CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));
-    k_score<<<n, SCORE_THREADS, C.smem, st>>>(db->v, sv, bv, S->d_features.as<FeatureOut>(), S->d_counts.as<uint32_t>(), C.pmax,
-                                             dbg ? S->d_dbgk.as<uint64_t>() : nullptr, dbg ? S->d_dbgm.as<uint32_t>() : nullptr);
+    k_score<<<n, SCORE_THREADS, C.smem, st>>>(db->v, sv, bv, L.d_features.as<FeatureOut>(), L.d_counts.as<uint32_t>(), C.pmax,
+                                             dbg ? L.d_dbgk.as<uint64_t>() : nullptr, dbg ? L.d_dbgm.as<uint32_t>() : nullptr);
     CUDA_TRY(cudaGetLastError());
     launches++;
-    CUDA_TRY(cudaEventRecord(S->ev[4], st));
-    CUDA_TRY(cudaMemcpyAsync(hc, S->d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-
-    sage_b200_counters& L = S->last;
-    float ms;
-    cudaEventElapsedTime(&ms, S->ev[1], S->ev[2]); L.ms_setup += ms;
-    cudaEventElapsedTime(&ms, S->ev[2], S->ev[3]); L.ms_prelim += ms;
-    cudaEventElapsedTime(&ms, S->ev[3], S->ev[4]); L.ms_score += ms;
-    cudaEventElapsedTime(&ms, S->ev[1], S->ev[4]); L.ms_total += ms;
-    L.spectra += n; L.peaks += C.npk; L.queries += hc[C_QUERIES]; L.tasks += hc[C_TASKS]; L.pages += hc[C_PAGES]; L.entries_scanned += hc[C_ENTRIES];
-    L.matched_fragments += hc[C_MATCHED]; L.candidates_scored += hc[C_CANDS]; L.peptide_record_floats += hc[C_PEPFLOATS]; L.psms += hc[C_PSMS];
-    L.wide_queries += hc[C_WIDE];
-    L.pep_queries += hc[C_PEPQ];
-    L.pep_fallbacks += hc[C_PEPFALLBACK];
-    L.wide_overflows += hc[C_WOVERFLOW];
-    L.d2h_bytes += 2 * 8 * C_COUNT;
-    L.kernel_launches += launches;
+    CUDA_TRY(cudaEventRecord(L.ev[4], st));
+    CUDA_TRY(cudaMemcpyAsync(hc, L.d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
+    L.launches = launches;
+    L.ran = true;
     return 0;
 }
 
-static int chunk_download(sage_b200_scorer* S, sage_b200_feature* fdst, uint32_t* cdst) {
+static int chunk_download(sage_b200_scorer* S, Lane& L, sage_b200_feature* fdst, uint32_t* cdst) {
     const ScorerView& sv = S->sv;
-    cudaStream_t st = S->stream;
-    ChunkState& C = S->chunk;
+    cudaStream_t st = L.stream;
+    ChunkState& C = L.chunk;
     if (!C.loaded) return fail(SAGE_B200_EINVAL, "no results on the device");
     const uint32_t n = C.n;
     int rc;
     const size_t fbytes = (size_t)n * sv.report_psms * sizeof(sage_b200_feature);
     const bool f_pinned = is_pinned(fdst), c_pinned = is_pinned(cdst);
-    if (!f_pinned && (rc = S->h_features.reserve(fbytes))) return rc;
-    if (!c_pinned && (rc = S->h_counts.reserve(4 * (size_t)n))) return rc;
-    CUDA_TRY(cudaEventRecord(S->ev[4], st));
-    CUDA_TRY(cudaMemcpyAsync(f_pinned ? (void*)fdst : S->h_features.p, S->d_features.p, fbytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(c_pinned ? (void*)cdst : S->h_counts.p, S->d_counts.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaEventRecord(S->ev[5], st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (!f_pinned) memcpy(fdst, S->h_features.p, fbytes);
-    if (!c_pinned) memcpy(cdst, S->h_counts.p, 4 * (size_t)n);
-    float ms;
-    cudaEventElapsedTime(&ms, S->ev[4], S->ev[5]);
-    S->last.ms_d2h += ms;
-    S->last.ms_total += ms;
+    if (!f_pinned && (rc = L.h_features.reserve(fbytes))) return rc;
+    if (!c_pinned && (rc = L.h_counts.reserve(4 * (size_t)n))) return rc;
+    CUDA_TRY(cudaEventRecord(L.ev[7], st));
+    CUDA_TRY(cudaMemcpyAsync(f_pinned ? (void*)fdst : L.h_features.p, L.d_features.p, fbytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c_pinned ? (void*)cdst : L.h_counts.p, L.d_counts.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(L.ev[5], st));
+    L.fdst = fdst; L.cdst = cdst; L.f_pinned = f_pinned; L.c_pinned = c_pinned;
+    L.downloading = true;
     S->last.d2h_bytes += fbytes + 4 * (size_t)n;
     return 0;
 }
 
-static int run_chunk(sage_b200_scorer* S, const sage_b200_spectra* sp, uint64_t c0, uint64_t c1, sage_b200_feature* features, uint32_t* counts, bool dbg) {
-    int rc;
-    if ((rc = chunk_upload(S, sp, c0, c1))) return rc;
-    if ((rc = chunk_run(S, dbg))) return rc;
-    return chunk_download(S, features + c0 * S->sv.report_psms, counts + c0);
+// Waits for everything queued on the lane and folds its counters / timings into S->last.
+static int lane_finish(sage_b200_scorer* S, Lane& L) {
+    ChunkState& C = L.chunk;
+    if (!C.loaded) return 0;
+    CUDA_TRY(cudaStreamSynchronize(L.stream));
+    sage_b200_counters& T = S->last;
+    float ms;
+    if (C.timed_upload) { cudaEventElapsedTime(&ms, L.ev[0], L.ev[1]); T.ms_h2d += ms; T.ms_total += ms; C.timed_upload = false; }
+    if (L.ran) {
+        const unsigned long long* hc = (const unsigned long long*)L.h_counters.p;
+        cudaEventElapsedTime(&ms, L.ev[6], L.ev[2]); T.ms_setup += ms;
+        cudaEventElapsedTime(&ms, L.ev[2], L.ev[3]); T.ms_prelim += ms;
+        cudaEventElapsedTime(&ms, L.ev[3], L.ev[4]); T.ms_score += ms;
+        cudaEventElapsedTime(&ms, L.ev[6], L.ev[4]); T.ms_total += ms;
+        T.spectra += C.n; T.peaks += C.npk; T.queries += hc[C_QUERIES]; T.tasks += hc[C_TASKS]; T.pages += hc[C_PAGES]; T.entries_scanned += hc[C_ENTRIES];
+        T.matched_fragments += hc[C_MATCHED]; T.candidates_scored += hc[C_CANDS]; T.peptide_record_floats += hc[C_PEPFLOATS]; T.psms += hc[C_PSMS];
+        T.wide_queries += hc[C_WIDE]; T.pep_queries += hc[C_PEPQ]; T.pep_fallbacks += hc[C_PEPFALLBACK]; T.wide_overflows += hc[C_WOVERFLOW];
+        T.d2h_bytes += 2 * 8 * C_COUNT;
+        T.kernel_launches += L.launches;
+        L.ran = false;
+    }
+    if (L.downloading) {
+        const size_t fbytes = (size_t)C.n * S->sv.report_psms * sizeof(sage_b200_feature);
+        if (!L.f_pinned) memcpy(L.fdst, L.h_features.p, fbytes);
+        if (!L.c_pinned) memcpy(L.cdst, L.h_counts.p, 4 * (size_t)C.n);
+        cudaEventElapsedTime(&ms, L.ev[7], L.ev[5]); T.ms_d2h += ms; T.ms_total += ms;
+        L.downloading = false;
+    }
+    return 0;
 }
 
 static void finish_counters(sage_b200_scorer* S) {
@@ -832,20 +856,35 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
     CUDA_TRY(cudaSetDevice(S->db->device));
     S->last = sage_b200_counters{};
     if (fragments_used) *fragments_used = 0;
-    // chunks bounded by spectra count and peak count so device staging stays modest
-    const uint64_t max_spec = 1u << 17, max_peaks = 1ull << 25;
+    for (Lane& L : S->lanes) { L.chunk.loaded = false; L.ran = false; L.downloading = false; }
+    // Chunks are bounded by spectra and peak counts (device staging) and sized so that a large batch becomes ~pipeline_chunks chunks:
+    // two lanes alternate, so the H2D of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i.
+    const uint64_t max_peaks = 1ull << 25;
+    // measured on cfg2 (50k spectra): 2 chunks of 25k beat 1, 4 and 6 (per-chunk launch/sync overhead vs exposed first H2D)
+    uint64_t target = (sp->n + (uint64_t)S->pipeline_chunks - 1) / (uint64_t)S->pipeline_chunks;
+    target = std::min<uint64_t>(std::max<uint64_t>(target, 8192), 32768);
     uint64_t c0 = 0;
+    int li = 0;
     while (c0 < sp->n) {
-        uint64_t c1 = std::min<uint64_t>(sp->n, c0 + max_spec);
+        uint64_t c1 = std::min<uint64_t>(sp->n, c0 + target);
         while (c1 > c0 + 1 && sp->peak_offsets[c1] - sp->peak_offsets[c0] > max_peaks) c1 = c0 + (c1 - c0) / 2;
-        if ((rc = run_chunk(S, sp, c0, c1, features, counts, false))) return rc;
+        Lane& L = S->lanes[li];
+        if ((rc = lane_finish(S, L))) return rc;   // the chunk that used this lane two iterations ago
+        if ((rc = chunk_upload(S, L, sp, c0, c1))) return rc;
+        if ((rc = chunk_run(S, L, false))) return rc;
+        if ((rc = chunk_download(S, L, features + c0 * S->sv.report_psms, counts + c0))) return rc;
         c0 = c1;
+        li ^= 1;
+    }
+    for (Lane& L : S->lanes) {
+        if ((rc = lane_finish(S, L))) return rc;
+        L.chunk.loaded = false;
     }
     finish_counters(S);
     return 0;
 }
 
-// Device-resident variant of score_batch, split in phases (single chunk): upload once, run the kernels any number of
+// Device-resident variant of score_batch, split in phases (single chunk, lane 0): upload once, run the kernels any number of
 // times (bench.py times this with the inputs already in HBM), download the Feature rows.
 extern "C" int sage_b200_batch_upload(sage_b200_scorer* S, const sage_b200_spectra* sp) {
     if (!S) return fail(SAGE_B200_EINVAL, "batch_upload: null scorer");
@@ -856,7 +895,9 @@ extern "C" int sage_b200_batch_upload(sage_b200_scorer* S, const sage_b200_spect
     std::lock_guard<std::mutex> lock(S->mu);
     CUDA_TRY(cudaSetDevice(S->db->device));
     S->last = sage_b200_counters{};
-    return chunk_upload(S, sp, 0, sp->n);
+    Lane& L = S->lanes[0];
+    if ((rc = chunk_upload(S, L, sp, 0, sp->n))) return rc;
+    return lane_finish(S, L);
 }
 extern "C" int sage_b200_batch_run(sage_b200_scorer* S) {
     if (!S) return fail(SAGE_B200_EINVAL, "batch_run: null scorer");
@@ -865,8 +906,10 @@ extern "C" int sage_b200_batch_run(sage_b200_scorer* S) {
     const uint64_t h2d = S->last.h2d_bytes;
     S->last = sage_b200_counters{};
     S->last.h2d_bytes = h2d;
-    int rc = chunk_run(S, false);
+    Lane& L = S->lanes[0];
+    int rc = chunk_run(S, L, false);
     if (rc) return rc;
+    if ((rc = lane_finish(S, L))) return rc;
     finish_counters(S);
     return 0;
 }
@@ -874,7 +917,10 @@ extern "C" int sage_b200_batch_download(sage_b200_scorer* S, sage_b200_feature* 
     if (!S || !features || !counts) return fail(SAGE_B200_EINVAL, "batch_download: null argument");
     std::lock_guard<std::mutex> lock(S->mu);
     CUDA_TRY(cudaSetDevice(S->db->device));
-    return chunk_download(S, features, counts);
+    Lane& L = S->lanes[0];
+    int rc = chunk_download(S, L, features, counts);
+    if (rc) return rc;
+    return lane_finish(S, L);
 }
 
 extern "C" int64_t sage_b200_initial_hits(sage_b200_scorer* S, const sage_b200_spectra* sp, uint16_t* matched, uint32_t* peptide, uint8_t* charge,
@@ -888,11 +934,16 @@ extern "C" int64_t sage_b200_initial_hits(sage_b200_scorer* S, const sage_b200_s
     S->last = sage_b200_counters{};
     std::vector<sage_b200_feature> f(S->sv.report_psms);
     uint32_t cnt = 0;
-    if ((rc = run_chunk(S, sp, 0, 1, f.data(), &cnt, true))) return rc;
+    Lane& L = S->lanes[0];
+    if ((rc = chunk_upload(S, L, sp, 0, 1))) return rc;
+    if ((rc = chunk_run(S, L, true))) return rc;
+    if ((rc = chunk_download(S, L, f.data(), &cnt))) return rc;
+    if ((rc = lane_finish(S, L))) return rc;
+    L.chunk.loaded = false;
     std::vector<uint64_t> keys(S->sv.kparam);
     uint32_t meta[4] = {0, 0, 0, 0};
-    if (cudaMemcpy(keys.data(), S->d_dbgk.p, 8 * (size_t)S->sv.kparam, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(meta, S->d_dbgm.p, 16, cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (cudaMemcpy(keys.data(), L.d_dbgk.p, 8 * (size_t)S->sv.kparam, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(meta, L.d_dbgm.p, 16, cudaMemcpyDeviceToHost) != cudaSuccess)
         return fail(SAGE_B200_ECUDA, "initial_hits: readback failed");
     const uint32_t nk = meta[0];
     for (uint32_t i = 0; i < nk && i < cap; i++) {
