@@ -125,8 +125,17 @@ def committed_traffic(workload):
     return None
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so the count is passed to the oracle explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_throughput(pep, spectra, wl, steps, warmup, threads=0):
     """Times the CPU oracle (OpenMP over spectra) on a bounded sample of the same workload. Returns list of spectra/s per step."""
+    threads = threads or host_threads()
     from oracle import oracle as O
     from helpers import oracle_db_from_peptides
     t0 = time.time()
@@ -142,7 +151,7 @@ def oracle_throughput(pep, spectra, wl, steps, warmup, threads=0):
         dt = time.perf_counter() - t
         if i >= warmup:
             rates.append(ns / dt)
-    return rates, ns, O.num_threads() if threads == 0 else threads
+    return rates, ns, threads
 
 
 def main():
