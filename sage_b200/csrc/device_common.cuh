@@ -12,7 +12,7 @@ namespace sb {
 constexpr int K_MAX = 128;            // max preliminary candidates kept per spectrum: max(50, 2*report_psms)
 constexpr uint32_t NARROW_CAP = 8192; // precursor windows up to this many peptides are counted in shared memory
 constexpr int PRELIM_THREADS = 256;
-constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_THREADS = 128;  // measured on cfg2: 128 (1.66 ms) beats 256 (1.95 ms) and 64 (1.75 ms); must stay >= K_MAX for the rank sort
 constexpr int MAX_KINDS = 6;
 constexpr uint32_t BUCKET_LUT_CELLS = 4096;
 

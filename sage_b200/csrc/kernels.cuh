@@ -168,20 +168,22 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* s_warp) 
 // of this path. A 256-cell LUT over the array's value range gives a conservative lower bound of lower_bound(arr, x) in O(1);
 // callers then advance linearly comparing the ACTUAL array values, so results stay exact.  start[c] = #{i : arr[i] < edge(c)},
 // edge(c) = base + c*w (c >= 1), start[0] = 0.
-constexpr uint32_t LUT_CELLS = 256;
+constexpr uint32_t LUT_CELLS = 256;        // per-charge bound arrays of the peptide-centric prelim path
+constexpr uint32_t SPEC_LUT_CELLS = 1024;  // spectrum peak LUT of k_score (~0.2 peaks per cell at 200 peaks)
 struct LutParams { float base, inv_w; };
 
-__device__ __forceinline__ LutParams lut_params(float first, float last) {
+__device__ __forceinline__ LutParams lut_params(float first, float last, uint32_t cells = LUT_CELLS) {
     LutParams L;
     L.base = first;
-    const float w = (last - first) / (float)LUT_CELLS;
+    const float w = (last - first) / (float)cells;
     L.inv_w = (w > 0.0f && w < 3.0e38f) ? 1.0f / w : 0.0f;
     return L;
 }
 __device__ __forceinline__ float lut_edge(const LutParams& L, uint32_t c) { return L.inv_w > 0.0f ? L.base + (float)c * (1.0f / L.inv_w) : L.base; }
 // Cooperative build: threads [t0, t0+stride, ...) fill start[0..LUT_CELLS)
-__device__ __forceinline__ void lut_build(const float* arr, uint32_t n, const LutParams& L, uint16_t* start, uint32_t t0, uint32_t stride) {
-    for (uint32_t c = t0; c < LUT_CELLS; c += stride) {
+__device__ __forceinline__ void lut_build(const float* arr, uint32_t n, const LutParams& L, uint16_t* start, uint32_t t0, uint32_t stride,
+                                          uint32_t cells = LUT_CELLS) {
+    for (uint32_t c = t0; c < cells; c += stride) {
         uint32_t lo = 0;
         if (c > 0 && L.inv_w > 0.0f) {
             const float e = lut_edge(L, c);
@@ -192,9 +194,9 @@ __device__ __forceinline__ void lut_build(const float* arr, uint32_t n, const Lu
     }
 }
 // A position s with arr[i] < x for all i < s (conservative: one cell early to absorb float rounding of the cell index).
-__device__ __forceinline__ uint32_t lut_start(const LutParams& L, const uint16_t* start, float x) {
+__device__ __forceinline__ uint32_t lut_start(const LutParams& L, const uint16_t* start, float x, uint32_t cells = LUT_CELLS) {
     const float t = (x - L.base) * L.inv_w;
-    int c = t > 1.0f ? (int)fminf(t, (float)(LUT_CELLS - 1)) - 1 : 0;
+    int c = t > 1.0f ? (int)fminf(t, (float)(cells - 1)) - 1 : 0;
     return start[c];
 }
 
@@ -985,7 +987,7 @@ __device__ __forceinline__ int select_most_intense_peak_lut(const float* masses,
     tol_bounds(tol, center, lo, hi);
     lo = __fadd_rn(lo, 0.0f);
     hi = __fadd_rn(hi, 0.0f);
-    uint32_t idx = lut_start(LP, lut, lo);
+    uint32_t idx = lut_start(LP, lut, lo, SPEC_LUT_CELLS);
     while (idx < n && masses[idx] < lo) idx++;
     int best = -1;
     float max_int = 0.0f;
@@ -1054,12 +1056,19 @@ __device__ __forceinline__ void score_candidate_warp(const DbView& db, const Sco
         uint32_t idx = 0;
         bool is_n = false;
         if (f < total) {
-            const uint32_t kind_i = f / per_kind;
-            const uint32_t rem = f - kind_i * per_kind;
-            idx = rem / nfc;
-            const uint32_t fc = rem - idx * nfc + 1;
+            // f = (kind * nions + idx) * nfc + (fc - 1); nfc is 1..3 in practice: divide by compile-time constants
+            uint32_t ki, fc;
+            switch (nfc) {
+                case 1: ki = f; fc = 1; break;
+                case 2: ki = f >> 1; fc = (f & 1) + 1; break;
+                case 3: ki = f / 3; fc = f - ki * 3 + 1; break;
+                default: ki = f / nfc; fc = f - ki * nfc + 1; break;
+            }
+            uint32_t kind_i = 0;
+            idx = ki;
+            while (idx >= nions) { idx -= nions; kind_i++; }   // <= n_kinds - 1 iterations
             is_n = (db.nterm_mask >> kind_i) & 1;
-            const float mz = __fdiv_rn(__ldg(ions + kind_i * nions + idx), (float)fc);  // scoring.rs:707
+            const float mz = __fdiv_rn(__ldg(ions + ki), (float)fc);  // scoring.rs:707   (ions[kind_i * nions + idx] == ions[ki])
             pk = sp.use_lut ? select_most_intense_peak_lut(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol, sp.lp, sp.lut)
                             : select_most_intense_peak(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol);
             if (pk >= 0 && mark == nullptr) {
@@ -1125,6 +1134,7 @@ struct FeatureOut {  // layout == sage_b200_feature
     uint32_t fragment_offset, fragment_count;
 };
 static_assert(sizeof(FeatureOut) == 128, "feature layout");
+static_assert(SCORE_THREADS >= K_MAX, "k_score ranks candidates one per thread");
 
 // Append a per-query hit list to a merge buffer (InitialHits += , scoring.rs:60-67). All-default runs are capped at
 // kparam entries: defaults beyond the first k positions can never displace the heap root, so the replay is unchanged.
@@ -1147,8 +1157,8 @@ __device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t
         bad |= !(m > 0.0f) || (i > 0 && !(m >= masses[i - 1]));
     }
     if (__syncthreads_or(bad)) return false;
-    lp = lut_params(masses[0], masses[np - 1]);
-    lut_build(masses, np, lp, lut, threadIdx.x, blockDim.x);
+    lp = lut_params(masses[0], masses[np - 1], SPEC_LUT_CELLS);
+    lut_build(masses, np, lp, lut, threadIdx.x, blockDim.x, SPEC_LUT_CELLS);
     __syncthreads();
     return true;
 }
@@ -1165,7 +1175,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
     ScoreRec* recs = reinterpret_cast<ScoreRec*>(tot + sc.lcap);
     uint32_t* order = reinterpret_cast<uint32_t*>(recs + sc.kparam);
     uint16_t* lut = reinterpret_cast<uint16_t*>(order + sc.kparam);
-    uint8_t* mark = reinterpret_cast<uint8_t*>(lut + LUT_CELLS);
+    uint8_t* mark = reinterpret_cast<uint8_t*>(lut + SPEC_LUT_CELLS);
     __shared__ uint32_t s_ntot, s_ncand, s_np, s_nvalid, s_next;
     __shared__ unsigned long long s_matched_peaks, s_scored;
     __shared__ float s_tic;

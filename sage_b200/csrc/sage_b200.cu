@@ -618,7 +618,7 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
         h_ims[i] = sp->inverse_ion_mobility ? sp->inverse_ion_mobility[c0 + i] : NAN;
     }
     memcpy(hs + C.o_chg, sp->precursor_charge + c0, n);
-    C.smem = (size_t)C.pmax * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + 2 * LUT_CELLS + C.pmax + 16;
+    C.smem = (size_t)C.pmax * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + 2 * SPEC_LUT_CELLS + C.pmax + 16;
     if (C.smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", C.pmax);
     C.nitems = (size_t)n * sv.qmax;
     if (C.nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
