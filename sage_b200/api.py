@@ -80,6 +80,8 @@ FEATURE_DTYPE = np.dtype([
     ("poisson", "<f8"), ("fragment_offset", "<u4"), ("fragment_count", "<u4"),
 ])
 assert FEATURE_DTYPE.itemsize == 128
+FRAGMENT_DTYPE = np.dtype([("kind", "<i4"), ("charge", "<i4"), ("ordinal", "<i4"), ("intensity", "<f4"), ("mz_calculated", "<f4"),
+                           ("mz_experimental", "<f4")])
 
 EXPORTED_SYMBOLS = [
     "sage_b200_device_count", "sage_b200_db_create", "sage_b200_db_build", "sage_b200_db_get_info", "sage_b200_db_export_index", "sage_b200_db_destroy",
@@ -378,6 +380,8 @@ class Scorer:
                  chimera=False, report_psms=1, wide_window=False, annotate_matches=False, score_type=0):
         self.db = db
         self.report_psms = int(report_psms)
+        self.fragment_capacity = None   # annotate_matches: size of the fragments array (default: generous estimate)
+        self.last_fragments = None      # Fragments rows of the last score_batch (Feature.fragment_offset/count index into it)
         p = CScorerParams()
         p.precursor_tol, p.fragment_tol = precursor_tol._c(), fragment_tol._c()
         p.min_matched_peaks = min_matched_peaks
@@ -414,6 +418,12 @@ class Scorer:
         keep: list = []
         cs = batch._c(keep)
         used = C.c_uint64(0)
+        if self._params.annotate_matches:
+            cap = int(self.fragment_capacity or (n * self.report_psms * 128 + 1024))
+            frags = np.zeros(cap, FRAGMENT_DTYPE)
+            _check(load_library().sage_b200_score_batch(self._h, C.byref(cs), _ptr(out), _ptr(counts), _ptr(frags), C.c_uint64(cap), C.byref(used)))
+            self.last_fragments = frags[:used.value]
+            return out, counts
         _check(load_library().sage_b200_score_batch(self._h, C.byref(cs), _ptr(out), _ptr(counts), None, C.c_uint64(0), C.byref(used)))
         return out, counts
 

@@ -126,7 +126,7 @@ struct QueryHits {
 struct ReplaySlot { unsigned long long off; uint32_t item, n_list, state /*0 = replay pending, 1 = nothing to do*/, k; };
 
 // Device counters (u64 slots)
-enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_PEPQ, C_PEPFALLBACK, C_WSLOT, C_WOVERFLOW, C_COUNT };
+enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_PEPQ, C_PEPFALLBACK, C_WSLOT, C_WOVERFLOW, C_FRAGS, C_COUNT };
 
 struct DbView {
     const uint2* frag;        // {peptide_index, fragment_mz bits}, reference bucket layout

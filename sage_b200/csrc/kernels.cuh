@@ -1148,6 +1148,52 @@ __device__ __forceinline__ uint32_t append_hits(uint64_t* buf, uint32_t len, uin
     return len;
 }
 
+struct FragmentOut { int32_t kind, charge, ordinal; float intensity, mz_calculated, mz_experimental; };  // == sage_b200_fragment
+
+// Fragments of one reported PSM (scoring.rs:738-751), written by one warp in the reference's order (kind, ion index, charge) to
+// out[0 .. matched_b + matched_y). Same lookups as score_candidate_warp on the same spectrum state.
+__device__ __forceinline__ void annotate_candidate_warp(const DbView& db, const ScorerView& sc, uint32_t pep, uint32_t charge, const SpecView& sp,
+                                                        FragmentOut* out, uint32_t cap_left) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t L = __ldg(db.pep_len + pep);
+    const uint32_t nions = L - 1;
+    const uint32_t nfc = max_fragment_charge(sc.max_fragment_charge_opt, charge) - 1;
+    const float* ions = db.ions + __ldg(db.ion_off + pep);
+    const uint32_t total = nions * nfc * db.n_kinds;
+    uint32_t written = 0;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t f = base + lane;
+        int pk = -1;
+        float mz = 0.f;
+        uint32_t idx = 0, kind_i = 0, fc = 1;
+        if (f < total) {
+            const uint32_t ki = f / nfc;
+            fc = f - ki * nfc + 1;
+            idx = ki;
+            while (idx >= nions) { idx -= nions; kind_i++; }
+            mz = __fdiv_rn(__ldg(ions + ki), (float)fc);
+            pk = sp.use_lut ? select_most_intense_peak_lut(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol, sp.lp, sp.lut)
+                            : select_most_intense_peak(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol);
+        }
+        const uint32_t ball = __ballot_sync(0xffffffffu, pk >= 0);
+        if (pk >= 0) {
+            const uint32_t pos = written + __popc(ball & ((1u << lane) - 1));
+            if (pos < cap_left) {
+                const bool is_n = (db.nterm_mask >> kind_i) & 1;
+                FragmentOut o;
+                o.kind = db.kinds[kind_i];
+                o.charge = (int32_t)fc;
+                o.ordinal = is_n ? (int32_t)idx + 1 : (int32_t)(L == 0 ? 0 : L - 1) - (int32_t)idx;   // scoring.rs:739-744
+                o.intensity = sp.intens[pk];
+                o.mz_calculated = __fadd_rn(mz, PROTON);            // scoring.rs:723
+                o.mz_experimental = __fadd_rn(sp.masses[pk], PROTON);  // scoring.rs:722
+                out[pos] = o;
+            }
+        }
+        written += __popc(ball);
+    }
+}
+
 // Validates that the (possibly peak-depleted) spectrum is ascending, positive and NaN-free and builds the bucket LUT; otherwise the
 // exact binary-search emulation is used for this spectrum.
 __device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t np, uint16_t* lut, LutParams& lp) {
@@ -1165,7 +1211,8 @@ __device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t
 
 // One CTA per spectrum.
 __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
-                                                         uint64_t* dbg_keys /*nullable: initial_hits dump*/, uint32_t* dbg_meta) {
+                                                         uint64_t* dbg_keys /*nullable: initial_hits dump*/, uint32_t* dbg_meta, FragmentOut* frag_out /*nullable*/,
+                                                         unsigned long long frag_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: masses[pmax] intens[pmax] cur[lcap] tot[lcap] recs[kparam] order[kparam] lut[256] mark[pmax]     (pmax is even)
     float* masses = reinterpret_cast<float*>(smem_raw);
@@ -1331,6 +1378,23 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
             f.poisson = isfinite(log10_poisson) ? log10_poisson : -INFINITY;
             f.fragment_offset = 0; f.fragment_count = 0;
             features[(size_t)s * sc.report_psms + nout + tid] = f;
+        }
+        if (frag_out != nullptr && emit) {   // annotate_matches: Fragments of every PSM reported in this round (scoring.rs:738-751)
+            __syncthreads();
+            for (uint32_t e = warp; e < emit; e += nwarps) {
+                const ScoreRec r = recs[order[e]];
+                const uint32_t cnt = (r.matched_b + r.matched_y) & 0xFFFF;
+                unsigned long long off = 0;
+                if (lane == 0) off = atomicAdd(b.counters + C_FRAGS, (unsigned long long)cnt);
+                off = __shfl_sync(0xffffffffu, off, 0);
+                const uint32_t cap_left = off >= frag_cap ? 0u : (uint32_t)min((unsigned long long)cnt, frag_cap - off);
+                annotate_candidate_warp(db, sc, r.peptide, r.charge, sv, frag_out + (off < frag_cap ? off : 0), cap_left);
+                if (lane == 0) {
+                    FeatureOut* fo = features + (size_t)s * sc.report_psms + nout + e;
+                    fo->fragment_offset = (uint32_t)off;
+                    fo->fragment_count = cnt;
+                }
+            }
         }
         nout += emit;
         if (!sc.chimera || emit == 0 || round + 1 == rounds) break;

@@ -448,6 +448,7 @@ struct Lane {
     DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_dbgk, d_dbgm, d_sort, d_sorttmp, d_wlist, d_wslots,
         d_ncap, d_noff, d_nlist, d_nslots, d_scantmp;
     PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
+    DevBuf d_frags;
     ChunkState chunk;
     // pending work of the chunk in flight
     bool ran = false, downloading = false;
@@ -457,7 +458,7 @@ struct Lane {
     bool f_pinned = false, c_pinned = false;
     void release() {
         for (DevBuf* b : {&d_small, &d_masses, &d_intens, &d_queries, &d_hits, &d_keys, &d_features, &d_counts, &d_counters, &d_dbgk, &d_dbgm, &d_sort, &d_sorttmp,
-                          &d_wlist, &d_wslots, &d_ncap, &d_noff, &d_nlist, &d_nslots, &d_scantmp}) b->release();
+                          &d_wlist, &d_wslots, &d_ncap, &d_noff, &d_nlist, &d_nslots, &d_scantmp, &d_frags}) b->release();
         for (PinBuf* b : {&h_small, &h_masses, &h_intens, &h_features, &h_counts, &h_counters}) b->release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -472,6 +473,9 @@ struct sage_b200_scorer {
     Lane lanes[2];
     DevBuf d_lnfact;
     int sort_spectra = 1;
+    // annotate_matches: caller's fragment array for the current call and the running global offset
+    sage_b200_fragment* frag_dst = nullptr;
+    uint64_t frag_cap = 0, frag_used = 0;
     int pipeline_chunks = 2;   // score_batch splits large batches into about this many chunks (>= 8192 spectra each)
     sage_b200_counters last{};
 };
@@ -482,7 +486,6 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     if (p->report_psms > K_MAX / 2) return fail(SAGE_B200_ELIMIT, "report_psms %u > %d not supported", p->report_psms, K_MAX / 2);
     if (p->precursor_tol.kind < 0 || p->precursor_tol.kind > 2 || p->fragment_tol.kind < 0 || p->fragment_tol.kind > 2) return fail(SAGE_B200_EINVAL, "bad tolerance kind");
     if (p->score_type > 1) return fail(SAGE_B200_EINVAL, "bad score_type");
-    if (p->annotate_matches) return fail(SAGE_B200_ELIMIT, "annotate_matches (Fragments output) is not implemented in this round");
     CUDA_TRY(cudaSetDevice(db->device));
     sage_b200_scorer* s = new sage_b200_scorer();
     s->db = db;
@@ -630,7 +633,7 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
     if ((rc = L.d_features.reserve((size_t)n * sv.report_psms * sizeof(FeatureOut)))) return rc;
     if ((rc = L.d_counts.reserve(4 * (size_t)n))) return rc;
     if ((rc = L.d_counters.reserve(8 * C_COUNT))) return rc;
-    if ((rc = L.h_counters.reserve(8 * C_COUNT + 16))) return rc;
+    if ((rc = L.h_counters.reserve(8 * C_COUNT + 32))) return rc;
 
     CUDA_TRY(cudaEventRecord(L.ev[0], st));
     CUDA_TRY(cudaMemcpyAsync(L.d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, st));
@@ -691,6 +694,13 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
 
     CUDA_TRY(cudaEventRecord(L.ev[6], st));
     CUDA_TRY(cudaMemsetAsync(L.d_counters.p, 0, 8 * C_COUNT, st));
+    const bool annotate = sv.annotate && S->frag_dst != nullptr;
+    if (annotate) {   // fragment offsets are global across the chunks of one call: start this chunk's counter at what was used so far
+        if ((rc = L.d_frags.reserve(S->frag_cap * sizeof(sage_b200_fragment) + 64))) return rc;
+        unsigned long long* hbase = (unsigned long long*)L.h_counters.p + C_COUNT + 1;
+        *hbase = S->frag_used;
+        CUDA_TRY(cudaMemcpyAsync(L.d_counters.as<unsigned long long>() + C_FRAGS, hbase, 8, cudaMemcpyHostToDevice, st));
+    }
     // ---- setup: resolve precursor windows. Peptide-centric counting needs LO/HI bound arrays of nfc_max * pmax floats in smem.
     ScorerView svq = sv;
     uint32_t mfc = sv.max_fragment_charge_opt >= 0 ? std::min<uint32_t>(C.zmax, (uint32_t)(sv.max_fragment_charge_opt + 1) & 0xFF) : C.zmax;
@@ -766,7 +776,8 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     // ---- candidate scoring + feature assembly
     CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));
     k_score<<<n, SCORE_THREADS, C.smem, st>>>(db->v, sv, bv, L.d_features.as<FeatureOut>(), L.d_counts.as<uint32_t>(), C.pmax,
-                                             dbg ? L.d_dbgk.as<uint64_t>() : nullptr, dbg ? L.d_dbgm.as<uint32_t>() : nullptr);
+                                             dbg ? L.d_dbgk.as<uint64_t>() : nullptr, dbg ? L.d_dbgm.as<uint32_t>() : nullptr,
+                                             annotate ? L.d_frags.as<FragmentOut>() : nullptr, (unsigned long long)S->frag_cap);
     CUDA_TRY(cudaGetLastError());
     launches++;
     CUDA_TRY(cudaEventRecord(L.ev[4], st));
@@ -816,6 +827,15 @@ static int lane_finish(sage_b200_scorer* S, Lane& L) {
         T.wide_queries += hc[C_WIDE]; T.pep_queries += hc[C_PEPQ]; T.pep_fallbacks += hc[C_PEPFALLBACK]; T.wide_overflows += hc[C_WOVERFLOW];
         T.d2h_bytes += 2 * 8 * C_COUNT;
         T.kernel_launches += L.launches;
+        if (S->sv.annotate && S->frag_dst != nullptr) {
+            const uint64_t end = hc[C_FRAGS], begin = S->frag_used;
+            const uint64_t lim = std::min<uint64_t>(end, S->frag_cap);
+            if (lim > begin) {
+                CUDA_TRY(cudaMemcpy(S->frag_dst + begin, L.d_frags.as<sage_b200_fragment>() + begin, (lim - begin) * sizeof(sage_b200_fragment), cudaMemcpyDeviceToHost));
+                T.d2h_bytes += (lim - begin) * sizeof(sage_b200_fragment);
+            }
+            S->frag_used = end;
+        }
         L.ran = false;
     }
     if (L.downloading) {
@@ -847,7 +867,6 @@ static int check_spectra(const sage_b200_spectra* sp) {
 
 extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectra* sp, sage_b200_feature* features, uint32_t* counts,
                                      sage_b200_fragment* fragments, uint64_t fragment_capacity, uint64_t* fragments_used) {
-    (void)fragments; (void)fragment_capacity;
     if (!S) return fail(SAGE_B200_EINVAL, "score_batch: null scorer");
     int rc = check_spectra(sp);
     if (rc) return rc;
@@ -856,6 +875,11 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
     CUDA_TRY(cudaSetDevice(S->db->device));
     S->last = sage_b200_counters{};
     if (fragments_used) *fragments_used = 0;
+    const bool annotate = S->sv.annotate != 0;
+    if (annotate && (!fragments || !fragments_used)) return fail(SAGE_B200_EINVAL, "annotate_matches needs a fragments array and fragments_used");
+    S->frag_dst = annotate ? fragments : nullptr;
+    S->frag_cap = annotate ? fragment_capacity : 0;
+    S->frag_used = 0;
     for (Lane& L : S->lanes) { L.chunk.loaded = false; L.ran = false; L.downloading = false; }
     // Chunks are bounded by spectra and peak counts (device staging) and sized so that a large batch becomes ~pipeline_chunks chunks:
     // two lanes alternate, so the H2D of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i.
@@ -873,14 +897,22 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
         if ((rc = chunk_upload(S, L, sp, c0, c1))) return rc;
         if ((rc = chunk_run(S, L, false))) return rc;
         if ((rc = chunk_download(S, L, features + c0 * S->sv.report_psms, counts + c0))) return rc;
+        if (annotate && (rc = lane_finish(S, L))) return rc;   // fragment offsets are global: chunks run one after another
         c0 = c1;
-        li ^= 1;
+        if (!annotate) li ^= 1;
     }
     for (Lane& L : S->lanes) {
         if ((rc = lane_finish(S, L))) return rc;
         L.chunk.loaded = false;
     }
     finish_counters(S);
+    if (annotate) {
+        *fragments_used = S->frag_used;
+        S->frag_dst = nullptr;
+        if (S->frag_used > fragment_capacity)
+            return fail(SAGE_B200_ELIMIT, "fragment_capacity %llu too small: %llu fragments matched (features are complete; re-run with a larger array)",
+                        (unsigned long long)fragment_capacity, (unsigned long long)S->frag_used);
+    }
     return 0;
 }
 

@@ -1,0 +1,73 @@
+"""BASELINE.json-size checks (cfg2 / cfg4 shapes: ~1.9 M peptides, 49 M fragments): oracle parity on samples the CPU finishes in seconds,
+and size-independent properties over the full 50 k-spectrum batch."""
+import numpy as np
+import pytest
+
+from sage_b200 import IndexedDatabase, Scorer, Tolerance, synth
+
+from helpers import assert_features_equal, oracle_cfg, oracle_db_from_peptides
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full():
+    pep = synth.make_peptides(2_000_000)
+    spectra = synth.make_spectra(pep, 50_000, seed=0xB202)
+    gdb = IndexedDatabase.build_from_peptides(pep)
+    odb = oracle_db_from_peptides(pep)
+    return pep, spectra, gdb, odb
+
+
+def test_index_matches_oracle_at_scale(full):
+    pep, _, gdb, odb = full
+    fp, fm, bm = gdb.export_index()
+    e = odb.export()
+    assert np.array_equal(bm.view(np.uint32), e["bucket_min"].view(np.uint32))
+    assert np.array_equal(fp, e["frag_pep"]) and np.array_equal(fm.view(np.uint32), e["frag_mz"].view(np.uint32))
+    # index invariants (crates/sage/tests/integration.rs:39-52): PeptideIx ascending inside a bucket, bucket minima ascending
+    bs = gdb.info["bucket_size"]
+    d = np.diff(fp.astype(np.int64))
+    assert np.all(d[np.arange(len(d)) % bs != bs - 1] >= 0) and np.all(np.diff(bm) >= 0)
+
+
+def test_cfg2_sample_parity_and_properties(full):
+    pep, spectra, gdb, odb = full
+    kw = dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=2)
+    sc = Scorer(gdb, **kw)
+    gf, gc = sc.score_batch(spectra)
+    # oracle parity on a 3000-spectrum sample spread over the batch
+    for a in (0, 23_000, 47_000):
+        sub = spectra.slice(a, a + 1000)
+        of, oc, _, _ = odb.score_batch(oracle_cfg(**kw), sub.as_dict())
+        of = of.copy()
+        of["spectrum"] += np.uint32(a)
+        assert_features_equal(gf[2 * a:2 * (a + 1000)], gc[a:a + 1000], of, oc, 2, what=f"cfg2 sample @{a}")
+    # properties over all 50k spectra
+    sel = (np.arange(len(gf)) % 2) < np.repeat(gc, 2)
+    g = gf[sel]
+    assert gc.sum() > 45_000
+    assert np.all(g["matched_peaks"] >= 4) and np.all(g["rank"] >= 1) and np.all(g["rank"] <= 2)
+    two = gc == 2
+    assert np.all(gf[0::2]["hyperscore"][two] >= gf[1::2]["hyperscore"][two])          # sorted by hyperscore
+    assert np.allclose(gf[0::2]["delta_next"][two], gf[0::2]["hyperscore"][two] - gf[1::2]["hyperscore"][two], rtol=0, atol=1e-9)
+    assert np.all(np.abs(g["delta_mass"]) <= 20.01 + 1e-3)                              # inside the precursor tolerance
+    # sharding invariance: halves scored separately give the same rows (spectrum index rebased)
+    h0, c0 = sc.score_batch(spectra.slice(0, 25_000))
+    h1, c1 = sc.score_batch(spectra.slice(25_000, 50_000))
+    h1 = h1.copy()
+    h1["spectrum"] += np.uint32(25_000)
+    both, cb = np.concatenate([h0, h1]), np.concatenate([c0, c1])
+    assert np.array_equal(cb, gc) and both[sel].tobytes() == gf[sel].tobytes()
+
+
+def test_cfg4_sample_parity(full):
+    pep, spectra, gdb, odb = full
+    kw = dict(precursor_tol=Tolerance.da(-500, 500), fragment_tol=Tolerance.ppm(-20, 20))
+    sub = spectra.slice(1000, 1096)
+    sc = Scorer(gdb, **kw)
+    gf, gc = sc.score_batch(sub)
+    of, oc, _, octr = odb.score_batch(oracle_cfg(**kw), sub.as_dict(), counters=True)
+    assert_features_equal(gf, gc, of, oc, 1, what="cfg4 sample")
+    c = sc.counters()
+    assert c["wide_queries"] == 96 and c["entries_scanned"] == octr["entries_scanned"] and c["pages"] == octr["pages"]

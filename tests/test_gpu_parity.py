@@ -175,6 +175,36 @@ def test_tolerance_kinds_and_openms_score(small):
     run_both(odb, gdb, spectra.slice(0, 400), precursor_tol=Tolerance.pct(-0.01, 0.01), fragment_tol=Tolerance.da(-0.02, 0.02), score_type=1)
 
 
+def test_annotate_matches_fragments(small):
+    # Fragments of every reported PSM (scoring.rs:738-751), standard and chimera paths
+    pep, odb, gdb, spectra = small
+    for kw, sub in ((dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=3, annotate_matches=True), spectra.slice(0, 500)),
+                    (dict(precursor_tol=Tolerance.da(-1.5, 1.5), fragment_tol=Tolerance.ppm(-20, 20), chimera=True, report_psms=3, annotate_matches=True,
+                          max_fragment_charge=2), synth.make_spectra(pep, 300, seed=14, chimeric=True))):
+        sc = Scorer(gdb, **kw)
+        gf, gc = sc.score_batch(sub)
+        gfr = sc.last_fragments
+        of, oc, ofr, _ = odb.score_batch(oracle_cfg(**kw), sub.as_dict())
+        n = assert_features_equal(gf, gc, of, oc, 3, what="annotate")
+        sel = (np.arange(len(gf)) % 3) < np.repeat(gc, 3)
+        g, o = gf[sel], of[sel]
+        assert n > 100 and len(gfr) == len(ofr) == int(g["fragment_count"].sum())
+        for a, b_ in zip(g, o):
+            assert a["fragment_count"] == b_["frag_count"] == a["matched_peaks"]
+            x = gfr[a["fragment_offset"]:a["fragment_offset"] + a["fragment_count"]]
+            y = ofr[b_["frag_offset"]:b_["frag_offset"] + b_["frag_count"]]
+            for f in ("kind", "charge", "ordinal"):
+                assert np.array_equal(x[f], y[f]), f
+            for f in ("intensity", "mz_calculated", "mz_experimental"):
+                assert np.array_equal(x[f].view(np.uint32), y[f].view(np.uint32)), f
+    # capacity too small -> ELIMIT with the required size reported, features still complete
+    sc = Scorer(gdb, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), annotate_matches=True)
+    sc.fragment_capacity = 16
+    with pytest.raises(sage_b200.SageB200Error) as e:
+        sc.score_batch(spectra.slice(0, 100))
+    assert e.value.code == -5 and "fragment_capacity" in e.value.message
+
+
 def test_initial_hits_heap_order(small):
     # white box: the preliminary list must come back in the reference's bounded_min_heapify order
     pep, odb, gdb, spectra = small
