@@ -171,6 +171,7 @@ struct ScorerView {
 
 struct BatchView {
     uint32_t n;                 // spectra in this chunk
+    uint32_t spectrum_base;     // index of the chunk's first spectrum in the caller's batch (Feature.spectrum is batch-relative)
     const uint32_t* peak_off;   // n+1
     const float* masses;
     const float* intens;

@@ -1361,7 +1361,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
             const uint32_t plen = r.plen;
             const float sum = __fadd_rn(r.summed_b, r.summed_y);
             FeatureOut f;
-            f.spectrum = s; f.peptide_idx = r.peptide; f.peptide_len = plen;
+            f.spectrum = b.spectrum_base + s; f.peptide_idx = r.peptide; f.peptide_len = plen;
             f.rank = sc.chimera ? round + 1 : tid + 1;
             f.label = (db.pep_flags[r.peptide] & 1) ? -1 : 1;
             f.expmass = precursor_mass; f.calcmass = mono; f.charge = r.charge;

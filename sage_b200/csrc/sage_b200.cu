@@ -433,7 +433,7 @@ extern "C" int sage_b200_db_export_index(const sage_b200_db* db, uint32_t* fragm
 // ------------------------------------------------------------------------------------------------ scorer
 struct ChunkState {
     bool loaded = false;
-    uint32_t n = 0, pmax = 2, zmax = 1;
+    uint32_t n = 0, pmax = 2, zmax = 1, base = 0;
     uint64_t npk = 0;
     size_t nitems = 0, smem = 0, small_bytes = 0;
     size_t o_off = 0, o_pmz = 0, o_tic = 0, o_ilo = 0, o_ihi = 0, o_rt = 0, o_ims = 0, o_chg = 0;
@@ -580,7 +580,7 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
     const uint64_t pk0 = sp->peak_offsets[c0], pk1 = sp->peak_offsets[c1];
     const uint64_t npk = pk1 - pk0;
     if (npk > 0xFFFFFFF0ull) return fail(SAGE_B200_ELIMIT, "chunk has too many peaks");
-    C.n = n; C.npk = npk;
+    C.n = n; C.npk = npk; C.base = (uint32_t)c0;
     // small per-spectrum arrays -> one pinned blob -> one H2D
     C.o_off = 0;
     C.o_pmz = align_up(C.o_off + 4 * (size_t)(n + 1), 16);
@@ -677,6 +677,7 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     BatchView bv{};
     unsigned char* ds = (unsigned char*)L.d_small.p;
     bv.n = n;
+    bv.spectrum_base = C.base;
     bv.peak_off = (const uint32_t*)(ds + C.o_off);
     bv.masses = L.d_masses.as<float>();
     bv.intens = L.d_intens.as<float>();

