@@ -164,6 +164,7 @@ struct ScorerView {
     uint32_t lcap;     // list capacity for merges
     uint32_t pep_cap;  // precursor windows up to this many peptides use the peptide-centric kernel path (0 = never)
     uint32_t wide_tile;        // peptides per shared-memory tile of the wide kernel
+    uint32_t wide_variant;     // A/B switch for the wide streaming filter (1 = m/z window as one unsigned compare)
     uint32_t wide_lmax;        // survivor-list capacity per query (<= WIDE_LMAX; smaller only in tests)
     const double* lnfact_tab;  // lnfact(n) for n < lnfact_n, computed on the host with libm log (scoring.rs:170-177)
     uint32_t lnfact_n;

@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
 // tile to tile (one binary search per visit and tile), whole warps stream the sub-slices with coalesced 8-byte loads (4 in
 // flight per lane), matches become shared-memory atomics, and after each tile the exact trim (heap replay in index order)
 // consumes the tile's counts straight from shared memory. Every index entry of [inner_left, inner_right) is read exactly once.
-constexpr int WIDE_THREADS = 512;
+constexpr int WIDE_THREADS = 1024;
 constexpr uint32_t WIDE_TILE = 80 * 1024;    // peptides per tile (u16 counts: 160 KB)
 constexpr uint32_t WIDE_VMAX = 2048;         // page visits whose running position is cached in smem
 constexpr uint32_t WIDE_TCACHE = 2048;       // (peak, charge) probes whose bucket range is cached in smem
@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         const uint32_t T0 = max(TILE / 8, 256u) & ~7u, T1 = max(TILE / 4, 256u) & ~7u;
         const uint32_t ntiles = n <= T0 ? 1 : (n <= T0 + T1 ? 2 : 2 + (n - T0 - T1 + TILE - 1) / TILE);
         uint32_t my_matched = 0, my_pages = 0, nz = 0;
+        uint32_t msum = 0;   // sum of all slot counts == matched_peaks of this query (replaces per-match counting in the streaming loop)
         long long my_entries = 0;
         auto tile_d0 = [&](uint32_t t) -> uint32_t { return t == 0 ? 0 : (t == 1 ? T0 : T0 + T1 + (t - 2) * TILE); };
 
@@ -590,13 +591,23 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                 // from each (8 loads = 2 KB in flight per warp, 32 KB per CTA)
                 const WideFast& F = S.u.fast;
                 const uint32_t nvis = S.s_nvis;
-                for (uint32_t v0 = warp * 2; v0 < nvis; v0 += nwarps * 2) {
+                // tile-specific accepted PeptideIx range as one unsigned compare: (pep - t_lo) <= t_span
+                const uint32_t t_lo = max(q.eff_lo, pep_lo);
+                const uint32_t t_hi = min(q.eff_hi, pep_hi_excl - 1);
+                const bool t_any = q.eff_lo <= q.eff_hi && t_lo <= t_hi;
+                const uint32_t t_span = t_any ? t_hi - t_lo : 0u;
+                for (uint32_t v0 = warp * 2; t_any && v0 < nvis; v0 += nwarps * 2) {
                     const uint32_t v1 = min(v0 + 1, nvis - 1);
                     const uint32_t stA = F.B[v0 * nb1 + tile], lnA = F.B[v0 * nb1 + tile + 1] - stA;
                     const uint32_t stB = F.B[v1 * nb1 + tile], lnB = v0 + 1 < nvis ? F.B[v1 * nb1 + tile + 1] - stB : 0;
                     const uint2* srcA = db.frag + (uint64_t)F.vpage[v0] * db.bucket_size + stA;
                     const uint2* srcB = db.frag + (uint64_t)F.vpage[v1] * db.bucket_size + stB;
+                    // m/z window as one unsigned compare on the bit patterns (exact for flo > 0: positive floats order like their bits);
+                    // otherwise an always-false bit window and the float compare decides
                     const float floA = F.vflo[v0], fhiA = F.vfhi[v0], floB = F.vflo[v1], fhiB = F.vfhi[v1];
+                    const bool bitsA = floA > 0.0f && fhiA >= floA, bitsB = floB > 0.0f && fhiB >= floB;
+                    const uint32_t lbA = __float_as_uint(floA), spA = __float_as_uint(fhiA) - lbA;
+                    const uint32_t lbB = __float_as_uint(floB), spB = __float_as_uint(fhiB) - lbB;
                     const uint32_t mx = max(lnA, lnB);
                     for (uint32_t e0 = 0; e0 < mx; e0 += 128) {
                         uint2 fa[4], fb[4];
@@ -608,17 +619,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                         }
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            const float ma = __uint_as_float(fa[u].y), mb = __uint_as_float(fb[u].y);
-                            if (fa[u].x >= q.eff_lo && fa[u].x <= q.eff_hi && ma >= floA && ma <= fhiA) {
-                                const uint32_t idx = fa[u].x - pep_lo;   // < dn by construction of the sub-slice
-                                atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16));
-                                my_matched++;
-                            }
-                            if (fb[u].x >= q.eff_lo && fb[u].x <= q.eff_hi && mb >= floB && mb <= fhiB) {
-                                const uint32_t idx = fb[u].x - pep_lo;
-                                atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16));
-                                my_matched++;
-                            }
+                            bool ha = fa[u].x - t_lo <= t_span, hb = fb[u].x - t_lo <= t_span;
+                            if (bitsA && sc.wide_variant) ha = ha && (fa[u].y - lbA <= spA);
+                            else { const float m = __uint_as_float(fa[u].y); ha = ha && m >= floA && m <= fhiA; }
+                            if (bitsB && sc.wide_variant) hb = hb && (fb[u].y - lbB <= spB);
+                            else { const float m = __uint_as_float(fb[u].y); hb = hb && m >= floB && m <= fhiB; }
+                            if (ha) { const uint32_t idx = fa[u].x - pep_lo; atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16)); }
+                            if (hb) { const uint32_t idx = fb[u].x - pep_lo; atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16)); }
                         }
                     }
                 }
@@ -724,6 +731,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                 for (uint32_t i = tid; i < k; i += WIDE_THREADS) {
                     const uint32_t c = cnt(i);
                     nz += c != 0;
+                    msum += c;
                     if (c) atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
                     list[i] = c ? prescore_key(c, q.pre_lo + i, q.charge, q.iso) : PRESCORE_DEFAULT;
                 }
@@ -757,6 +765,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                         for (int u = 0; u < 4; u++) {
                             nzm += __popc(__vcmpne2(ww[u], 0u));
                             svm += __popc(__vcmpgeu2(ww[u], lvl2) & __vcmpne2(ww[u], 0u));
+                            msum += (ww[u] & 0xFFFFu) + (ww[u] >> 16);
                         }
                         nz += nzm >> 4;
                         wcount += svm >> 4;
@@ -766,7 +775,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                     for (int u = 0; u < 8; u++) {
                         const uint32_t c = (ww[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu;
                         if (c && i + u >= scan_from && i + u < dn) {
-                            if (edge) { nz++; wcount += c >= level; }
+                            if (edge) { nz++; wcount += c >= level; msum += c; }
                             if (c >= level) atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
                         }
                     }
@@ -847,7 +856,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                     for (int u = 0; u < 2; u++) {
                         const uint32_t i = base + 2 * tid + u;
                         const uint32_t c = i < dn ? cnt(i) : 0;
-                        if (count_nz) nz += c != 0;
+                        if (count_nz) { nz += c != 0; msum += c; }
                         const uint64_t kk = prescore_key(c, q.pre_lo + d0 + i, q.charge, q.iso);
                         if (c != 0 && kk > hmin) key[ncand++] = kk;
                     }
@@ -880,7 +889,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
             }
             __syncthreads();
         }
-        const uint32_t matched_total = block_sum_u32(my_matched, S.s_warp);
+        (void)my_matched;
+        const uint32_t matched_total = block_sum_u32(msum, S.s_warp);
         const uint32_t pages_total = block_sum_u32(my_pages, S.s_warp);
         const uint32_t nonzero_total = block_sum_u32(nz, S.s_warp);
         // entries: sum of (inner_right - inner_left) over page visits; per-thread partial sums can be negative, total is not

@@ -275,7 +275,7 @@ extern "C" int sage_b200_db_create(const sage_b200_peptides* peptides, const sag
     db->v.n_frag = nf;
     db->v.n_bucket = (uint32_t)index->n_buckets;
     db->v.bucket_size = (uint32_t)index->bucket_size;
-    if ((rc = dmalloc(db, &db->d_frag, 8 * nf))) { sage_b200_db_destroy(db); return rc; }
+    if ((rc = dmalloc(db, &db->d_frag, 8 * nf + 64))) { sage_b200_db_destroy(db); return rc; }
     if ((rc = dmalloc(db, &db->d_bucket_min, 4 * index->n_buckets))) { sage_b200_db_destroy(db); return rc; }
     void *t_pep = nullptr, *t_mz = nullptr;
     auto cleanup = [&]() { if (t_pep) cudaFree(t_pep); if (t_mz) cudaFree(t_mz); };
@@ -357,7 +357,7 @@ extern "C" int sage_b200_db_build(const sage_b200_peptides* peptides, uint64_t b
     db->v.bucket_size = (uint32_t)bucket_size;
     db->v.min_ion_index = (uint32_t)std::min<uint64_t>(min_ion_index, 0xFFFFFFFFull);
     db->v.pep_centric_ok = 1;  // the index is generated from the ion table with this filter by construction
-    if ((rc = dmalloc(db, &db->d_frag, 8 * nf))) { sage_b200_db_destroy(db); return rc; }
+    if ((rc = dmalloc(db, &db->d_frag, 8 * nf + 64))) { sage_b200_db_destroy(db); return rc; }
     if ((rc = dmalloc(db, &db->d_bucket_min, 4 * nb))) { sage_b200_db_destroy(db); return rc; }
     db->v.frag = (const uint2*)db->d_frag;
     db->v.bucket_min = (const float*)db->d_bucket_min;
@@ -508,6 +508,8 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     v.lcap = std::max<uint32_t>(std::max<uint32_t>(v.n_iso, v.n_ch_max), 1) * v.kparam;
     v.wide_tile = WIDE_TILE;
     v.wide_lmax = WIDE_LMAX;
+    v.wide_variant = 0;  // measured: float compares 142 ms vs unsigned bit-window 150 ms on cfg4
+    if (const char* e = getenv("SAGE_B200_WIDE_VARIANT")) v.wide_variant = (uint32_t)atoi(e);
     v.pep_cap = 64;  // measured crossover on cfg2 (mean window 177 peptides): index probing wins above ~100 candidates
     if (const char* e = getenv("SAGE_B200_PEP_CAP")) v.pep_cap = (uint32_t)std::min<long>(std::max<long>(atol(e), 0), (long)NARROW_CAP);
     {   // lnfact table with the host libm (the reference's f64::ln): Stirling form of scoring.rs:170-177
