@@ -33,6 +33,9 @@ WORKLOADS = {
     # name: (n_spectra, n_peptides_target, scorer kwargs (tolerances as (kind, lo, hi)), spectra kwargs, cpu sample)
     "cfg2": dict(desc="50k synthetic MS2 spectra (200 peaks) vs ~2M-peptide tryptic index, +-20 ppm precursor, +-20 ppm fragment", n_spectra=50_000,
                  n_peptides=2_000_000, scorer=dict(precursor_tol=(0, -20.0, 20.0), fragment_tol=(0, -20.0, 20.0)), spectra={}, cpu_sample=50_000),
+    "cfg3": dict(desc="25k spectra per GPU (200k / 8-GPU shard) vs a larger index with variable M oxidation + static C (target 12M -> ~7M peptides), "
+                 "+-20 ppm / +-20 ppm", n_spectra=25_000, n_peptides=12_000_000, peptides=dict(var_mod_m=True, static_c=True),
+                 scorer=dict(precursor_tol=(0, -20.0, 20.0), fragment_tol=(0, -20.0, 20.0)), spectra={}, cpu_sample=5_000),
     "cfg4": dict(desc="open search: 50k spectra, -500..+500 Da precursor window, ~2M-peptide tryptic index, +-20 ppm fragment", n_spectra=50_000,
                  n_peptides=2_000_000, scorer=dict(precursor_tol=(2, -500.0, 500.0), fragment_tol=(0, -20.0, 20.0)), spectra={}, cpu_sample=512),
     "cfg5": dict(desc="chimeric search (report_psms=5) on 100k co-fragmenting spectra, +-20 ppm / +-20 ppm", n_spectra=100_000, n_peptides=2_000_000,
@@ -50,7 +53,8 @@ def log(*a):
 def load_or_make(name, wl, rank):
     """Synthetic peptide table (shared by all ranks) and this rank's spectra; cached under /tmp to keep reruns short."""
     from sage_b200 import Peptides, SpectraBatch, synth
-    cache = f"/tmp/sage_b200_pep_{wl['n_peptides']}.npz"
+    pk = wl.get("peptides", {})
+    cache = f"/tmp/sage_b200_pep_{wl['n_peptides']}_{int(pk.get('var_mod_m', False))}{int(pk.get('static_c', False))}.npz"
     t0 = time.time()
     pep = None
     if os.path.exists(cache):
@@ -60,7 +64,7 @@ def load_or_make(name, wl, rank):
         except Exception:
             pep = None
     if pep is None:
-        pep = synth.make_peptides(wl["n_peptides"])
+        pep = synth.make_peptides(wl["n_peptides"], **pk)
         if rank == 0:
             tmp = cache + f".{os.getpid()}.tmp.npz"
             np.savez(tmp, **pep.__dict__)
