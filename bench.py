@@ -137,7 +137,7 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def oracle_throughput(pep, spectra, wl, steps, warmup, threads=0):
+def oracle_throughput(pep, spectra, wl, steps, warmup, threads=0, check=None):
     """Times the CPU oracle (OpenMP over spectra) on a bounded sample of the same workload. Returns list of spectra/s per step."""
     threads = threads or host_threads()
     from oracle import oracle as O
@@ -166,6 +166,14 @@ def oracle_throughput(pep, spectra, wl, steps, warmup, threads=0):
         dt = time.perf_counter() - t
         if i >= warmup:
             rates.append(ns / dt)
+    if check is not None:   # parity of the measured GPU results against the oracle on the CPU sample (same run, same inputs)
+        from helpers import assert_features_equal
+        gf, gc = check
+        r = cfg.report_psms
+        of, oc, _, _ = odb.score_batch(cfg, sub, nthreads=threads)
+        check_n = assert_features_equal(gf[:ns * r], gc[:ns], of, oc, r, what="bench parity check")
+        log(f"parity check: {check_n} PSMs of {ns} spectra identical to the oracle")
+        return rates, ns, threads, check_n
     return rates, ns, threads
 
 
@@ -319,7 +327,9 @@ def main():
               "psms_per_step_rank0": psms}
 
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
-        rates, ns, cores = oracle_throughput(pep, spectra, wl, steps=2, warmup=1)
+        rates, ns, cores, check_n = oracle_throughput(pep, spectra, wl, steps=2, warmup=1, check=(np.array(out), np.array(counts)))
+        result["parity_checked"] = {"spectra": ns, "psms_identical_to_oracle": check_n,
+                                    "tolerance": "integer/f32 fields bit-exact; f64 scores rtol 1e-6 (tests/helpers.py)"}
         result["cpu_baseline"] = {"value": float(max(rates)), "unit": "spectra/s", "cores": cores, "kind": "port",
                                   "sample": f"{ns} spectra of the same workload, best of 2 after 1 warm-up; C++ port of sage-core's Scorer::score, OpenMP over spectra"}
     if rank == 0:
