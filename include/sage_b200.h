@@ -163,6 +163,10 @@ int sage_b200_scorer_set_option(sage_b200_scorer* scorer, const char* name, int6
 int sage_b200_score_batch(sage_b200_scorer* scorer, const sage_b200_spectra* spectra, sage_b200_feature* features, uint32_t* counts,
                           sage_b200_fragment* fragments, uint64_t fragment_capacity, uint64_t* fragments_used);
 
+/* Scorer::quick_score over a batch (scoring.rs:255-298; prefilter of runner.rs:143-278). keep has one byte per peptide of the db and is
+ * OR-ed (the reference stores `true` into &[AtomicBool]). prefilter_low_memory selects the branch of scoring.rs:270. */
+int sage_b200_quick_score(sage_b200_scorer* scorer, const sage_b200_spectra* spectra, int prefilter_low_memory, uint8_t* keep);
+
 /* The same call split in phases for device-resident reuse (one batch of <= 131072 spectra / 2^25 peaks):
  * upload makes the spectra resident in HBM, run launches the kernels (results stay on the device; may be repeated),
  * download copies the Feature rows back. score_batch == upload + run + download per chunk. */

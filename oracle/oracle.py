@@ -83,6 +83,7 @@ def lib():
                   "so_ion_series", "so_process_ms2", "so_page_search"):
             getattr(_lib, f).restype = C.c_uint64
         _lib.so_score_batch.restype = C.c_int64
+        _lib.so_quick_score.restype = C.c_int64
         _lib.so_initial_hits.restype = C.c_int64
         _lib.so_max_fragment_charge.restype = C.c_uint8
     return _lib
@@ -261,6 +262,22 @@ class OracleDB:
         if frag is not None:
             frag = frag[:frag_used.value]
         return out, counts, frag, (dict(zip(COUNTER_FIELDS, list(ctr))) if counters else None)
+
+    def quick_score(self, cfg: ScorerConfig, spectra: dict, low_memory: bool) -> np.ndarray:
+        """Scorer::quick_score (scoring.rs:255-298) over a batch -> keep[n_peptides] (uint8)."""
+        n = len(spectra["prec_mz"])
+        keep = np.zeros(self.n_peptides, np.uint8)
+        peak_off = np.ascontiguousarray(spectra["peak_off"], dtype=np.uint64)
+        masses, intens = _f32(spectra["masses"]), _f32(spectra["intensities"])
+        prec_mz, tic = _f32(spectra["prec_mz"]), _f32(spectra["tic"])
+        prec_charge = np.ascontiguousarray(spectra["prec_charge"], dtype=np.uint8)
+        iso_lo, iso_hi = _f32(spectra["iso_lo"]), _f32(spectra["iso_hi"])
+        sp = cfg.to_c()
+        rc = lib().so_quick_score(self.h, C.byref(sp), C.c_uint64(n), _p(peak_off), _p(masses), _p(intens), _p(prec_mz), _p(prec_charge), _p(iso_lo),
+                                  _p(iso_hi), _p(tic), C.c_int(int(low_memory)), _p(keep))
+        if rc != 0:
+            raise RuntimeError(f"oracle: reference would panic (code {rc})")
+        return keep
 
     def initial_hits(self, cfg: ScorerConfig, masses, intens, prec_mz, prec_charge=0, iso_lo=np.nan, iso_hi=np.nan):
         cap = 1 << 22

@@ -1017,6 +1017,43 @@ struct Scorer {  // :210-232
         }
         return cands;
     }
+    // :255-298 quick_score (prefilter). `keep` has one byte per peptide.
+    // The low-memory branch calls bounded_min_heapify on Vec<Score>; heap.rs compares with `<` / `>`, i.e. Score's DERIVED PartialOrd
+    // (lexicographic, first field = peptide, scoring.rs:17-30), not its hyperscore Ord — restated literally.
+    int quick_score(const Spectrum& q, bool low_memory, uint8_t* keep) const {
+        if (q.level != 2) return -1;
+        if (!q.has_precursor) return -2;
+        InitialHits hits = initial_hits(q, q.precursor, nullptr);
+        if (low_memory) {
+            std::vector<Score> sv;
+            for (const PreScore& p : hits.preliminary) {
+                if (p.peptide == 0xFFFFFFFFu) continue;
+                Score sc = score_candidate(q, p, nullptr, nullptr);
+                if ((unsigned)(sc.matched_b + sc.matched_y) < min_matched_peaks) continue;
+                sv.push_back(sc);
+            }
+            size_t k = std::min(report_psms, sv.size());
+            auto lt = [](const Score& a, const Score& b) {  // derived PartialOrd::lt; a NaN field makes the comparison false
+                if (a.peptide != b.peptide) return a.peptide < b.peptide;
+                if (a.matched_b != b.matched_b) return a.matched_b < b.matched_b;
+                if (a.matched_y != b.matched_y) return a.matched_y < b.matched_y;
+                if (!(a.summed_b == b.summed_b)) return a.summed_b < b.summed_b;
+                if (!(a.summed_y == b.summed_y)) return a.summed_y < b.summed_y;
+                if (a.longest_b != b.longest_b) return a.longest_b < b.longest_b;
+                if (a.longest_y != b.longest_y) return a.longest_y < b.longest_y;
+                if (!(a.hyperscore == b.hyperscore)) return a.hyperscore < b.hyperscore;
+                if (!(a.ppm_difference == b.ppm_difference)) return a.ppm_difference < b.ppm_difference;
+                if (a.precursor_charge != b.precursor_charge) return a.precursor_charge < b.precursor_charge;
+                return a.isotope_error < b.isotope_error;
+            };
+            bounded_min_heapify(sv.data(), sv.size(), k, lt);
+            for (size_t i = 0; i < k; i++) keep[sv[i].peptide] = 1;
+        } else {
+            for (const PreScore& p : hits.preliminary)
+                if (p.peptide != 0xFFFFFFFFu) keep[p.peptide] = 1;
+        }
+        return 0;
+    }
     // :300-309. Returns -1 (reference panics) for non-MS2 / missing precursor.
     int score(const Spectrum& q, std::vector<Feature>& out, Counters* ctr) const {
         if (q.level != 2) return -1;
@@ -1317,6 +1354,26 @@ int64_t so_score_batch(void* h, const so_scorer_params* sp, uint64_t n, const ui
                     total.candidates_scored, total.psms, total.peptide_record_floats};
     }
     return err;
+}
+
+// Scorer::quick_score over a batch; keep[n_peptides] bytes are OR-ed (AtomicBool store(true)).
+int64_t so_quick_score(void* h, const so_scorer_params* sp, uint64_t n, const uint64_t* peak_off, const float* masses, const float* intens,
+                       const float* prec_mz, const uint8_t* prec_charge, const float* iso_lo, const float* iso_hi, const float* tic, int low_memory,
+                       uint8_t* keep) {
+    DB* db = (DB*)h;
+    Scorer sc = make_scorer(db, sp);
+    for (uint64_t i = 0; i < n; i++) {
+        Spectrum q;
+        q.has_precursor = !std::isnan(prec_mz[i]);
+        q.precursor.mz = prec_mz[i];
+        if (prec_charge[i]) q.precursor.charge = prec_charge[i];
+        if (!std::isnan(iso_lo[i]) && !std::isnan(iso_hi[i])) q.precursor.isolation_window = Tolerance{DA, iso_lo[i], iso_hi[i]};
+        q.masses = masses + peak_off[i]; q.intensities = intens + peak_off[i]; q.n_peaks = (size_t)(peak_off[i + 1] - peak_off[i]);
+        q.total_ion_current = tic[i];
+        int rc = sc.quick_score(q, low_memory != 0, keep);
+        if (rc) return -((int64_t)i * 4 + (-rc));
+    }
+    return 0;
 }
 
 // Preliminary hits of one spectrum (after initial_hits), in heap order, for white-box parity of the trim kernels.

@@ -86,7 +86,7 @@ FRAGMENT_DTYPE = np.dtype([("kind", "<i4"), ("charge", "<i4"), ("ordinal", "<i4"
 EXPORTED_SYMBOLS = [
     "sage_b200_device_count", "sage_b200_db_create", "sage_b200_db_build", "sage_b200_db_get_info", "sage_b200_db_export_index", "sage_b200_db_destroy",
     "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_scorer_set_option", "sage_b200_score_batch", "sage_b200_batch_upload", "sage_b200_batch_run",
-    "sage_b200_batch_download", "sage_b200_initial_hits", "sage_b200_counters_get",
+    "sage_b200_batch_download", "sage_b200_quick_score", "sage_b200_initial_hits", "sage_b200_counters_get",
     "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
 ]
 
@@ -445,6 +445,16 @@ class Scorer:
             counts = np.zeros(n, np.uint32)
         _check(load_library().sage_b200_batch_download(self._h, _ptr(out), _ptr(counts)))
         return out, counts
+
+    def quick_score(self, batch: SpectraBatch, prefilter_low_memory: bool, keep: np.ndarray | None = None) -> np.ndarray:
+        """Scorer::quick_score (scoring.rs:255-298) over a batch: keep[PeptideIx] (uint8) is OR-ed and returned."""
+        if keep is None:
+            keep = np.zeros(self.db.info["n_peptides"], np.uint8)
+        keep_c = np.ascontiguousarray(keep, dtype=np.uint8)
+        kl: list = []
+        cs = batch._c(kl)
+        _check(load_library().sage_b200_quick_score(self._h, C.byref(cs), C.c_int(int(prefilter_low_memory)), _ptr(keep_c)))
+        return keep_c
 
     def score(self, spectrum: ProcessedSpectrum):
         """Scorer::score (scoring.rs:300): one spectrum -> list of Feature rows."""

@@ -1222,7 +1222,8 @@ __device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t
 // One CTA per spectrum.
 __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
                                                          uint64_t* dbg_keys /*nullable: initial_hits dump*/, uint32_t* dbg_meta, FragmentOut* frag_out /*nullable*/,
-                                                         unsigned long long frag_cap) {
+                                                         unsigned long long frag_cap, uint32_t quick_mode /*0 score, 1 keep all prelim, 2 low-memory*/,
+                                                         uint8_t* keep /*quick_score: one byte per peptide*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: masses[pmax] intens[pmax] cur[lcap] tot[lcap] recs[kparam] order[kparam] lut[256] mark[pmax]     (pmax is even)
     float* masses = reinterpret_cast<float*>(smem_raw);
@@ -1311,6 +1312,10 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
         if (tid == 0) { dbg_meta[s * 4 + 0] = s_ntot; dbg_meta[s * 4 + 1] = (uint32_t)s_matched_peaks; dbg_meta[s * 4 + 2] = (uint32_t)s_scored; }
     }
     const uint32_t ncand = s_ncand;
+    if (quick_mode == 1) {   // Scorer::quick_score, prefilter_low_memory == false (scoring.rs:291-296): every preliminary peptide is kept
+        for (uint32_t i = tid; i < ncand; i += SCORE_THREADS) keep[key_peptide(cur[i])] = 1;
+        return;
+    }
     const float mzp = __fsub_rn(b.prec_mz[s], PROTON);
     const double lambda = (double)s_matched_peaks / (double)s_scored;  // scoring.rs:499
     const uint32_t rounds = sc.chimera ? sc.report_psms : 1;
@@ -1333,6 +1338,23 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
         if (tid < ncand) finalize_rec(sc, recs[tid]);
         if (tid == 0) s_next = 0;
         __syncthreads();
+        if (quick_mode == 2) {
+            // Scorer::quick_score, low-memory branch (scoring.rs:270-290): bounded_min_heapify(score_vector, report_psms) compares Score
+            // with its DERIVED PartialOrd whose first field is the peptide index (heap.rs uses < and >), so the kept set is the
+            // report_psms entries with the largest PeptideIx among those reaching min_matched_peaks (entries of one peptide are
+            // interchangeable for the keep[] marks).
+            if (tid < ncand && recs[tid].valid) {
+                const uint32_t pme = recs[tid].peptide;
+                uint32_t pos = 0;
+                for (uint32_t j = 0; j < ncand; j++) {
+                    if (!recs[j].valid) continue;
+                    const uint32_t pj = recs[j].peptide;
+                    pos += (pj > pme) || (pj == pme && j < tid);
+                }
+                if (pos < sc.report_psms) keep[pme] = 1;
+            }
+            return;
+        }
         // stable sort by hyperscore descending (scoring.rs:495) via rank counting
         uint32_t my_floats = 0;
         if (tid < ncand) {

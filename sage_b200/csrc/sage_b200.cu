@@ -471,7 +471,8 @@ struct sage_b200_scorer {
     ScorerView sv{};
     std::mutex mu;
     Lane lanes[2];
-    DevBuf d_lnfact;
+    DevBuf d_lnfact, d_keep;
+    uint32_t quick_mode = 0;   // != 0 only inside sage_b200_quick_score
     int sort_spectra = 1;
     // annotate_matches: caller's fragment array for the current call and the running global offset
     sage_b200_fragment* frag_dst = nullptr;
@@ -564,6 +565,7 @@ extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
     cudaSetDevice(s->db->device);
     for (Lane& L : s->lanes) L.release();
     s->d_lnfact.release();
+    s->d_keep.release();
     delete s;
 }
 
@@ -780,7 +782,8 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));
     k_score<<<n, SCORE_THREADS, C.smem, st>>>(db->v, sv, bv, L.d_features.as<FeatureOut>(), L.d_counts.as<uint32_t>(), C.pmax,
                                              dbg ? L.d_dbgk.as<uint64_t>() : nullptr, dbg ? L.d_dbgm.as<uint32_t>() : nullptr,
-                                             annotate ? L.d_frags.as<FragmentOut>() : nullptr, (unsigned long long)S->frag_cap);
+                                             annotate ? L.d_frags.as<FragmentOut>() : nullptr, (unsigned long long)S->frag_cap, S->quick_mode,
+                                             S->d_keep.as<uint8_t>());
     CUDA_TRY(cudaGetLastError());
     launches++;
     CUDA_TRY(cudaEventRecord(L.ev[4], st));
@@ -916,6 +919,40 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
             return fail(SAGE_B200_ELIMIT, "fragment_capacity %llu too small: %llu fragments matched (features are complete; re-run with a larger array)",
                         (unsigned long long)fragment_capacity, (unsigned long long)S->frag_used);
     }
+    return 0;
+}
+
+// Scorer::quick_score over a batch (scoring.rs:255-298), the prefilter used by runner.rs:143-278: keep[PeptideIx] |= peptide identified.
+// prefilter_low_memory != 0: peptides of the report_psms "largest" scored candidates per spectrum (see k_score); == 0: every preliminary hit.
+extern "C" int sage_b200_quick_score(sage_b200_scorer* S, const sage_b200_spectra* sp, int prefilter_low_memory, uint8_t* keep) {
+    if (!S || !keep) return fail(SAGE_B200_EINVAL, "quick_score: null argument");
+    int rc = check_spectra(sp);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(S->mu);
+    CUDA_TRY(cudaSetDevice(S->db->device));
+    const size_t npep = S->db->v.n_pep;
+    if ((rc = S->d_keep.reserve(npep + 16))) return rc;
+    CUDA_TRY(cudaMemset(S->d_keep.p, 0, npep + 16));
+    S->last = sage_b200_counters{};
+    S->frag_dst = nullptr;
+    for (Lane& L : S->lanes) { L.chunk.loaded = false; L.ran = false; L.downloading = false; }
+    S->quick_mode = prefilter_low_memory ? 2u : 1u;
+    const uint64_t max_peaks = 1ull << 25;
+    uint64_t c0 = 0;
+    Lane& L = S->lanes[0];
+    while (c0 < sp->n && rc == 0) {
+        uint64_t c1 = std::min<uint64_t>(sp->n, c0 + 32768);
+        while (c1 > c0 + 1 && sp->peak_offsets[c1] - sp->peak_offsets[c0] > max_peaks) c1 = c0 + (c1 - c0) / 2;
+        if ((rc = chunk_upload(S, L, sp, c0, c1)) == 0 && (rc = chunk_run(S, L, false)) == 0) rc = lane_finish(S, L);
+        c0 = c1;
+    }
+    S->quick_mode = 0;
+    L.chunk.loaded = false;
+    if (rc) return rc;
+    std::vector<uint8_t> h(npep);
+    CUDA_TRY(cudaMemcpy(h.data(), S->d_keep.p, npep, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < npep; i++) keep[i] |= h[i];
+    finish_counters(S);
     return 0;
 }
 

@@ -205,6 +205,24 @@ def test_annotate_matches_fragments(small):
     assert e.value.code == -5 and "fragment_capacity" in e.value.message
 
 
+def test_quick_score_prefilter(small):
+    # Scorer::quick_score (scoring.rs:255-298): both branches, incl. isotope fold and unknown charges
+    pep, odb, gdb, spectra = small
+    sub = SpectraBatch(**{**spectra.slice(0, 600).__dict__, "prec_charge": np.where(np.arange(600) % 4 == 0, 0, spectra.prec_charge[:600]).astype(np.uint8)})
+    for kw in (dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=1),
+               dict(precursor_tol=Tolerance.da(-3, 3), fragment_tol=Tolerance.ppm(-10, 10), min_isotope_err=-1, max_isotope_err=2, report_psms=3,
+                    min_matched_peaks=3)):
+        sc = Scorer(gdb, **kw)
+        for low in (False, True):
+            g = sc.quick_score(sub, low)
+            o = odb.quick_score(oracle_cfg(**kw), sub.as_dict(), low)
+            assert g.sum() > 100 and np.array_equal(g, o), (kw, low, int(g.sum()), int(o.sum()))
+        # OR semantics
+        k0 = np.zeros(len(pep), np.uint8)
+        k0[:10] = 1
+        assert np.array_equal(sc.quick_score(sub, True, k0)[:10], np.ones(10, np.uint8))
+
+
 def test_initial_hits_heap_order(small):
     # white box: the preliminary list must come back in the reference's bounded_min_heapify order
     pep, odb, gdb, spectra = small
