@@ -181,6 +181,21 @@ int64_t sage_b200_initial_hits(sage_b200_scorer* scorer, const sage_b200_spectra
 
 int sage_b200_counters_get(const sage_b200_scorer* scorer, sage_b200_counters* out);
 
+/* SpectrumProcessor (spectrum.rs:39-44, 263-412) for centroided MS2 spectra — the step right before the hot path. */
+typedef struct { uint64_t take_top_n; uint8_t deisotope; float min_deisotope_mz; } sage_b200_processor_params;
+typedef struct {                    /* &[RawSpectrum] flattened (spectrum.rs:81-106) */
+    uint64_t n;
+    const uint64_t* peak_offsets;   /* n+1 */
+    const float* mz;                /* RawSpectrum::mz (ascending) */
+    const float* intensity;         /* RawSpectrum::intensity */
+    const uint8_t* precursor_charge;/* precursors.first().charge, 0 = None (deisotoping then assumes up to 3+, spectrum.rs:289-293) */
+    const uint8_t* level;           /* ms_level; NULL = all 2; other levels are rejected */
+} sage_b200_raw_spectra;
+/* process(): out_peak_offsets[n+1]; out_masses / out_intensities sized for the raw peak count (at most min(raw, take_top_n) are kept per spectrum);
+ * out_tic[n] = ProcessedSpectrum::total_ion_current. */
+int sage_b200_process_spectra(int device, const sage_b200_processor_params* processor, const sage_b200_raw_spectra* raw, uint64_t* out_peak_offsets,
+                              float* out_masses, float* out_intensities, float* out_tic);
+
 /* Page-locked host buffers: spectra/feature arrays placed here are copied by DMA without a staging memcpy. */
 void* sage_b200_host_alloc(size_t bytes);
 void sage_b200_host_free(void* p);

@@ -87,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "sage_b200_device_count", "sage_b200_db_create", "sage_b200_db_build", "sage_b200_db_get_info", "sage_b200_db_export_index", "sage_b200_db_destroy",
     "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_scorer_set_option", "sage_b200_score_batch", "sage_b200_batch_upload", "sage_b200_batch_run",
     "sage_b200_batch_download", "sage_b200_quick_score", "sage_b200_initial_hits", "sage_b200_counters_get",
-    "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
+    "sage_b200_process_spectra", "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
 ]
 
 _lib = None
@@ -478,6 +478,36 @@ class Scorer:
         cc = CCounters()
         _check(load_library().sage_b200_counters_get(self._h, C.byref(cc)))
         return {k: getattr(cc, k) for k, _ in CCounters._fields_}
+
+
+class CProcessorParams(C.Structure):
+    _fields_ = [("take_top_n", C.c_uint64), ("deisotope", C.c_uint8), ("min_deisotope_mz", C.c_float)]
+
+
+class CRawSpectra(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("peak_offsets", C.c_void_p), ("mz", C.c_void_p), ("intensity", C.c_void_p), ("precursor_charge", C.c_void_p),
+                ("level", C.c_void_p)]
+
+
+class SpectrumProcessor:
+    """SpectrumProcessor::new(take_top_n, deisotope, min_deisotope_mz) (spectrum.rs:271); process() runs on the device."""
+
+    def __init__(self, take_top_n: int, deisotope: bool, min_deisotope_mz: float, device: int = 0):
+        self.take_top_n, self.deisotope, self.min_deisotope_mz, self.device = int(take_top_n), bool(deisotope), float(min_deisotope_mz), device
+
+    def process_batch(self, peak_off, mz, intensity, precursor_charge):
+        """Raw centroided MS2 spectra (CSR) -> (peak_off[n+1], masses, intensities, tic[n]) of the ProcessedSpectrum batch."""
+        peak_off = np.ascontiguousarray(peak_off, np.uint64)
+        mz, intensity = np.ascontiguousarray(mz, np.float32), np.ascontiguousarray(intensity, np.float32)
+        chg = np.ascontiguousarray(precursor_charge, np.uint8)
+        n = len(chg)
+        pp = CProcessorParams(self.take_top_n, int(self.deisotope), self.min_deisotope_mz)
+        raw = CRawSpectra(n, _ptr(peak_off), _ptr(mz), _ptr(intensity), _ptr(chg), None)
+        out_off = np.zeros(n + 1, np.uint64)
+        om, oi, tic = np.zeros(max(1, len(mz)), np.float32), np.zeros(max(1, len(mz)), np.float32), np.zeros(n, np.float32)
+        _check(load_library().sage_b200_process_spectra(C.c_int(self.device), C.byref(pp), C.byref(raw), _ptr(out_off), _ptr(om), _ptr(oi), _ptr(tic)))
+        k = int(out_off[-1])
+        return out_off, om[:k].copy(), oi[:k].copy(), tic
 
 
 Feature = FEATURE_DTYPE

@@ -1,9 +1,12 @@
 // kernels.cuh — hand-written sm_100a kernels for the fragment-index search-and-score path.
 //
 //   k_setup_queries   IndexedDatabase::query per (spectrum, charge, isotope)      database.rs:402-425, scoring.rs:418-458
-//   k_prelim_narrow   matched_peaks_with_isotope + trim_hits, counts in smem       scoring.rs:335-382, database.rs:480-536, heap.rs
-//   k_prelim_wide     same, precursor windows > NARROW_CAP: cooperative streaming of page slices, counts in HBM/L2 scratch
-//   k_score           fold/trim of per-query hits, score_candidate, build_features, chimera loop   scoring.rs:384-767
+//   k_prelim_narrow   matched_peaks_with_isotope (counting), counts in smem, emits the ordered key list    scoring.rs:335-375, database.rs:480-536
+//   k_prelim_wide     same for precursor windows > NARROW_CAP (open search): tiled smem counts, streamed page slices
+//   k_replay          trim_hits == bounded_min_heapify + truncate, one thread per query                       scoring.rs:322-329, heap.rs:7-60
+//   k_score           fold/trim of per-query hits, score_candidate, build_features, chimera loop, Fragments, quick_score   scoring.rs:255-767
+//   k_process_ms2     SpectrumProcessor::process for MS2 (deisotope, top-N, sort, TIC)                          spectrum.rs:179-412
+//   k_build_* / k_gen_fragments / k_bucket_keys ...  Parameters::build_from_peptides + search directories     database.rs:265-365
 //
 // All of this is integer/f32 gather-reduce work bound by memory latency/bandwidth; tensor cores are not used.
 #pragma once
@@ -80,77 +83,7 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
     atomicMax(b.counters + C_MAXPOT, maxpot);
 }
 
-// --------------------------------------------------------------------------------------------- trim (exact)
-// trim_hits (scoring.rs:322-329) == bounded_min_heapify(dense, k) + truncate(k) applied to the dense per-window
-// Vec<PreScore> (one slot per PeptideIx of the window, untouched slots == PreScore::default()).
-// The heap ORDER is observable downstream (stable sort by hyperscore), so it is reproduced exactly:
-//   * the first k dense slots seed the heap literally (zeros included) and are heapified sequentially;
-//   * only slots with matched > 0 can ever exceed the heap minimum, and the minimum is monotone, so the block
-//     scans the remaining slots in index order, filters against the minimum as of the chunk start (a superset
-//     of the true insertions), compacts survivors in index order and lets one thread replay them.
-// cnt(i) -> matched count of dense slot i. Returns the number of entries written to heap[] (min(n,k)); *nonzero =
-// number of slots with matched > 0 (== scored_candidates).
-template <class CountFn>
-__device__ uint32_t trim_dense(CountFn cnt, uint32_t n, uint32_t k, uint32_t pre_lo, uint32_t charge, int iso, uint64_t* heap /*K_MAX*/,
-                               uint64_t* queue /*blockDim.x*/, uint32_t* s_warp /*>= 33 words*/, uint32_t* nonzero) {
-    const uint32_t tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-    uint32_t nz = 0;
-    const uint32_t head = n < k ? n : k;
-    for (uint32_t i = tid; i < head; i += nthreads) {
-        const uint32_t c = cnt(i);
-        nz += c != 0;
-        heap[i] = c ? prescore_key(c, pre_lo + i, charge, iso) : PRESCORE_DEFAULT;
-    }
-    __syncthreads();
-    if (n > k) {
-        if (tid == 0)
-            for (uint32_t i = k / 2; i-- > 0;) sift_down(heap, k, i);
-        __syncthreads();
-        for (uint32_t base = k; base < n; base += nthreads) {
-            const uint32_t i = base + tid;
-            const uint32_t c = i < n ? cnt(i) : 0;
-            nz += c != 0;
-            const uint64_t key = prescore_key(c, pre_lo + i, charge, iso);
-            const bool cand = c != 0 && key > heap[0];
-            if (__syncthreads_or(cand)) {
-                const uint32_t ball = __ballot_sync(0xffffffffu, cand);
-                if (lane == 0) s_warp[warp] = __popc(ball);
-                __syncthreads();
-                uint32_t off = 0, total = 0;
-                for (uint32_t w = 0; w < nwarps; w++) {
-                    const uint32_t x = s_warp[w];
-                    if (w < warp) off += x;
-                    total += x;
-                }
-                if (cand) queue[off + __popc(ball & ((1u << lane) - 1))] = key;
-                __syncthreads();
-                if (tid == 0) {
-                    for (uint32_t j = 0; j < total; j++) {
-                        const uint64_t kq = queue[j];
-                        if (kq > heap[0]) {  // slice[i] > slice[0]: swap, sift_down (the swapped-out root lands at i >= k and is truncated)
-                            heap[0] = kq;
-                            sift_down(heap, k, 0);
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-        }
-    }
-    // block-reduce nz
-    for (int o = 16; o > 0; o >>= 1) nz += __shfl_down_sync(0xffffffffu, nz, o);
-    __syncthreads();
-    if (lane == 0) s_warp[warp] = nz;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t t = 0;
-        for (uint32_t w = 0; w < nwarps; w++) t += s_warp[w];
-        *nonzero = t;
-    }
-    __syncthreads();
-    return head;
-}
-
+// --------------------------------------------------------------------------------------------- block helpers
 __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* s_warp) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -1476,6 +1409,151 @@ __global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView s
     if (tid == 0) {
         counts[s] = nout;
         if (nout) atomicAdd(b.counters + C_PSMS, (unsigned long long)nout);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- spectrum preprocessing
+// SpectrumProcessor::process for centroided MS2 spectra (spectrum.rs:279-412): deisotope (spectrum.rs:179-227), sort by intensity,
+// drop isotope-envelope members, MH+ -> M with the assigned charge, keep the top N, sort by mass, total ion current.
+// One warp per spectrum: the deisotoping pass is a sequential recurrence (lane 0), the two sorts are warp bitonic sorts in smem.
+struct ProcParams { uint32_t take_top_n; uint32_t deisotope; float min_deisotope_mz; };
+
+__device__ __forceinline__ void warp_bitonic(uint64_t* keys, uint32_t* vals, uint32_t n2) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < n2; i += 32) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const bool asc = (i & k) == 0;
+                    const uint64_t a = keys[i], c = keys[l];
+                    if ((a > c) == asc) { keys[i] = c; keys[l] = a; const uint32_t t = vals[i]; vals[i] = vals[l]; vals[l] = t; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+__device__ __forceinline__ uint32_t f32_ukey(float x) { return (uint32_t)f32_key(x) ^ 0x80000000u; }   // unsigned order == total_cmp order
+
+__global__ void __launch_bounds__(32) k_process_ms2(ProcParams pp, uint32_t n, const uint32_t* peak_off, const float* mz_in, const float* int_in,
+                                                      const uint8_t* prec_charge, uint32_t pmax, uint32_t p2max, float* out_mass, float* out_int,
+                                                      uint32_t* out_count, float* out_tic) {
+    extern __shared__ __align__(16) unsigned char praw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(praw);          // [p2max]
+    uint32_t* vals = reinterpret_cast<uint32_t*>(keys + p2max);   // [p2max]
+    float* mz = reinterpret_cast<float*>(vals + p2max);           // [pmax]
+    float* it0 = mz + pmax;                                       // original intensities
+    float* acc = it0 + pmax;                                      // Deisotoped::intensity
+    float* omass = acc + pmax;                                    // kept peaks (mass, intensity), <= take_top_n of them
+    float* oint = omass + pmax;
+    uint8_t* chg = reinterpret_cast<uint8_t*>(oint + pmax);       // Deisotoped::charge (0 = None)
+    uint8_t* env = chg + pmax;                                    // Deisotoped::envelope.is_some()
+    const uint32_t s = blockIdx.x, lane = threadIdx.x;
+    if (s >= n) return;
+    const uint32_t p0 = peak_off[s], np = peak_off[s + 1] - p0;
+    for (uint32_t i = lane; i < np; i += 32) { mz[i] = mz_in[p0 + i]; it0[i] = int_in[p0 + i]; acc[i] = it0[i]; chg[i] = 0; env[i] = 0; }
+    __syncwarp();
+    uint32_t nkeep = 0;
+    if (pp.deisotope) {
+        if (lane == 0 && np > 0) {   // deisotope(mz, int, charge, 10.0, min_deisotope_mz), spectrum.rs:179-227
+            const uint32_t max_charge = prec_charge[s] ? prec_charge[s] : 3;   // spectrum.rs:289-293
+            const float ppm = 10.0f;
+            for (uint32_t i = np; i-- > 0;) {
+                uint32_t j = i == 0 ? 0 : i - 1;
+                const float tol = __fdiv_rn(__fmul_rn(ppm, mz[i]), 1000000.0f);   // ppm_to_delta_mass(mz[i], ppm)
+                while (__fsub_rn(mz[i], mz[j]) <= __fadd_rn(NEUTRON, tol) && mz[j] >= pp.min_deisotope_mz) {
+                    const float delta = __fsub_rn(mz[i], mz[j]);
+                    for (uint32_t c = 1; c <= max_charge; c++) {
+                        const float iso = __fdiv_rn(NEUTRON, (float)c);
+                        if (fabsf(__fsub_rn(delta, iso)) <= tol && it0[i] < it0[j]) {
+                            if (chg[i] != 0 && chg[i] != c) continue;   // already part of an envelope with another charge
+                            acc[j] = __fadd_rn(acc[j], acc[i]);
+                            chg[j] = (uint8_t)c;
+                            chg[i] = (uint8_t)c;
+                            env[i] = 1;
+                        }
+                    }
+                    j = j == 0 ? 0 : j - 1;
+                    if (j == 0) break;
+                }
+            }
+        }
+        __syncwarp();
+        // sort by (intensity descending, mz ascending)  spectrum.rs:303-307
+        uint32_t n2 = 1;
+        while (n2 < np) n2 <<= 1;
+        for (uint32_t i = lane; i < n2; i += 32) {
+            if (i < np) { keys[i] = ((uint64_t)(~f32_ukey(acc[i])) << 32) | f32_ukey(mz[i]); vals[i] = i; }
+            else { keys[i] = ~0ull; vals[i] = 0xFFFFFFFFu; }
+        }
+        __syncwarp();
+        warp_bitonic(keys, vals, n2);
+        // keep non-envelope peaks, MH+ -> M, first take_top_n  (spectrum.rs:309-321)
+        for (uint32_t base = 0; base < np && nkeep < pp.take_top_n; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t src = i < np ? vals[i] : 0xFFFFFFFFu;
+            const bool keep = src != 0xFFFFFFFFu && env[src] == 0;
+            const uint32_t ball = __ballot_sync(0xffffffffu, keep);
+            const uint32_t pos = nkeep + __popc(ball & ((1u << lane) - 1));
+            if (keep && pos < pp.take_top_n) {
+                omass[pos] = __fmul_rn(__fsub_rn(mz[src], PROTON), (float)(chg[src] ? chg[src] : 1));
+                oint[pos] = acc[src];
+            }
+            nkeep = min(nkeep + (uint32_t)__popc(ball), pp.take_top_n);
+        }
+        __syncwarp();
+    } else {
+        // (mz - PROTON) * 1.0, bounded_min_heapify(peaks, take_top_n) with Peak's Ord (intensity, then mass), truncate  spectrum.rs:323-334
+        for (uint32_t i = lane; i < np; i += 32) { omass[i] = __fmul_rn(__fsub_rn(mz[i], PROTON), 1.0f); oint[i] = it0[i]; }
+        __syncwarp();
+        const uint32_t k = pp.take_top_n;
+        if (np > k) {
+            if (lane == 0) {
+                auto pkey = [&](uint32_t i) -> uint64_t { return ((uint64_t)f32_ukey(oint[i]) << 32) | f32_ukey(omass[i]); };
+                for (uint32_t i = 0; i < np; i++) { keys[i] = pkey(i); vals[i] = i; }   // heap over (key, original index)
+                auto sift = [&](uint32_t index) {
+                    while (index * 2 + 1 < k) {
+                        uint32_t sm = index, l = index * 2 + 1, r = index * 2 + 2;
+                        if (keys[l] < keys[sm]) sm = l;
+                        if (r < k && keys[r] < keys[sm]) sm = r;
+                        if (sm == index) break;
+                        const uint64_t tk = keys[sm]; keys[sm] = keys[index]; keys[index] = tk;
+                        const uint32_t tv = vals[sm]; vals[sm] = vals[index]; vals[index] = tv;
+                        index = sm;
+                    }
+                };
+                for (uint32_t i = k / 2; i-- > 0;) sift(i);
+                for (uint32_t i = k; i < np; i++) {
+                    if (keys[i] > keys[0]) {
+                        const uint64_t tk = keys[i]; keys[i] = keys[0]; keys[0] = tk;
+                        const uint32_t tv = vals[i]; vals[i] = vals[0]; vals[0] = tv;
+                        sift(0);
+                    }
+                }
+                for (uint32_t i = 0; i < k; i++) { mz[i] = omass[vals[i]]; acc[i] = oint[vals[i]]; }   // heap order
+                for (uint32_t i = 0; i < k; i++) { omass[i] = mz[i]; oint[i] = acc[i]; }
+            }
+            __syncwarp();
+            nkeep = k;
+        } else nkeep = np;
+    }
+    // stable sort by mass (spectrum.rs:393), then SoA + TIC (spectrum.rs:394-398)
+    uint32_t m2 = 1;
+    while (m2 < nkeep) m2 <<= 1;
+    for (uint32_t i = lane; i < m2; i += 32) {
+        if (i < nkeep) { keys[i] = ((uint64_t)f32_ukey(omass[i]) << 32) | i; vals[i] = i; }
+        else { keys[i] = ~0ull; vals[i] = 0xFFFFFFFFu; }
+    }
+    __syncwarp();
+    warp_bitonic(keys, vals, m2);
+    for (uint32_t i = lane; i < nkeep; i += 32) { out_mass[p0 + i] = omass[vals[i]]; out_int[p0 + i] = oint[vals[i]]; }
+    __syncwarp();
+    if (lane == 0) {
+        float t = 0.0f;
+        for (uint32_t i = 0; i < nkeep; i++) t = __fadd_rn(t, oint[vals[i]]);
+        out_tic[s] = t;
+        out_count[s] = nkeep;
     }
 }
 

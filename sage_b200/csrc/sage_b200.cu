@@ -886,7 +886,10 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
     S->frag_dst = annotate ? fragments : nullptr;
     S->frag_cap = annotate ? fragment_capacity : 0;
     S->frag_used = 0;
-    for (Lane& L : S->lanes) { L.chunk.loaded = false; L.ran = false; L.downloading = false; }
+    for (Lane& L : S->lanes) {   // a previous call may have failed half-way: make sure nothing is still queued on the lanes
+        CUDA_TRY(cudaStreamSynchronize(L.stream));
+        L.chunk.loaded = false; L.ran = false; L.downloading = false;
+    }
     // Chunks are bounded by spectra and peak counts (device staging) and sized so that a large batch becomes ~pipeline_chunks chunks:
     // two lanes alternate, so the H2D of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i.
     const uint64_t max_peaks = 1ull << 25;
@@ -1028,6 +1031,62 @@ extern "C" int64_t sage_b200_initial_hits(sage_b200_scorer* S, const sage_b200_s
     if (matched_peaks) *matched_peaks = meta[1];
     if (scored_candidates) *scored_candidates = meta[2];
     return (int64_t)nk;
+}
+
+// SpectrumProcessor::new(take_top_n, deisotope, min_deisotope_mz).process(..) for a batch of centroided MS2 RawSpectrum (spectrum.rs:271-412).
+extern "C" int sage_b200_process_spectra(int device, const sage_b200_processor_params* pr, const sage_b200_raw_spectra* raw, uint64_t* out_peak_offsets,
+                                         float* out_masses, float* out_intensities, float* out_tic) {
+    if (!pr || !raw || !out_peak_offsets || !out_tic) return fail(SAGE_B200_EINVAL, "process_spectra: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SAGE_B200_ECUDA, "no CUDA device available: sage_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(SAGE_B200_EINVAL, "device out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    const uint64_t n = raw->n;
+    out_peak_offsets[0] = 0;
+    if (n == 0) return 0;
+    if (!raw->peak_offsets || !raw->precursor_charge) return fail(SAGE_B200_EINVAL, "process_spectra: null array");
+    const uint64_t pk0 = raw->peak_offsets[0], npk = raw->peak_offsets[n] - pk0;
+    if (npk && (!raw->mz || !raw->intensity || !out_masses || !out_intensities)) return fail(SAGE_B200_EINVAL, "process_spectra: null peak arrays");
+    if (n > 0x7FFFFFFFull || npk > 0xFFFFFFF0ull) return fail(SAGE_B200_ELIMIT, "process_spectra: batch too large");
+    std::vector<uint32_t> off(n + 1);
+    uint32_t pmax = 1;
+    for (uint64_t i = 0; i <= n; i++) off[i] = (uint32_t)(raw->peak_offsets[i] - pk0);
+    for (uint64_t i = 0; i < n; i++) {
+        if (raw->level && raw->level[i] != 2) return fail(SAGE_B200_ENOTMS2, "process_spectra handles MS2 spectra only (spectrum %llu has level %u)", (unsigned long long)i, raw->level[i]);
+        pmax = std::max(pmax, off[i + 1] - off[i]);
+    }
+    uint32_t p2 = 1;
+    while (p2 < pmax) p2 <<= 1;
+    const size_t smem = (size_t)p2 * 12 + (size_t)pmax * (5 * 4 + 2) + 32;
+    if (smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u raw peaks exceeds the shared-memory budget of the preprocessing kernel", pmax);
+    void *d_off = nullptr, *d_mz = nullptr, *d_int = nullptr, *d_chg = nullptr, *d_om = nullptr, *d_oi = nullptr, *d_cnt = nullptr, *d_tic = nullptr;
+    auto cleanup = [&]() { for (void* p : {d_off, d_mz, d_int, d_chg, d_om, d_oi, d_cnt, d_tic}) if (p) cudaFree(p); };
+#define TRY_P(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(SAGE_B200_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    TRY_P(cudaMalloc(&d_off, 4 * (n + 1))); TRY_P(cudaMalloc(&d_mz, 4 * npk + 16)); TRY_P(cudaMalloc(&d_int, 4 * npk + 16)); TRY_P(cudaMalloc(&d_chg, n));
+    TRY_P(cudaMalloc(&d_om, 4 * npk + 16)); TRY_P(cudaMalloc(&d_oi, 4 * npk + 16)); TRY_P(cudaMalloc(&d_cnt, 4 * n)); TRY_P(cudaMalloc(&d_tic, 4 * n));
+    TRY_P(cudaMemcpy(d_off, off.data(), 4 * (n + 1), cudaMemcpyHostToDevice));
+    if (npk) { TRY_P(cudaMemcpy(d_mz, raw->mz + pk0, 4 * npk, cudaMemcpyHostToDevice)); TRY_P(cudaMemcpy(d_int, raw->intensity + pk0, 4 * npk, cudaMemcpyHostToDevice)); }
+    TRY_P(cudaMemcpy(d_chg, raw->precursor_charge, n, cudaMemcpyHostToDevice));
+    ProcParams pp{(uint32_t)std::min<uint64_t>(pr->take_top_n, 0xFFFFFFFFull), pr->deisotope ? 1u : 0u, pr->min_deisotope_mz};
+    TRY_P(cudaFuncSetAttribute(k_process_ms2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_process_ms2<<<(unsigned)n, 32, smem>>>(pp, (uint32_t)n, (const uint32_t*)d_off, (const float*)d_mz, (const float*)d_int, (const uint8_t*)d_chg, pmax, p2,
+                                            (float*)d_om, (float*)d_oi, (uint32_t*)d_cnt, (float*)d_tic);
+    TRY_P(cudaGetLastError());
+    std::vector<uint32_t> cnt(n);
+    std::vector<float> om(npk), oi(npk);
+    TRY_P(cudaMemcpy(cnt.data(), d_cnt, 4 * n, cudaMemcpyDeviceToHost));
+    TRY_P(cudaMemcpy(out_tic, d_tic, 4 * n, cudaMemcpyDeviceToHost));
+    if (npk) { TRY_P(cudaMemcpy(om.data(), d_om, 4 * npk, cudaMemcpyDeviceToHost)); TRY_P(cudaMemcpy(oi.data(), d_oi, 4 * npk, cudaMemcpyDeviceToHost)); }
+#undef TRY_P
+    cleanup();
+    uint64_t w = 0;   // compact: spectrum i keeps cnt[i] <= raw count peaks
+    for (uint64_t i = 0; i < n; i++) {
+        memcpy(out_masses + w, om.data() + off[i], 4 * (size_t)cnt[i]);
+        memcpy(out_intensities + w, oi.data() + off[i], 4 * (size_t)cnt[i]);
+        w += cnt[i];
+        out_peak_offsets[i + 1] = w;
+    }
+    return 0;
 }
 
 extern "C" int sage_b200_counters_get(const sage_b200_scorer* S, sage_b200_counters* out) {
