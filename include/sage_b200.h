@@ -163,6 +163,11 @@ int sage_b200_scorer_set_option(sage_b200_scorer* scorer, const char* name, int6
 int sage_b200_score_batch(sage_b200_scorer* scorer, const sage_b200_spectra* spectra, sage_b200_feature* features, uint32_t* counts,
                           sage_b200_fragment* fragments, uint64_t fragment_capacity, uint64_t* fragments_used);
 
+/* Same result as sage_b200_score_batch, computed by several GPUs of one box from one host process: contiguous blocks of spectra go to
+ * scorers[0..n) (one per device, each on its own index replica, one host thread each); no collective. annotate_matches is not supported here. */
+int sage_b200_score_batch_multi(sage_b200_scorer* const* scorers, int n_scorers, const sage_b200_spectra* spectra, sage_b200_feature* features,
+                                uint32_t* counts);
+
 /* Scorer::quick_score over a batch (scoring.rs:255-298; prefilter of runner.rs:143-278). keep has one byte per peptide of the db and is
  * OR-ed (the reference stores `true` into &[AtomicBool]). prefilter_low_memory selects the branch of scoring.rs:270. */
 int sage_b200_quick_score(sage_b200_scorer* scorer, const sage_b200_spectra* spectra, int prefilter_low_memory, uint8_t* keep);

@@ -86,7 +86,7 @@ FRAGMENT_DTYPE = np.dtype([("kind", "<i4"), ("charge", "<i4"), ("ordinal", "<i4"
 EXPORTED_SYMBOLS = [
     "sage_b200_device_count", "sage_b200_db_create", "sage_b200_db_build", "sage_b200_db_get_info", "sage_b200_db_export_index", "sage_b200_db_destroy",
     "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_scorer_set_option", "sage_b200_score_batch", "sage_b200_batch_upload", "sage_b200_batch_run",
-    "sage_b200_batch_download", "sage_b200_quick_score", "sage_b200_initial_hits", "sage_b200_counters_get",
+    "sage_b200_batch_download", "sage_b200_score_batch_multi", "sage_b200_quick_score", "sage_b200_initial_hits", "sage_b200_counters_get",
     "sage_b200_process_spectra", "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
 ]
 
@@ -478,6 +478,17 @@ class Scorer:
         cc = CCounters()
         _check(load_library().sage_b200_counters_get(self._h, C.byref(cc)))
         return {k: getattr(cc, k) for k, _ in CCounters._fields_}
+
+
+def score_batch_multi(scorers, batch: SpectraBatch):
+    """sage_b200_score_batch_multi: one process, one Scorer per GPU (same settings), spectra split into contiguous blocks."""
+    n, r = len(batch), scorers[0].report_psms
+    out, counts = np.zeros(n * r, FEATURE_DTYPE), np.zeros(n, np.uint32)
+    keep: list = []
+    cs = batch._c(keep)
+    arr = (C.c_void_p * len(scorers))(*[s._h for s in scorers])
+    _check(load_library().sage_b200_score_batch_multi(arr, C.c_int(len(scorers)), C.byref(cs), _ptr(out), _ptr(counts)))
+    return out, counts
 
 
 class CProcessorParams(C.Structure):

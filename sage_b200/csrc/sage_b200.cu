@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -922,6 +923,52 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
             return fail(SAGE_B200_ELIMIT, "fragment_capacity %llu too small: %llu fragments matched (features are complete; re-run with a larger array)",
                         (unsigned long long)fragment_capacity, (unsigned long long)S->frag_used);
     }
+    return 0;
+}
+
+// One process, several GPUs: spectra are independent, so the batch is cut into contiguous blocks, block g goes to
+// scorers[g] (each bound to its own device and index replica) on its own host thread; Feature.spectrum stays batch-relative.
+// No collective and no peer traffic: results land directly in the caller's arrays.
+extern "C" int sage_b200_score_batch_multi(sage_b200_scorer* const* scorers, int n_scorers, const sage_b200_spectra* sp, sage_b200_feature* features,
+                                           uint32_t* counts) {
+    if (!scorers || n_scorers <= 0) return fail(SAGE_B200_EINVAL, "score_batch_multi: no scorers");
+    int rc = check_spectra(sp);
+    if (rc) return rc;
+    if (sp->n && (!features || !counts)) return fail(SAGE_B200_EINVAL, "score_batch_multi: null output");
+    for (int g = 0; g < n_scorers; g++) {
+        if (!scorers[g]) return fail(SAGE_B200_EINVAL, "score_batch_multi: null scorer %d", g);
+        if (scorers[g]->sv.report_psms != scorers[0]->sv.report_psms || scorers[g]->sv.annotate)
+            return fail(SAGE_B200_EINVAL, "score_batch_multi: scorers must share report_psms and not annotate matches");
+    }
+    const uint32_t r = scorers[0]->sv.report_psms;
+    std::vector<int> rcs(n_scorers, 0);
+    std::vector<std::string> msgs(n_scorers);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_scorers; g++) {
+        const uint64_t a = sp->n * (uint64_t)g / (uint64_t)n_scorers, b = sp->n * (uint64_t)(g + 1) / (uint64_t)n_scorers;
+        th.emplace_back([&, g, a, b]() {
+            if (a == b) return;
+            sage_b200_spectra sub = *sp;   // a view: same arrays, shifted per-spectrum pointers (peak_offsets stay absolute)
+            sub.n = b - a;
+            sub.peak_offsets = sp->peak_offsets + a;
+            sub.precursor_mz = sp->precursor_mz + a;
+            sub.precursor_charge = sp->precursor_charge + a;
+            sub.isolation_lo = sp->isolation_lo ? sp->isolation_lo + a : nullptr;
+            sub.isolation_hi = sp->isolation_hi ? sp->isolation_hi + a : nullptr;
+            sub.total_ion_current = sp->total_ion_current + a;
+            sub.level = sp->level ? sp->level + a : nullptr;
+            sub.scan_start_time = sp->scan_start_time ? sp->scan_start_time + a : nullptr;
+            sub.inverse_ion_mobility = sp->inverse_ion_mobility ? sp->inverse_ion_mobility + a : nullptr;
+            rcs[g] = sage_b200_score_batch(scorers[g], &sub, features + a * r, counts + a, nullptr, 0, nullptr);
+            if (rcs[g]) msgs[g] = g_last_error;
+            else
+                for (uint64_t i = a; i < b; i++)
+                    for (uint32_t k = 0; k < counts[i]; k++) features[i * r + k].spectrum += (uint32_t)a;
+        });
+    }
+    for (auto& x : th) x.join();
+    for (int g = 0; g < n_scorers; g++)
+        if (rcs[g]) return fail(rcs[g], "scorer %d (device %d): %s", g, scorers[g]->db->device, msgs[g].c_str());
     return 0;
 }
 

@@ -205,6 +205,19 @@ def test_annotate_matches_fragments(small):
     assert e.value.code == -5 and "fragment_capacity" in e.value.message
 
 
+def test_score_batch_multi_single_process(small):
+    # one process driving every visible GPU (falls back to two scorers on one device when only one GPU is visible)
+    from sage_b200.api import score_batch_multi
+    pep, odb, gdb, spectra = small
+    kw = dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=2)
+    ndev = max(1, sage_b200.device_count())
+    dbs = [gdb] + [IndexedDatabase.build_from_peptides(pep, device=d) for d in range(1, ndev)]
+    scorers = [Scorer(dbs[d % ndev], **kw) for d in range(max(2, ndev))] + [Scorer(gdb, **kw)]   # odd count: uneven blocks
+    gf, gc = score_batch_multi(scorers, spectra)
+    of, oc, _, _ = odb.score_batch(oracle_cfg(**kw), spectra.as_dict())
+    assert_features_equal(gf, gc, of, oc, 2, what=f"score_batch_multi over {len(scorers)} scorers / {ndev} device(s)")
+
+
 def test_quick_score_prefilter(small):
     # Scorer::quick_score (scoring.rs:255-298): both branches, incl. isotope fold and unknown charges
     pep, odb, gdb, spectra = small
