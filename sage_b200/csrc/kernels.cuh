@@ -1153,7 +1153,7 @@ __device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t
 }
 
 // One CTA per spectrum.
-__global__ void __launch_bounds__(SCORE_THREADS) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
+__global__ void __launch_bounds__(SCORE_THREADS, 14) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
                                                          uint64_t* dbg_keys /*nullable: initial_hits dump*/, uint32_t* dbg_meta, FragmentOut* frag_out /*nullable*/,
                                                          unsigned long long frag_cap, uint32_t quick_mode /*0 score, 1 keep all prelim, 2 low-memory*/,
                                                          uint8_t* keep /*quick_score: one byte per peptide*/) {
