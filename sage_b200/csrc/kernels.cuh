@@ -1158,10 +1158,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, 14) k_score(DbView db, ScorerVi
                                                          unsigned long long frag_cap, uint32_t quick_mode /*0 score, 1 keep all prelim, 2 low-memory*/,
                                                          uint8_t* keep /*quick_score: one byte per peptide*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: masses[pmax] intens[pmax] cur[lcap] tot[lcap] recs[kparam] order[kparam] lut[256] mark[pmax]     (pmax is even)
-    float* masses = reinterpret_cast<float*>(smem_raw);
-    float* intens = masses + pmax;
-    uint64_t* cur = reinterpret_cast<uint64_t*>(intens + pmax);
+    // layout: masses_raw[pmax+4] intens_raw[pmax+4] cur[lcap] tot[lcap] recs[kparam] order[kparam] lut[1024] mark[pmax]   (pmax % 4 == 0)
+    float* masses_raw = reinterpret_cast<float*>(smem_raw);
+    float* intens_raw = masses_raw + pmax + 4;
+    uint64_t* cur = reinterpret_cast<uint64_t*>(intens_raw + pmax + 4);
     uint64_t* tot = cur + sc.lcap;
     ScoreRec* recs = reinterpret_cast<ScoreRec*>(tot + sc.lcap);
     uint32_t* order = reinterpret_cast<uint32_t*>(recs + sc.kparam);
@@ -1174,8 +1174,22 @@ __global__ void __launch_bounds__(SCORE_THREADS, 14) k_score(DbView db, ScorerVi
     const uint32_t s = b.order ? b.order[blockIdx.x] : blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SCORE_THREADS / 32;
     const uint32_t p0 = b.peak_off[s];
     uint32_t np = b.peak_off[s + 1] - p0;
-    for (uint32_t i = tid; i < np; i += SCORE_THREADS) { masses[i] = b.masses[p0 + i]; intens[i] = b.intens[p0 + i]; }
-    if (tid == 0) s_next = 0;
+    // Stage the spectrum's peaks with the bulk-async copy engine (TMA 1-D): two cp.async.bulk copies complete on an mbarrier while the
+    // prologue below folds the preliminary hits. Copies start at the 16-byte boundary below the first peak (`head` floats of slack).
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t a0 = p0 & ~3u, head = p0 - a0;
+    const uint32_t bytes = ((head + np) * 4 + 15) & ~15u;
+    float* masses = masses_raw + head;
+    float* intens = intens_raw + head;
+    if (tid == 0) {   // one thread initialises the barrier and issues both copies; everyone else first touches s_bar after the prologue's barrier
+        s_next = 0;
+        mbar_init(&s_bar, 1);
+        if (np) {
+            mbar_arrive_expect_tx(&s_bar, 2 * bytes);
+            bulk_copy_g2s(masses_raw, b.masses + a0, bytes, &s_bar);
+            bulk_copy_g2s(intens_raw, b.intens + a0, bytes, &s_bar);
+        }
+    }
 
     const QueryDesc* qd = b.queries + (size_t)s * sc.qmax;
     const QueryHits* qh = b.hits + (size_t)s * sc.qmax;
@@ -1244,6 +1258,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 14) k_score(DbView db, ScorerVi
         for (uint32_t i = tid; i < s_ntot; i += SCORE_THREADS) dbg_keys[(size_t)s * sc.kparam + i] = tot[i];
         if (tid == 0) { dbg_meta[s * 4 + 0] = s_ntot; dbg_meta[s * 4 + 1] = (uint32_t)s_matched_peaks; dbg_meta[s * 4 + 2] = (uint32_t)s_scored; }
     }
+    if (np) mbar_wait(&s_bar, 0);   // peaks have landed in shared memory
     const uint32_t ncand = s_ncand;
     if (quick_mode == 1) {   // Scorer::quick_score, prefilter_low_memory == false (scoring.rs:291-296): every preliminary peptide is kept
         for (uint32_t i = tid; i < ncand; i += SCORE_THREADS) keep[key_peptide(cur[i])] = 1;

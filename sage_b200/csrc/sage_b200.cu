@@ -611,7 +611,7 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
             return fail(SAGE_B200_ENOTMS2, "internal bug, trying to score a non-MS2 scan! (spectrum %llu has level %u)", (unsigned long long)(c0 + i), sp->level[c0 + i]);
         if (std::isnan(sp->precursor_mz[c0 + i])) return fail(SAGE_B200_ENOPRECURSOR, "missing MS1 precursor for spectrum %llu", (unsigned long long)(c0 + i));
     }
-    C.pmax = (pmax + 1) & ~1u;
+    C.pmax = (pmax + 3) & ~3u;   // multiple of 4 floats: the staged copies in k_score are 16-byte granular
     C.zmax = zmax;
     memcpy(hs + C.o_pmz, sp->precursor_mz + c0, 4 * (size_t)n);
     memcpy(hs + C.o_tic, sp->total_ion_current + c0, 4 * (size_t)n);
@@ -626,7 +626,7 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
         h_ims[i] = sp->inverse_ion_mobility ? sp->inverse_ion_mobility[c0 + i] : NAN;
     }
     memcpy(hs + C.o_chg, sp->precursor_charge + c0, n);
-    C.smem = (size_t)C.pmax * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + 2 * SPEC_LUT_CELLS + C.pmax + 16;
+    C.smem = (size_t)(C.pmax + 4) * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + 2 * SPEC_LUT_CELLS + C.pmax + 16;
     if (C.smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", C.pmax);
     C.nitems = (size_t)n * sv.qmax;
     if (C.nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
