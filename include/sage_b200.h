@@ -201,6 +201,11 @@ typedef struct {                    /* &[RawSpectrum] flattened (spectrum.rs:81-
 int sage_b200_process_spectra(int device, const sage_b200_processor_params* processor, const sage_b200_raw_spectra* raw, uint64_t* out_peak_offsets,
                               float* out_masses, float* out_intensities, float* out_tic);
 
+/* tmt::find_reporter_ions (tmt.rs:193-211) over a batch: out[i * n_labels + l] = intensity of the most intense peak of spectrum i within
+ * label_tolerance of labels[l] (offset -PROTON, as the reference), 0 where none (the unwrap_or_default of tmt::quantify, tmt.rs:333). */
+int sage_b200_find_reporter_ions(int device, uint64_t n, const uint64_t* peak_offsets, const float* masses, const float* intensities, const float* labels,
+                                 uint64_t n_labels, sage_b200_tolerance label_tolerance, float* out);
+
 /* Page-locked host buffers: spectra/feature arrays placed here are copied by DMA without a staging memcpy. */
 void* sage_b200_host_alloc(size_t bytes);
 void sage_b200_host_free(void* p);

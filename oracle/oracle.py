@@ -367,5 +367,15 @@ def process_ms2(mz, inten, precursor_charge, take_top_n, deisotope_, min_deisoto
     return om[:k].copy(), oi[:k].copy(), np.float32(tic.value)
 
 
+def find_reporter_ions(peak_off, masses, intens, labels, tol):
+    """tmt.rs:193-211 over a batch -> float32 [n, n_labels] (0 where no peak is within tolerance)."""
+    peak_off = np.ascontiguousarray(peak_off, np.uint64)
+    masses, intens, labels = _f32(masses), _f32(intens), _f32(labels)
+    n = len(peak_off) - 1
+    out = np.zeros((n, len(labels)), np.float32)
+    lib().so_find_reporter_ions(C.c_uint64(n), _p(peak_off), _p(masses), _p(intens), _p(labels), C.c_uint64(len(labels)), Tol(*tol), _p(out))
+    return out
+
+
 def num_threads() -> int:
     return int(lib().so_num_threads())

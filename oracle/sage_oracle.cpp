@@ -1456,6 +1456,16 @@ uint64_t so_page_search(void* h, float precursor_mass, so_tol ptol, so_tol ftol,
     page_search(q, mass, nullptr, [&](const Theoretical& f) { if (n < cap) { out_pep[n] = f.peptide_index; out_mz[n] = f.fragment_mz; } n++; });
     return n;
 }
+// tmt.rs:193-211 find_reporter_ions (+ unwrap_or_default of tmt.rs:333): intensity of the most intense peak within tolerance of each label, else 0
+void so_find_reporter_ions(uint64_t n, const uint64_t* peak_off, const float* masses, const float* intens, const float* labels, uint64_t n_labels, so_tol tol,
+                           float* out) {
+    for (uint64_t i = 0; i < n; i++)
+        for (uint64_t l = 0; l < n_labels; l++) {
+            const int pk = select_most_intense_peak(masses + peak_off[i], intens + peak_off[i], (size_t)(peak_off[i + 1] - peak_off[i]), labels[l],
+                                                    Tolerance{tol.kind, tol.lo, tol.hi}, std::optional<float>(-PROTON));
+            out[i * n_labels + l] = pk >= 0 ? intens[peak_off[i] + pk] : 0.0f;
+        }
+}
 int so_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

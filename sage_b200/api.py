@@ -87,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "sage_b200_device_count", "sage_b200_db_create", "sage_b200_db_build", "sage_b200_db_get_info", "sage_b200_db_export_index", "sage_b200_db_destroy",
     "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_scorer_set_option", "sage_b200_score_batch", "sage_b200_batch_upload", "sage_b200_batch_run",
     "sage_b200_batch_download", "sage_b200_score_batch_multi", "sage_b200_quick_score", "sage_b200_initial_hits", "sage_b200_counters_get",
-    "sage_b200_process_spectra", "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
+    "sage_b200_process_spectra", "sage_b200_find_reporter_ions", "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
 ]
 
 _lib = None
@@ -519,6 +519,20 @@ class SpectrumProcessor:
         _check(load_library().sage_b200_process_spectra(C.c_int(self.device), C.byref(pp), C.byref(raw), _ptr(out_off), _ptr(om), _ptr(oi), _ptr(tic)))
         k = int(out_off[-1])
         return out_off, om[:k].copy(), oi[:k].copy(), tic
+
+
+TMT6PLEX = np.float32([126.127726, 127.124761, 128.134436, 129.131471, 130.141145, 131.138180])   # tmt.rs:213-215
+
+
+def find_reporter_ions(peak_off, masses, intensities, labels, label_tolerance: Tolerance, device: int = 0) -> np.ndarray:
+    """tmt::find_reporter_ions (tmt.rs:193-211) over a batch of ProcessedSpectrum -> float32 [n, n_labels]."""
+    peak_off = np.ascontiguousarray(peak_off, np.uint64)
+    masses, intensities, labels = (np.ascontiguousarray(x, np.float32) for x in (masses, intensities, labels))
+    n = len(peak_off) - 1
+    out = np.zeros((n, len(labels)), np.float32)
+    _check(load_library().sage_b200_find_reporter_ions(C.c_int(device), C.c_uint64(n), _ptr(peak_off), _ptr(masses), _ptr(intensities), _ptr(labels),
+                                                       C.c_uint64(len(labels)), label_tolerance._c(), _ptr(out)))
+    return out
 
 
 Feature = FEATURE_DTYPE

@@ -1572,6 +1572,35 @@ __global__ void __launch_bounds__(32) k_process_ms2(ProcParams pp, uint32_t n, c
     }
 }
 
+// ------------------------------------------------------------------------------------------- TMT reporter ions
+// find_reporter_ions (tmt.rs:193-211): one thread per (spectrum, label); select_most_intense_peak with offset Some(-PROTON) (spectrum.rs:134-159).
+__global__ void k_find_reporter_ions(uint32_t n, uint32_t n_labels, const uint32_t* peak_off, const float* masses, const float* intens, const float* labels,
+                                     Tol tol, float* out) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (uint64_t)n * n_labels) return;
+    const uint32_t s = (uint32_t)(j / n_labels), l = (uint32_t)(j - (uint64_t)s * n_labels);
+    const uint32_t p0 = peak_off[s], np = peak_off[s + 1] - p0;
+    const float* m = masses + p0;
+    const float* it = intens + p0;
+    float lo, hi;
+    tol_bounds(tol, labels[l], lo, hi);
+    lo = __fadd_rn(lo, -PROTON);   // lo + offset.unwrap_or_default()
+    hi = __fadd_rn(hi, -PROTON);
+    const int klo = f32_key(lo), khi = f32_key(hi);
+    uint32_t a, b2;
+    binary_search_slice(np, [&](uint32_t k) { return f32_key(__ldg(m + k)) < klo; }, [&](uint32_t k) { return f32_key(__ldg(m + k)) <= khi; }, a, b2);
+    int best = -1;
+    float max_int = 0.0f;
+    for (uint32_t idx = a; idx < b2; idx++) {
+        const float mm = __ldg(m + idx);
+        if (mm >= lo && mm <= hi) {
+            const float v = __ldg(it + idx);
+            if (v >= max_int) { max_int = v; best = (int)idx; }
+        }
+    }
+    out[j] = best >= 0 ? __ldg(it + best) : 0.0f;
+}
+
 // ------------------------------------------------------------------------------------------- index construction
 // IonSeries (ion_series.rs:36-85) for every kind of every peptide; one thread per peptide (sequential f32 running sum).
 __global__ void k_build_ions(uint32_t n_pep, const uint32_t* seq_off, const uint8_t* seq, const float* mods, const float* nterm, const float* mono,

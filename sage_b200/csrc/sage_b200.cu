@@ -1136,6 +1136,39 @@ extern "C" int sage_b200_process_spectra(int device, const sage_b200_processor_p
     return 0;
 }
 
+// tmt::find_reporter_ions over a batch of ProcessedSpectrum (tmt.rs:193-211, called from tmt::quantify tmt.rs:322-333).
+extern "C" int sage_b200_find_reporter_ions(int device, uint64_t n, const uint64_t* peak_offsets, const float* masses, const float* intensities, const float* labels,
+                                            uint64_t n_labels, sage_b200_tolerance label_tolerance, float* out) {
+    if (n == 0 || n_labels == 0) return 0;
+    if (!peak_offsets || !labels || !out) return fail(SAGE_B200_EINVAL, "find_reporter_ions: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SAGE_B200_ECUDA, "no CUDA device available: sage_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(SAGE_B200_EINVAL, "device out of range");
+    if (label_tolerance.kind < 0 || label_tolerance.kind > 2) return fail(SAGE_B200_EINVAL, "bad tolerance kind");
+    CUDA_TRY(cudaSetDevice(device));
+    const uint64_t pk0 = peak_offsets[0], npk = peak_offsets[n] - pk0;
+    if (npk && (!masses || !intensities)) return fail(SAGE_B200_EINVAL, "find_reporter_ions: null peak arrays");
+    if (n > 0x7FFFFFFFull || npk > 0xFFFFFFF0ull || n_labels > 4096) return fail(SAGE_B200_ELIMIT, "find_reporter_ions: batch too large");
+    std::vector<uint32_t> off(n + 1);
+    for (uint64_t i = 0; i <= n; i++) off[i] = (uint32_t)(peak_offsets[i] - pk0);
+    void *d_off = nullptr, *d_m = nullptr, *d_i = nullptr, *d_l = nullptr, *d_o = nullptr;
+    auto cleanup = [&]() { for (void* p : {d_off, d_m, d_i, d_l, d_o}) if (p) cudaFree(p); };
+#define TRY_R(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(SAGE_B200_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    TRY_R(cudaMalloc(&d_off, 4 * (n + 1))); TRY_R(cudaMalloc(&d_m, 4 * npk + 16)); TRY_R(cudaMalloc(&d_i, 4 * npk + 16));
+    TRY_R(cudaMalloc(&d_l, 4 * n_labels)); TRY_R(cudaMalloc(&d_o, 4 * n * n_labels));
+    TRY_R(cudaMemcpy(d_off, off.data(), 4 * (n + 1), cudaMemcpyHostToDevice));
+    if (npk) { TRY_R(cudaMemcpy(d_m, masses + pk0, 4 * npk, cudaMemcpyHostToDevice)); TRY_R(cudaMemcpy(d_i, intensities + pk0, 4 * npk, cudaMemcpyHostToDevice)); }
+    TRY_R(cudaMemcpy(d_l, labels, 4 * n_labels, cudaMemcpyHostToDevice));
+    const uint64_t total = n * n_labels;
+    k_find_reporter_ions<<<(unsigned)((total + 255) / 256), 256>>>((uint32_t)n, (uint32_t)n_labels, (const uint32_t*)d_off, (const float*)d_m, (const float*)d_i,
+                                                                  (const float*)d_l, Tol{label_tolerance.kind, label_tolerance.lo, label_tolerance.hi}, (float*)d_o);
+    TRY_R(cudaGetLastError());
+    TRY_R(cudaMemcpy(out, d_o, 4 * total, cudaMemcpyDeviceToHost));
+#undef TRY_R
+    cleanup();
+    return 0;
+}
+
 extern "C" int sage_b200_counters_get(const sage_b200_scorer* S, sage_b200_counters* out) {
     if (!S || !out) return fail(SAGE_B200_EINVAL, "counters_get: null argument");
     *out = S->last;

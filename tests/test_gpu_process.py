@@ -61,3 +61,26 @@ def test_process_config1_fixture(config1):
         goff, gm, gi, gt = SpectrumProcessor(top_n, True, 0.0).process_batch(off, config1["mz"], config1["intensity"], chg)
         om, oi, ot = O.process_ms2(config1["mz"], config1["intensity"], config1["precursor_charge"], top_n, True, 0.0)
         assert len(gm) == len(om) == top_n and np.array_equal(gm, om) and np.array_equal(gi, oi) and gt[0] == ot
+
+
+def test_find_reporter_ions_matches_oracle():
+    # tmt.rs:193-211; the -PROTON offset semantics are pinned by the reference test spectrum.rs:589-605 (in test_oracle_known_answers.py)
+    from sage_b200 import Tolerance
+    from sage_b200.api import TMT6PLEX, find_reporter_ions
+    rng = np.random.default_rng(77)
+    n = 300
+    off, masses, intens = [0], [], []
+    for i in range(n):
+        k = int(rng.choice([0, 3, 50, 200]))
+        m = rng.uniform(100, 1500, k)
+        lab = TMT6PLEX[rng.random(6) < 0.7].astype(np.float64) - 1.0072764
+        m = np.concatenate([m, lab * (1 + rng.normal(0, 3e-6, len(lab))), lab * (1 + rng.normal(0, 8e-6, len(lab)))])
+        m = np.sort(m.astype(np.float32))
+        masses.append(m)
+        intens.append(rng.lognormal(8, 1, len(m)).astype(np.float32))
+        off.append(off[-1] + len(m))
+    masses, intens, off = np.concatenate(masses), np.concatenate(intens), np.array(off, np.uint64)
+    for tol, otol in ((Tolerance.ppm(-20, 20), (O.PPM, -20.0, 20.0)), (Tolerance.da(-0.003, 0.003), (O.DA, -0.003, 0.003))):
+        g = find_reporter_ions(off, masses, intens, TMT6PLEX, tol)
+        o = O.find_reporter_ions(off, masses, intens, TMT6PLEX, otol)
+        assert (g > 0).sum() > 500 and np.array_equal(g.view(np.uint32), o.view(np.uint32))
