@@ -133,6 +133,7 @@ typedef struct {
     uint64_t prelim_bytes;         /* the part of it the preliminary-scoring kernel(s) move */
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied across PCIe for the batch */
     uint64_t kernel_launches;
+    uint64_t chunk_retries;        /* chunks re-run because a device work list was sized too small (first batches of a scorer) */
     float ms_total, ms_h2d, ms_setup, ms_prelim, ms_score, ms_d2h; /* summed over chunks */
 } sage_b200_counters;
 
@@ -153,8 +154,12 @@ void sage_b200_db_destroy(sage_b200_db* db);
 
 int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_scorer_params* params, sage_b200_scorer** out);
 void sage_b200_scorer_destroy(sage_b200_scorer* scorer);
-/* Tuning knobs that do not change results. "pep_cap": precursor windows with at most this many peptides are counted by streaming
- * the candidates' ion tables instead of probing the fragment index (0 = always probe the index, the reference's loop order). */
+/* Tuning knobs that do not change results.
+ *   "pep_cap"         precursor windows with at most this many peptides are counted by streaming the candidates' ion tables instead of
+ *                     probing the fragment index (default 0 = always probe the index, the reference's loop order)
+ *   "sort_spectra"    1 (default): process spectra in ascending precursor order for cache locality; results are returned in input order
+ *   "pipeline_chunks" cut every batch into at least this many pipelined chunks (default 1: a short first chunk + chunks of <= 65536 spectra)
+ *   "wide_tile", "wide_lmax", "worklist_reset"   test hooks (tile size / survivor-list size of the open-search kernel; forget learned list sizes) */
 int sage_b200_scorer_set_option(sage_b200_scorer* scorer, const char* name, int64_t value);
 
 /* Scorer::score over a batch (runner.rs:311-325 `par_iter().flat_map(|s| scorer.score(s))`).

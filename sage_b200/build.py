@@ -14,7 +14,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 
 
 def library_path() -> str:
-    return _OUT
+    return os.environ.get("SAGE_B200_LIB") or _OUT   # SAGE_B200_LIB: load a specific build (A/B measurements)
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

@@ -152,7 +152,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 struct ReplaySlot { unsigned long long off; uint32_t item, n_list, state /*0 = replay pending, 1 = nothing to do*/, k; };
 
 // Device counters (u64 slots)
-enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_PEPQ, C_PEPFALLBACK, C_WSLOT, C_WOVERFLOW, C_FRAGS, C_COUNT };
+enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_PEPQ, C_PEPFALLBACK, C_WSLOT, C_WOVERFLOW, C_FRAGS,
+       C_NLIST /* bump cursor of the narrow key-list arena */, C_NLIST_NEED /* arena entries this chunk needs (exact upper bound) */, C_COUNT };
 
 struct DbView {
     const uint2* frag;        // {peptide_index, fragment_mz bits}, reference bucket layout
@@ -214,6 +215,11 @@ struct BatchView {
     QueryHits* hits;            // n * qmax
     uint64_t* hit_keys;         // n * qmax * kparam
     unsigned long long* counters;
+    // Device-side work lists sized from what earlier chunks needed (no host round trip inside a chunk): when a capacity turns out too
+    // small the affected queries produce no hits, the host sees need > capacity in the counters and re-runs the chunk with exact sizes.
+    uint32_t* wide_items;             // compacted item ids of the open-search (mode 2) queries, wide_cap entries
+    uint32_t wide_cap;
+    unsigned long long nlist_cap;     // entries in the narrow key-list arena
 };
 
 }  // namespace sb

@@ -17,7 +17,7 @@ namespace sb {
 // ------------------------------------------------------------------------------------------------ setup
 // One thread per spectrum: enumerate the (charge, isotope) queries of Scorer::initial_hits and resolve each
 // precursor window to a PeptideIx range (two binary searches over peptides[].monoisotopic).
-__global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t* sort_key, uint32_t* sort_val, uint32_t* list_cap) {
+__global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t* sort_key, uint32_t* sort_val) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n) return;
     const float pmz = b.prec_mz[s];
@@ -28,7 +28,7 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
     uint32_t c1 = fold ? sc.max_charge : known;
     QueryDesc* out = b.queries + (size_t)s * sc.qmax;
     uint32_t qi = 0;
-    unsigned long long nq = 0, nwide = 0, maxpot = 0, npepq = 0;
+    unsigned long long nq = 0, nwide = 0, maxpot = 0, npepq = 0, list_need = 0;
     for (uint32_t z = c0; z <= c1 && qi < sc.qmax; z++) {
         const float precursor_mass = __fmul_rn(mz, (float)z);
         Tol ptol = sc.precursor_tol;
@@ -64,9 +64,13 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
             q.nfc = (uint8_t)(mfc - 1);
             q.mode = q.potential > NARROW_CAP ? 2 : ((db.pep_centric_ok && q.potential <= sc.pep_cap) ? 3 : 1);
             out[qi] = q;
-            if (list_cap) list_cap[(size_t)s * sc.qmax + qi] = (q.mode == 1 || q.mode == 3) ? q.potential : 0;
+            if (q.mode != 2 && q.potential > sc.kparam) list_need += q.potential;   // k_prelim_narrow reserves exactly this much of the arena
             nq++;
-            if (q.mode == 2) nwide++;
+            if (q.mode == 2) {   // "no hits" until k_prelim_wide gets to it (it may not, when wide_cap is too small: the host then re-runs the chunk)
+                nwide++;
+                QueryHits h0; h0.n = 0; h0.default_run = q.potential; h0.matched_peaks = 0; h0.scored_candidates = 0;
+                b.hits[(size_t)s * sc.qmax + qi] = h0;
+            }
             if (q.mode == 3) npepq++;
             if (q.potential > maxpot) maxpot = q.potential;
         }
@@ -74,11 +78,15 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
     for (; qi < sc.qmax; qi++) {
         QueryDesc q = {};
         out[qi] = q;
-        if (list_cap) list_cap[(size_t)s * sc.qmax + qi] = 0;
     }
     if (sort_key) { sort_key[s] = out[0].mode ? out[0].pre_lo : 0xFFFFFFFFu; sort_val[s] = s; }
     if (nq) atomicAdd(b.counters + C_QUERIES, nq);
-    if (nwide) atomicAdd(b.counters + C_WIDE, nwide);
+    if (nwide) {   // compact work list of the open-search queries (one reservation per spectrum)
+        unsigned long long w = atomicAdd(b.counters + C_WIDE, nwide);
+        for (uint32_t j = 0; j < sc.qmax; j++)
+            if (out[j].mode == 2) { if (w < b.wide_cap) b.wide_items[w] = s * sc.qmax + j; w++; }
+    }
+    if (list_need) atomicAdd(b.counters + C_NLIST_NEED, list_need);
     if (npepq) atomicAdd(b.counters + C_PEPQ, npepq);
     atomicMax(b.counters + C_MAXPOT, maxpot);
 }
@@ -180,7 +188,7 @@ __device__ __forceinline__ uint32_t page_lower_bound_dir(const DbView& db, uint3
 //    (bounds computed with the reference's f32 ops; both arrays are monotone in the peak mass, which is verified per
 //    spectrum — otherwise the CTA falls back to the index path).
 __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b, uint32_t pmax, uint64_t* nlist,
-                                                                  const uint32_t* nlist_off, ReplaySlot* nslots) {
+                                                                  ReplaySlot* nslots) {
     __shared__ uint32_t cnt32[NARROW_CAP / 2 + 1];
     __shared__ uint32_t s_warp[40];
     extern __shared__ float bounds_smem[];  // LO[nfc][np] then HI[nfc][np] (peptide-centric path only)
@@ -196,6 +204,9 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
     const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
     const uint32_t nwords = (q.potential + 1) >> 1;
     for (uint32_t i = tid; i < nwords; i += PRELIM_THREADS) cnt32[i] = 0;
+    // key-list space for the trim (only windows larger than k need one): bump-allocated from the chunk's arena, read after the barrier below
+    __shared__ unsigned long long s_loff;
+    if (tid == 0 && q.potential > sc.kparam) s_loff = atomicAdd(b.counters + C_NLIST, (unsigned long long)q.potential);
 
     const uint32_t nfc = q.nfc;
     const uint32_t ntask = np * nfc;
@@ -347,7 +358,15 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
         }
         return;
     }
-    uint64_t* list = nlist + nlist_off[item];
+    const unsigned long long loff = s_loff;
+    if (loff + n > b.nlist_cap) {   // arena too small (the host sees C_NLIST_NEED > capacity and re-runs the chunk): leave "no hits"
+        if (tid == 0) {
+            h->n = 0; h->default_run = q.potential; h->matched_peaks = 0; h->scored_candidates = 0;
+            slot->off = 0; slot->item = item; slot->n_list = 0; slot->state = 1; slot->k = 0;
+        }
+        return;
+    }
+    uint64_t* list = nlist + loff;
     for (uint32_t i = tid; i < k; i += PRELIM_THREADS) {
         const uint32_t c = cnt(i);
         nzc += c != 0;
@@ -374,7 +393,7 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
     const uint32_t nzt = block_sum_u32(nzc, s_warp);
     if (tid == 0) {
         h->n = k; h->default_run = 0; h->matched_peaks = matched_total; h->scored_candidates = nzt;
-        slot->off = nlist_off[item]; slot->item = item; slot->n_list = wbase; slot->state = 0; slot->k = k;
+        slot->off = loff; slot->item = item; slot->n_list = wbase; slot->state = 0; slot->k = k;
     }
 }
 
@@ -435,14 +454,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            uint32_t it;
-            for (;;) {  // next wide item
-                it = (uint32_t)atomicAdd(b.counters + C_WORK, 1ull);
-                if (it >= n_items || b.queries[it].mode == 2) break;
-            }
-            S.s_item = it;
-            if (it < n_items) {
-                S.s_slot = (uint32_t)atomicAdd(b.counters + C_WSLOT, 1ull);
+            // next entry of the compacted open-search work list (k_setup_queries); slot == position in that list
+            const unsigned long long nw = min(b.counters[C_WIDE], (unsigned long long)b.wide_cap);
+            const unsigned long long w = atomicAdd(b.counters + C_WORK, 1ull);
+            S.s_item = w < nw ? b.wide_items[w] : n_items;
+            if (w < nw) {
+                S.s_slot = (uint32_t)w;
                 S.s_level = 1; S.s_listn = 0; S.s_serial = 0;
             }
         }
@@ -859,9 +876,11 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
 // serial replays (their result ORDER is observable) of all queries of the batch run concurrently instead of stalling a whole CTA each.
 // Heaps live in shared memory, interleaved by thread. Used by both preliminary-scoring kernels.
 constexpr int REPLAY_THREADS = 128;
-__global__ void __launch_bounds__(REPLAY_THREADS) k_replay(ScorerView sc, BatchView b, const uint64_t* lists, const ReplaySlot* slots, uint32_t n_slots) {
+__global__ void __launch_bounds__(REPLAY_THREADS) k_replay(ScorerView sc, BatchView b, const uint64_t* lists, const ReplaySlot* slots, uint32_t n_slots,
+                                                           const unsigned long long* n_slots_dev) {
     extern __shared__ uint64_t rheap[];  // [kparam][REPLAY_THREADS]
     const uint32_t slot = blockIdx.x * REPLAY_THREADS + threadIdx.x;
+    if (n_slots_dev != nullptr) n_slots = (uint32_t)min((unsigned long long)n_slots, *n_slots_dev);   // slots actually filled (device-side count)
     if (slot >= n_slots) return;
     const ReplaySlot ws = slots[slot];
     if (ws.state != 0) return;

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -235,8 +236,13 @@ static int db_build_directories(sage_b200_db* db) {
     if (v.n_frag == 0 || v.n_bucket == 0 || v.n_pep == 0 || (getenv("SAGE_B200_NO_DIRECTORIES") && getenv("SAGE_B200_NO_DIRECTORIES")[0] == '1')) return 0;
     int rc;
     if (v.bucket_size <= 65535u) {
+        // cells per page ~ bucket_size / entries-per-cell: the in-cell search that follows a grid lookup is a chain of dependent loads
+        uint32_t epc = 4;   // measured on cfg2: 32 -> 4 entries per cell = -3 % preliminary-scoring time for +3 % index memory
+        if (const char* e = getenv("SAGE_B200_GRID_ENTRIES")) epc = (uint32_t)std::min(1024, std::max(1, atoi(e)));
+        uint32_t cells = 64;
+        while (cells < 16384 && (uint64_t)cells * epc < v.bucket_size) cells <<= 1;
         uint32_t shift = 0;
-        while (((uint64_t)v.n_pep >> shift) >= 256) shift++;
+        while (((uint64_t)v.n_pep >> shift) >= cells) shift++;
         const uint32_t gn = (uint32_t)(((uint64_t)v.n_pep - 1) >> shift) + 1;   // cells 0..gn-1 cover every PeptideIx
         const uint64_t total = (uint64_t)v.n_bucket * (gn + 1);
         if ((rc = dmalloc(db, &db->d_page_grid, 2 * total))) return rc;
@@ -439,30 +445,38 @@ struct ChunkState {
     size_t nitems = 0, smem = 0, small_bytes = 0;
     size_t o_off = 0, o_pmz = 0, o_tic = 0, o_ilo = 0, o_ihi = 0, o_rt = 0, o_ims = 0, o_chg = 0;
     bool timed_upload = false;
+    uint64_t nlist_cap = 0, force_nlist = 0, force_wide = 0;   // work-list capacities of the current attempt / exact needs for a re-run
+    uint32_t wide_cap = 0;
+    double t_issue0 = 0, t_issue1 = 0;   // host time (ms since the call started) when queueing this chunk began / ended (trace only)
 };
 
 // One in-flight chunk: its own stream, device buffers, pinned staging and pending-download bookkeeping. score_batch alternates
 // between two lanes so that the H2D copy of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i.
 struct Lane {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // kernels + D2H
+    cudaStream_t copy = nullptr;     // H2D: masses first (all the counting kernels need), intensities behind them, overlapping setup + preliminary scoring
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_masses = nullptr, ev_intens = nullptr;
     DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_dbgk, d_dbgm, d_sort, d_sorttmp, d_wlist, d_wslots,
-        d_ncap, d_noff, d_nlist, d_nslots, d_scantmp;
+        d_witems, d_nlist, d_nslots;
     PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
     DevBuf d_frags;
     ChunkState chunk;
     // pending work of the chunk in flight
-    bool ran = false, downloading = false;
+    bool ran = false, downloading = false, dbg = false;
     uint64_t launches = 0;
     sage_b200_feature* fdst = nullptr;
     uint32_t* cdst = nullptr;
     bool f_pinned = false, c_pinned = false;
     void release() {
         for (DevBuf* b : {&d_small, &d_masses, &d_intens, &d_queries, &d_hits, &d_keys, &d_features, &d_counts, &d_counters, &d_dbgk, &d_dbgm, &d_sort, &d_sorttmp,
-                          &d_wlist, &d_wslots, &d_ncap, &d_noff, &d_nlist, &d_nslots, &d_scantmp, &d_frags}) b->release();
+                          &d_wlist, &d_wslots, &d_witems, &d_nlist, &d_nslots, &d_frags}) b->release();
         for (PinBuf* b : {&h_small, &h_masses, &h_intens, &h_features, &h_counts, &h_counters}) b->release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (ev_masses) cudaEventDestroy(ev_masses);
+        if (ev_intens) cudaEventDestroy(ev_intens);
         if (stream) cudaStreamDestroy(stream);
+        if (copy) cudaStreamDestroy(copy);
     }
 };
 
@@ -478,7 +492,15 @@ struct sage_b200_scorer {
     // annotate_matches: caller's fragment array for the current call and the running global offset
     sage_b200_fragment* frag_dst = nullptr;
     uint64_t frag_cap = 0, frag_used = 0;
-    int pipeline_chunks = 2;   // score_batch splits large batches into about this many chunks (>= 8192 spectra each)
+    int pipeline_chunks = 1;   // score_batch cuts a batch into at least this many chunks (tuning / tests; large batches are cut at 65536 spectra anyway)
+    // learned work-list sizes (per spectrum of a chunk): narrow key-list arena entries and open-search queries. A chunk that needs more than
+    // its capacity is re-run once with the exact sizes it counted, and the estimates grow.
+    double nlist_per_spectrum = 512.0, wide_per_spectrum = 0.0;
+    int first_chunk_pct = 20;
+    // SAGE_B200_TRACE=1: per-chunk device timeline (ms since the start of the call) on stderr
+    bool trace = false;
+    cudaEvent_t ev_base = nullptr;
+    std::chrono::steady_clock::time_point t_base;
     sage_b200_counters last{};
 };
 
@@ -512,7 +534,7 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     v.wide_lmax = WIDE_LMAX;
     v.wide_variant = 0;  // measured: float compares 142 ms vs unsigned bit-window 150 ms on cfg4
     if (const char* e = getenv("SAGE_B200_WIDE_VARIANT")) v.wide_variant = (uint32_t)atoi(e);
-    v.pep_cap = 64;  // measured crossover on cfg2 (mean window 177 peptides): index probing wins above ~100 candidates
+    v.pep_cap = 0;   // peptide-centric counting of small windows is opt-in: with the dense page grid the index path wins on cfg2 at every cap (0: 1.71 ms, 32: 1.74, 64: 1.82)
     if (const char* e = getenv("SAGE_B200_PEP_CAP")) v.pep_cap = (uint32_t)std::min<long>(std::max<long>(atol(e), 0), (long)NARROW_CAP);
     {   // lnfact table with the host libm (the reference's f64::ln): Stirling form of scoring.rs:170-177
         const uint32_t N = 4096;
@@ -531,9 +553,15 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     if (const char* e = getenv("SAGE_B200_SORT")) s->sort_spectra = atoi(e);
     for (Lane& L : s->lanes) {
         CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&L.copy, cudaStreamNonBlocking));
         for (auto& e : L.ev) CUDA_TRY(cudaEventCreate(&e));
+        CUDA_TRY(cudaEventCreate(&L.ev_masses));
+        CUDA_TRY(cudaEventCreate(&L.ev_intens));
     }
     if (const char* e = getenv("SAGE_B200_PIPELINE_CHUNKS")) s->pipeline_chunks = std::max(1, atoi(e));
+    if (const char* e = getenv("SAGE_B200_TRACE")) s->trace = e[0] == '1';
+    if (const char* e = getenv("SAGE_B200_FIRST_CHUNK_PCT")) s->first_chunk_pct = std::min(50, std::max(0, atoi(e)));
+    CUDA_TRY(cudaEventCreate(&s->ev_base));
     *out = s;
     return 0;
 }
@@ -553,7 +581,13 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
         s->sv.wide_tile = (uint32_t)value;
         return 0;
     }
-    if (!strcmp(name, "pep_cap")) {  // 0 = always probe the fragment index (reference loop order); default 64
+    if (!strcmp(name, "worklist_reset")) {   // test hook: forget the learned work-list sizes; value = narrow arena entries per spectrum to start from
+        if (value < 0) return fail(SAGE_B200_EINVAL, "worklist_reset takes a non-negative entry count");
+        s->nlist_per_spectrum = (double)value;
+        s->wide_per_spectrum = 0.0;
+        return 0;
+    }
+    if (!strcmp(name, "pep_cap")) {  // 0 (default) = always probe the fragment index (reference loop order)
         if (value < 0 || value > (int64_t)NARROW_CAP) return fail(SAGE_B200_EINVAL, "pep_cap must be 0..%u", NARROW_CAP);
         s->sv.pep_cap = (uint32_t)value;
         return 0;
@@ -565,6 +599,7 @@ extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
     if (!s) return;
     cudaSetDevice(s->db->device);
     for (Lane& L : s->lanes) L.release();
+    if (s->ev_base) cudaEventDestroy(s->ev_base);
     s->d_lnfact.release();
     s->d_keep.release();
     delete s;
@@ -578,7 +613,6 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 //   chunk_download D2H of Feature rows + counts
 static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* sp, uint64_t c0, uint64_t c1) {
     const ScorerView& sv = S->sv;
-    cudaStream_t st = L.stream;
     ChunkState& C = L.chunk;
     C.loaded = false;
     const uint32_t n = (uint32_t)(c1 - c0);
@@ -599,49 +633,12 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
     int rc;
     if ((rc = L.h_small.reserve(C.small_bytes))) return rc;
     if ((rc = L.d_small.reserve(C.small_bytes))) return rc;
-    unsigned char* hs = (unsigned char*)L.h_small.p;
-    uint32_t* h_off = (uint32_t*)(hs + C.o_off);
-    uint32_t pmax = 2, zmax = sv.max_charge;
-    for (uint32_t i = 0; i <= n; i++) h_off[i] = (uint32_t)(sp->peak_offsets[c0 + i] - pk0);
-    for (uint32_t i = 0; i < n; i++) {
-        zmax = std::max<uint32_t>(zmax, sp->precursor_charge[c0 + i]);
-        if (sp->peak_offsets[c0 + i + 1] < sp->peak_offsets[c0 + i]) return fail(SAGE_B200_EINVAL, "peak_offsets not monotone at spectrum %llu", (unsigned long long)(c0 + i));
-        pmax = std::max(pmax, h_off[i + 1] - h_off[i]);
-        if (sp->level && sp->level[c0 + i] != 2)
-            return fail(SAGE_B200_ENOTMS2, "internal bug, trying to score a non-MS2 scan! (spectrum %llu has level %u)", (unsigned long long)(c0 + i), sp->level[c0 + i]);
-        if (std::isnan(sp->precursor_mz[c0 + i])) return fail(SAGE_B200_ENOPRECURSOR, "missing MS1 precursor for spectrum %llu", (unsigned long long)(c0 + i));
-    }
-    C.pmax = (pmax + 3) & ~3u;   // multiple of 4 floats: the staged copies in k_score are 16-byte granular
-    C.zmax = zmax;
-    memcpy(hs + C.o_pmz, sp->precursor_mz + c0, 4 * (size_t)n);
-    memcpy(hs + C.o_tic, sp->total_ion_current + c0, 4 * (size_t)n);
-    float* h_ilo = (float*)(hs + C.o_ilo);
-    float* h_ihi = (float*)(hs + C.o_ihi);
-    float* h_rt = (float*)(hs + C.o_rt);
-    float* h_ims = (float*)(hs + C.o_ims);
-    for (uint32_t i = 0; i < n; i++) {
-        h_ilo[i] = sp->isolation_lo ? sp->isolation_lo[c0 + i] : NAN;
-        h_ihi[i] = sp->isolation_hi ? sp->isolation_hi[c0 + i] : NAN;
-        h_rt[i] = sp->scan_start_time ? sp->scan_start_time[c0 + i] : 0.0f;
-        h_ims[i] = sp->inverse_ion_mobility ? sp->inverse_ion_mobility[c0 + i] : NAN;
-    }
-    memcpy(hs + C.o_chg, sp->precursor_charge + c0, n);
-    C.smem = (size_t)(C.pmax + 4) * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + 2 * SPEC_LUT_CELLS + C.pmax + 16;
-    if (C.smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", C.pmax);
-    C.nitems = (size_t)n * sv.qmax;
-    if (C.nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
     if ((rc = L.d_masses.reserve(4 * npk + 16))) return rc;
     if ((rc = L.d_intens.reserve(4 * npk + 16))) return rc;
-    if ((rc = L.d_queries.reserve(C.nitems * sizeof(QueryDesc)))) return rc;
-    if ((rc = L.d_hits.reserve(C.nitems * sizeof(QueryHits)))) return rc;
-    if ((rc = L.d_keys.reserve(C.nitems * sv.kparam * 8))) return rc;
-    if ((rc = L.d_features.reserve((size_t)n * sv.report_psms * sizeof(FeatureOut)))) return rc;
-    if ((rc = L.d_counts.reserve(4 * (size_t)n))) return rc;
-    if ((rc = L.d_counters.reserve(8 * C_COUNT))) return rc;
-    if ((rc = L.h_counters.reserve(8 * C_COUNT + 32))) return rc;
-
-    CUDA_TRY(cudaEventRecord(L.ev[0], st));
-    CUDA_TRY(cudaMemcpyAsync(L.d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, st));
+    // The peak masses (half of the H2D bytes) go first and need no host preparation: their copy is in flight while the per-spectrum
+    // arrays are validated and packed below.
+    cudaStream_t cp = L.copy;
+    CUDA_TRY(cudaEventRecord(L.ev[0], cp));
     const float* src_m = sp->masses + pk0;
     const float* src_i = sp->intensities + pk0;
     if (npk) {
@@ -650,17 +647,67 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
             memcpy(L.h_masses.p, src_m, 4 * npk);
             src_m = (const float*)L.h_masses.p;
         }
-        if (!is_pinned(src_i)) {
-            if ((rc = L.h_intens.reserve(4 * npk))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(L.d_masses.p, src_m, 4 * npk, cudaMemcpyHostToDevice, cp));
+    }
+    unsigned char* hs = (unsigned char*)L.h_small.p;
+    auto pack = [&]() -> int {   // small per-spectrum arrays -> one pinned blob -> one H2D
+        uint32_t* h_off = (uint32_t*)(hs + C.o_off);
+        uint32_t pmax = 2, zmax = sv.max_charge;
+        for (uint32_t i = 0; i <= n; i++) h_off[i] = (uint32_t)(sp->peak_offsets[c0 + i] - pk0);
+        for (uint32_t i = 0; i < n; i++) {
+            zmax = std::max<uint32_t>(zmax, sp->precursor_charge[c0 + i]);
+            if (sp->peak_offsets[c0 + i + 1] < sp->peak_offsets[c0 + i]) return fail(SAGE_B200_EINVAL, "peak_offsets not monotone at spectrum %llu", (unsigned long long)(c0 + i));
+            pmax = std::max(pmax, h_off[i + 1] - h_off[i]);
+            if (sp->level && sp->level[c0 + i] != 2)
+                return fail(SAGE_B200_ENOTMS2, "internal bug, trying to score a non-MS2 scan! (spectrum %llu has level %u)", (unsigned long long)(c0 + i), sp->level[c0 + i]);
+            if (std::isnan(sp->precursor_mz[c0 + i])) return fail(SAGE_B200_ENOPRECURSOR, "missing MS1 precursor for spectrum %llu", (unsigned long long)(c0 + i));
+        }
+        C.pmax = (pmax + 3) & ~3u;   // multiple of 4 floats: the staged copies in k_score are 16-byte granular
+        C.zmax = zmax;
+        memcpy(hs + C.o_pmz, sp->precursor_mz + c0, 4 * (size_t)n);
+        memcpy(hs + C.o_tic, sp->total_ion_current + c0, 4 * (size_t)n);
+        float* h_ilo = (float*)(hs + C.o_ilo);
+        float* h_ihi = (float*)(hs + C.o_ihi);
+        float* h_rt = (float*)(hs + C.o_rt);
+        float* h_ims = (float*)(hs + C.o_ims);
+        for (uint32_t i = 0; i < n; i++) {
+            h_ilo[i] = sp->isolation_lo ? sp->isolation_lo[c0 + i] : NAN;
+            h_ihi[i] = sp->isolation_hi ? sp->isolation_hi[c0 + i] : NAN;
+            h_rt[i] = sp->scan_start_time ? sp->scan_start_time[c0 + i] : 0.0f;
+            h_ims[i] = sp->inverse_ion_mobility ? sp->inverse_ion_mobility[c0 + i] : NAN;
+        }
+        memcpy(hs + C.o_chg, sp->precursor_charge + c0, n);
+        C.smem = (size_t)(C.pmax + 4) * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + 2 * SPEC_LUT_CELLS + C.pmax + 16;
+        if (C.smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", C.pmax);
+        C.nitems = (size_t)n * sv.qmax;
+        if (C.nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
+        int r;
+        if ((r = L.d_queries.reserve(C.nitems * sizeof(QueryDesc)))) return r;
+        if ((r = L.d_hits.reserve(C.nitems * sizeof(QueryHits)))) return r;
+        if ((r = L.d_keys.reserve(C.nitems * sv.kparam * 8))) return r;
+        if ((r = L.d_features.reserve((size_t)n * sv.report_psms * sizeof(FeatureOut)))) return r;
+        if ((r = L.d_counts.reserve(4 * (size_t)n))) return r;
+        if ((r = L.d_counters.reserve(8 * C_COUNT))) return r;
+        if ((r = L.h_counters.reserve(8 * C_COUNT + 32))) return r;
+        if (npk && !is_pinned(src_i)) {
+            if ((r = L.h_intens.reserve(4 * npk))) return r;
             memcpy(L.h_intens.p, src_i, 4 * npk);
             src_i = (const float*)L.h_intens.p;
         }
-        CUDA_TRY(cudaMemcpyAsync(L.d_masses.p, src_m, 4 * npk, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(L.d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, st));
+        return 0;
+    };
+    if ((rc = pack())) {
+        cudaStreamSynchronize(cp);   // the masses copy may still be reading the caller's array
+        return rc;
     }
-    CUDA_TRY(cudaEventRecord(L.ev[1], st));
+    CUDA_TRY(cudaMemcpyAsync(L.d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, cp));
+    CUDA_TRY(cudaEventRecord(L.ev_masses, cp));   // setup + preliminary scoring can start: they never read intensities
+    if (npk) CUDA_TRY(cudaMemcpyAsync(L.d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, cp));
+    CUDA_TRY(cudaEventRecord(L.ev_intens, cp));
+    CUDA_TRY(cudaEventRecord(L.ev[1], cp));
     S->last.h2d_bytes += C.small_bytes + 8 * npk;
     C.loaded = true;
+    C.force_nlist = C.force_wide = 0;
     C.timed_upload = true;
     L.ran = false;
     L.downloading = false;
@@ -698,6 +745,10 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     bv.hit_keys = L.d_keys.as<uint64_t>();
     bv.counters = L.d_counters.as<unsigned long long>();
 
+    // kernels of the two lanes never overlap (measured: k_score of one chunk next to k_prelim_narrow of the other slows both); only
+    // copies overlap kernels. ev[4] = end of the other lane's k_score (a never-recorded event counts as complete).
+    CUDA_TRY(cudaStreamWaitEvent(st, S->lanes[(&L - S->lanes) ^ 1].ev[4], 0));
+    CUDA_TRY(cudaStreamWaitEvent(st, L.ev_masses, 0));
     CUDA_TRY(cudaEventRecord(L.ev[6], st));
     CUDA_TRY(cudaMemsetAsync(L.d_counters.p, 0, 8 * C_COUNT, st));
     const bool annotate = sv.annotate && S->frag_dst != nullptr;
@@ -724,62 +775,53 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
         if ((rc = L.d_sorttmp.reserve(sort_tmp + 16))) return rc;
     }
-    // per-item list capacity (window size of narrow queries) -> exclusive scan -> list offsets for the replay kernel
-    if ((rc = L.d_ncap.reserve(4 * (C.nitems + 1)))) return rc;
-    if ((rc = L.d_noff.reserve(4 * (C.nitems + 1)))) return rc;
-    size_t scan_tmp = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, L.d_ncap.as<uint32_t>(), L.d_noff.as<uint32_t>(), (int)(C.nitems + 1), st));
-    if ((rc = L.d_scantmp.reserve(scan_tmp + 16))) return rc;
-    CUDA_TRY(cudaMemsetAsync(L.d_ncap.as<uint32_t>() + C.nitems, 0, 4, st));
-    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv, sk_in, sv_in, L.d_ncap.as<uint32_t>());
+    // Work-list capacities come from what earlier chunks needed (S->nlist_per_spectrum / wide_per_spectrum) or, on a re-run, from the
+    // exact need the failed attempt counted: nothing in a chunk waits for the host, so chunks of both lanes queue back to back.
+    C.nlist_cap = std::max<uint64_t>(C.force_nlist, (uint64_t)std::ceil(S->nlist_per_spectrum * (double)n) + 4096);
+    C.wide_cap = (uint32_t)std::min<uint64_t>(C.nitems, std::max<uint64_t>(C.force_wide, S->wide_per_spectrum > 0.0
+                                                                               ? (uint64_t)std::ceil(S->wide_per_spectrum * 1.1 * (double)n) + 64 : 0));
+    if ((rc = L.d_nlist.reserve(8 * (C.nlist_cap + 16)))) return rc;
+    if ((rc = L.d_nslots.reserve(C.nitems * sizeof(ReplaySlot)))) return rc;
+    if (C.wide_cap) {
+        if ((rc = L.d_witems.reserve(4 * (size_t)C.wide_cap))) return rc;
+        if ((rc = L.d_wlist.reserve((size_t)C.wide_cap * WIDE_LMAX * 8))) return rc;
+        if ((rc = L.d_wslots.reserve((size_t)C.wide_cap * sizeof(WideSlot)))) return rc;
+    }
+    bv.wide_items = L.d_witems.as<uint32_t>();
+    bv.wide_cap = C.wide_cap;
+    bv.nlist_cap = C.nlist_cap;
+    k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv, sk_in, sv_in);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(L.d_scantmp.p, scan_tmp, L.d_ncap.as<uint32_t>(), L.d_noff.as<uint32_t>(), (int)(C.nitems + 1), st));
     if (sk_in) {
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(L.d_sorttmp.p, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
         bv.order = sv_out;
     }
     CUDA_TRY(cudaEventRecord(L.ev[2], st));
-    unsigned long long* hc = (unsigned long long*)L.h_counters.p;
-    CUDA_TRY(cudaMemcpyAsync(hc, L.d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
-    uint32_t* h_total = (uint32_t*)(hc + C_COUNT);
-    CUDA_TRY(cudaMemcpyAsync(h_total, L.d_noff.as<uint32_t>() + C.nitems, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    const uint64_t n_queries = hc[C_QUERIES], n_wide = hc[C_WIDE], max_pot = hc[C_MAXPOT];
-    const uint64_t nlist_total = *h_total;
     uint64_t launches = 1;
 
-    // ---- preliminary scoring
-    if (n_queries > n_wide) {
-        if ((rc = L.d_nlist.reserve(8 * (nlist_total + 16)))) return rc;
-        if ((rc = L.d_nslots.reserve(C.nitems * sizeof(ReplaySlot)))) return rc;
-        k_prelim_narrow<<<(unsigned)C.nitems, PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>(), L.d_noff.as<uint32_t>(),
-                                                                              L.d_nslots.as<ReplaySlot>());
-        CUDA_TRY(cudaGetLastError());
-        const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
-        CUDA_TRY(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-        k_replay<<<(unsigned)((C.nitems + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, L.d_nlist.as<uint64_t>(),
-                                                                                                           L.d_nslots.as<ReplaySlot>(), (uint32_t)C.nitems);
-        CUDA_TRY(cudaGetLastError());
-        launches += 2;
-    }
-    if (n_wide) {
-        (void)max_pot;
-        const int ctas = (int)std::min<uint64_t>((uint64_t)db->sm_count, n_wide);
+    // ---- preliminary scoring. Both kernels are always queued: CTAs whose query belongs to the other kernel (or to nobody) exit at once.
+    const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
+    CUDA_TRY(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+    k_prelim_narrow<<<(unsigned)C.nitems, PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>(), L.d_nslots.as<ReplaySlot>());
+    CUDA_TRY(cudaGetLastError());
+    k_replay<<<(unsigned)((C.nitems + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, L.d_nlist.as<uint64_t>(), L.d_nslots.as<ReplaySlot>(),
+                                                                                                       (uint32_t)C.nitems, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    launches += 2;
+    if (C.wide_cap) {
+        const int ctas = (int)std::min<uint64_t>((uint64_t)db->sm_count, C.wide_cap);
         CUDA_TRY(cudaFuncSetAttribute(k_prelim_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WideSmem)));
-        if ((rc = L.d_wlist.reserve((size_t)n_wide * WIDE_LMAX * 8))) return rc;
-        if ((rc = L.d_wslots.reserve((size_t)n_wide * sizeof(WideSlot)))) return rc;
         k_prelim_wide<<<ctas, WIDE_THREADS, sizeof(WideSmem), st>>>(db->v, sv, bv, (uint32_t)C.nitems, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>());
         CUDA_TRY(cudaGetLastError());
-        const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
-        CUDA_TRY(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-        k_replay<<<(unsigned)((n_wide + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, L.d_wlist.as<uint64_t>(),
-                                                                                                              L.d_wslots.as<WideSlot>(), (uint32_t)n_wide);
+        k_replay<<<(unsigned)((C.wide_cap + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(
+            sv, bv, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>(), C.wide_cap, L.d_counters.as<unsigned long long>() + C_WIDE);
         CUDA_TRY(cudaGetLastError());
         launches += 2;
     }
     CUDA_TRY(cudaEventRecord(L.ev[3], st));
 
-    // ---- candidate scoring + feature assembly
+    // ---- candidate scoring + feature assembly (first reader of the intensities)
+    CUDA_TRY(cudaStreamWaitEvent(st, L.ev_intens, 0));
     CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));
     k_score<<<n, SCORE_THREADS, C.smem, st>>>(db->v, sv, bv, L.d_features.as<FeatureOut>(), L.d_counts.as<uint32_t>(), C.pmax,
                                              dbg ? L.d_dbgk.as<uint64_t>() : nullptr, dbg ? L.d_dbgm.as<uint32_t>() : nullptr,
@@ -788,8 +830,9 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     CUDA_TRY(cudaGetLastError());
     launches++;
     CUDA_TRY(cudaEventRecord(L.ev[4], st));
-    CUDA_TRY(cudaMemcpyAsync(hc, L.d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(L.h_counters.p, L.d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
     L.launches = launches;
+    L.dbg = dbg;
     L.ran = true;
     return 0;
 }
@@ -819,7 +862,39 @@ static int chunk_download(sage_b200_scorer* S, Lane& L, sage_b200_feature* fdst,
 static int lane_finish(sage_b200_scorer* S, Lane& L) {
     ChunkState& C = L.chunk;
     if (!C.loaded) return 0;
-    CUDA_TRY(cudaStreamSynchronize(L.stream));
+    CUDA_TRY(cudaStreamSynchronize(L.copy));
+    for (int attempt = 0;; attempt++) {
+        CUDA_TRY(cudaStreamSynchronize(L.stream));
+        if (!L.ran) break;
+        const unsigned long long* hc = (const unsigned long long*)L.h_counters.p;
+        const uint64_t need = hc[C_NLIST_NEED], nw = hc[C_WIDE];
+        if (need <= C.nlist_cap && nw <= C.wide_cap) {   // the chunk fitted its work lists: remember what it needed
+            S->nlist_per_spectrum = std::max(S->nlist_per_spectrum, 1.25 * (double)need / (double)C.n);
+            S->wide_per_spectrum = std::max(S->wide_per_spectrum, (double)nw / (double)C.n);
+            break;
+        }
+        if (attempt >= 2) return fail(SAGE_B200_ECUDA, "internal error: chunk re-run with exact work-list sizes did not fit");
+        // a work list was too small: the queries it could not hold reported no hits. Re-run the chunk with the sizes just counted.
+        C.force_nlist = need;
+        C.force_wide = nw;
+        S->last.chunk_retries++;
+        int rc;
+        if ((rc = chunk_run(S, L, L.dbg))) return rc;
+        if (L.downloading) {
+            S->last.d2h_bytes -= (uint64_t)C.n * S->sv.report_psms * sizeof(sage_b200_feature) + 4 * (uint64_t)C.n;
+            if ((rc = chunk_download(S, L, L.fdst, L.cdst))) return rc;
+        }
+    }
+    if (S->trace && L.ran && L.downloading) {
+        float t[8];
+        const int order[8] = {0, 1, 6, 2, 3, 4, 7, 5};
+        for (int i = 0; i < 8; i++) cudaEventElapsedTime(&t[i], S->ev_base, L.ev[order[i]]);
+        const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S->t_base).count();
+        float tm = 0;
+        cudaEventElapsedTime(&tm, S->ev_base, L.ev_masses);
+        fprintf(stderr, "[sage_b200 trace] chunk base=%u n=%u | host issue %.3f..%.3f, finished %.3f | dev h2d %.3f..(masses %.3f)..%.3f run %.3f setup-end %.3f prelim-end %.3f score-end %.3f d2h %.3f..%.3f\n",
+                C.base, C.n, C.t_issue0, C.t_issue1, now, t[0], tm, t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+    }
     sage_b200_counters& T = S->last;
     float ms;
     if (C.timed_upload) { cudaEventElapsedTime(&ms, L.ev[0], L.ev[1]); T.ms_h2d += ms; T.ms_total += ms; C.timed_upload = false; }
@@ -888,25 +963,34 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
     S->frag_cap = annotate ? fragment_capacity : 0;
     S->frag_used = 0;
     for (Lane& L : S->lanes) {   // a previous call may have failed half-way: make sure nothing is still queued on the lanes
+        CUDA_TRY(cudaStreamSynchronize(L.copy));
         CUDA_TRY(cudaStreamSynchronize(L.stream));
         L.chunk.loaded = false; L.ran = false; L.downloading = false;
     }
-    // Chunks are bounded by spectra and peak counts (device staging) and sized so that a large batch becomes ~pipeline_chunks chunks:
-    // two lanes alternate, so the H2D of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i.
+    if (S->trace) { S->t_base = std::chrono::steady_clock::now(); CUDA_TRY(cudaEventRecord(S->ev_base, S->lanes[0].stream)); }
     const uint64_t max_peaks = 1ull << 25;
-    // measured on cfg2 (50k spectra): 2 chunks of 25k beat 1, 4 and 6 (per-chunk launch/sync overhead vs exposed first H2D)
-    uint64_t target = (sp->n + (uint64_t)S->pipeline_chunks - 1) / (uint64_t)S->pipeline_chunks;
-    target = std::min<uint64_t>(std::max<uint64_t>(target, 8192), 32768);
+    // Chunks are as large as the staging bounds allow: on cfg2 one 50k chunk computes in 3.6 ms, two 25k chunks in 4.2 ms (the kernels process
+    // spectra in precursor order, so a denser chunk shares more index lines). Inside a chunk the intensities copy overlaps setup + preliminary
+    // scoring; across chunks (two lanes) the whole H2D of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i.
+    const uint64_t max_chunk = S->wide_per_spectrum > 0.0 ? 32768 : 65536;   // open search: one ~100 KB survivor list per query
+    // A short first chunk (first_chunk_pct of the batch, at most 16384 spectra) lets the kernels start while most of the H2D is still in flight.
+    uint64_t first = 0, rest = sp->n;
+    if (S->pipeline_chunks <= 1 && sp->n >= 16384) { first = std::min<uint64_t>(sp->n * (uint64_t)S->first_chunk_pct / 100, 16384); rest = sp->n - first; }
+    const uint64_t nchunks = std::max<uint64_t>((uint64_t)S->pipeline_chunks, (rest + max_chunk - 1) / max_chunk);
+    uint64_t target = (rest + nchunks - 1) / nchunks;
+    target = std::min<uint64_t>(std::max<uint64_t>(target, 1), max_chunk);
     uint64_t c0 = 0;
     int li = 0;
     while (c0 < sp->n) {
-        uint64_t c1 = std::min<uint64_t>(sp->n, c0 + target);
+        uint64_t c1 = std::min<uint64_t>(sp->n, c0 + (c0 == 0 && first ? first : target));
         while (c1 > c0 + 1 && sp->peak_offsets[c1] - sp->peak_offsets[c0] > max_peaks) c1 = c0 + (c1 - c0) / 2;
         Lane& L = S->lanes[li];
         if ((rc = lane_finish(S, L))) return rc;   // the chunk that used this lane two iterations ago
+        const double ti0 = S->trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S->t_base).count() : 0.0;
         if ((rc = chunk_upload(S, L, sp, c0, c1))) return rc;
         if ((rc = chunk_run(S, L, false))) return rc;
         if ((rc = chunk_download(S, L, features + c0 * S->sv.report_psms, counts + c0))) return rc;
+        if (S->trace) { L.chunk.t_issue0 = ti0; L.chunk.t_issue1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S->t_base).count(); }
         if (annotate && (rc = lane_finish(S, L))) return rc;   // fragment offsets are global: chunks run one after another
         c0 = c1;
         if (!annotate) li ^= 1;

@@ -59,6 +59,10 @@ def test_cfg2_sample_parity_and_properties(full):
     h1["spectrum"] += np.uint32(25_000)
     both, cb = np.concatenate([h0, h1]), np.concatenate([c0, c1])
     assert np.array_equal(cb, gc) and both[sel].tobytes() == gf[sel].tobytes()
+    # chunking invariance: the same batch cut into 3 pipelined chunks (two lanes alternate) gives the same bytes
+    sc.set_option("pipeline_chunks", 3)
+    g3, c3 = sc.score_batch(spectra)
+    assert np.array_equal(c3, gc) and g3[sel].tobytes() == gf[sel].tobytes()
 
 
 def test_cfg4_sample_parity(full):

@@ -304,3 +304,21 @@ def test_small_bucket_sizes():
         gdb = IndexedDatabase.build_from_peptides(pep, bucket_size=bs)
         run_both(odb, gdb, spectra, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20))
         run_both(odb, gdb, spectra.slice(0, 50), precursor_tol=Tolerance.da(-2000, 2000), fragment_tol=Tolerance.da(-0.5, 0.5))
+
+
+def test_worklist_undersized_chunk_is_rerun(small):
+    """Device work lists (narrow key-list arena, open-search item list) are sized from earlier chunks with no host round trip inside a
+    chunk; a chunk that needs more is re-run with the exact sizes it counted. Results must not depend on that."""
+    pep, odb, gdb, spectra = small
+    sub = spectra.slice(0, 400)
+    for kw in (dict(precursor_tol=Tolerance.da(-30.0, 30.0), fragment_tol=Tolerance.ppm(-20, 20)),        # narrow windows > k: arena in use
+               dict(precursor_tol=Tolerance.da(-800.0, 800.0), fragment_tol=Tolerance.ppm(-20, 20))):      # open search: wide item list
+        of, oc, _, _ = odb.score_batch(oracle_cfg(**kw), sub.as_dict())
+        sc = Scorer(gdb, **kw)
+        sc.set_option("worklist_reset", 0)
+        gf, gc = sc.score_batch(sub)
+        assert sc.counters()["chunk_retries"] >= 1
+        assert_features_equal(gf, gc, of, oc, 1, what="first batch (undersized work lists)")
+        gf, gc = sc.score_batch(sub)
+        assert sc.counters()["chunk_retries"] == 0   # sizes learned
+        assert_features_equal(gf, gc, of, oc, 1, what="second batch (learned sizes)")
