@@ -14,7 +14,12 @@ constexpr uint32_t NARROW_CAP = 8192; // precursor windows up to this many pepti
 constexpr int PRELIM_THREADS = 256;
 constexpr int SCORE_THREADS = 128;  // measured on cfg2: 128 (1.66 ms) beats 256 (1.95 ms) and 64 (1.75 ms); must stay >= K_MAX for the rank sort
 constexpr int MAX_KINDS = 6;
-constexpr uint32_t BUCKET_LUT_CELLS = 4096;
+// k_prelim_narrow_warp: measured on cfg2 (prelim ms): cap 1024 x 2 warps x 24 CTAs/SM 1.04 | cap 512 1.09 | cap 256 1.35 | cap 2048 1.60 (its
+// 192 KB of shared memory per SM leaves too little L1 for the index lines) | 4 warps 1.06 | 8 warps 1.08
+constexpr uint32_t WARPQ_CAP = 1024;       // precursor windows up to this many peptides are counted by one warp (u16 counts: 2 KB of smem per warp)
+constexpr int WARPQ_WARPS = 2;             // queries (warps) per CTA of k_prelim_narrow_warp
+constexpr int WARPQ_MIN_CTAS = 24;         // CTAs per SM the register budget is held to
+constexpr uint32_t BUCKET_LUT_CELLS = 32768;   // ~5 cells per page on a 2M-peptide index: the LUT start is within one page of the answer
 
 // mass.rs:5-8
 constexpr float PROTON = 1.0072764f;
@@ -153,7 +158,7 @@ struct ReplaySlot { unsigned long long off; uint32_t item, n_list, state /*0 = r
 
 // Device counters (u64 slots)
 enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_PEPQ, C_PEPFALLBACK, C_WSLOT, C_WOVERFLOW, C_FRAGS,
-       C_NLIST /* bump cursor of the narrow key-list arena */, C_NLIST_NEED /* arena entries this chunk needs (exact upper bound) */, C_COUNT };
+       C_NLIST /* bump cursor of the narrow key-list arena */, C_NCTA /* queries listed in cta_items */, C_NLIST_NEED /* arena entries this chunk needs (exact upper bound) */, C_COUNT };
 
 struct DbView {
     const uint2* frag;        // {peptide_index, fragment_mz bits}, reference bucket layout
@@ -218,6 +223,8 @@ struct BatchView {
     // Device-side work lists sized from what earlier chunks needed (no host round trip inside a chunk): when a capacity turns out too
     // small the affected queries produce no hits, the host sees need > capacity in the counters and re-runs the chunk with exact sizes.
     uint32_t* wide_items;             // compacted item ids of the open-search (mode 2) queries, wide_cap entries
+    uint32_t* cta_items;              // compacted item ids of the narrow queries counted by a whole CTA (modes 1 and 3), n * qmax entries
+    ReplaySlot* nslots;               // one per item (narrow kernels); k_setup_queries resets them to "nothing to replay"
     uint32_t wide_cap;
     unsigned long long nlist_cap;     // entries in the narrow key-list arena
 };

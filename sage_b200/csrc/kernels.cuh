@@ -28,7 +28,7 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
     uint32_t c1 = fold ? sc.max_charge : known;
     QueryDesc* out = b.queries + (size_t)s * sc.qmax;
     uint32_t qi = 0;
-    unsigned long long nq = 0, nwide = 0, maxpot = 0, npepq = 0, list_need = 0;
+    unsigned long long nq = 0, nwide = 0, maxpot = 0, npepq = 0, list_need = 0, ncta = 0;
     for (uint32_t z = c0; z <= c1 && qi < sc.qmax; z++) {
         const float precursor_mass = __fmul_rn(mz, (float)z);
         Tol ptol = sc.precursor_tol;
@@ -62,9 +62,12 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
             q.charge = (uint8_t)z;
             q.iso = (int8_t)iso;
             q.nfc = (uint8_t)(mfc - 1);
-            q.mode = q.potential > NARROW_CAP ? 2 : ((db.pep_centric_ok && q.potential <= sc.pep_cap) ? 3 : 1);
+            // 2 = open search (k_prelim_wide), 3 = peptide-centric CTA, 4 = one warp per query (k_prelim_narrow_warp), 1 = one CTA per query
+            q.mode = q.potential > NARROW_CAP ? 2 : ((db.pep_centric_ok && q.potential <= sc.pep_cap) ? 3 : (q.potential <= WARPQ_CAP ? 4 : 1));
             out[qi] = q;
             if (q.mode != 2 && q.potential > sc.kparam) list_need += q.potential;   // k_prelim_narrow reserves exactly this much of the arena
+            if (q.mode == 4) b.counters[C_COUNT + qi] = 1ull;   // query slot qi is in use by some warp-counted query (benign race: everybody stores 1)
+            ncta += (q.mode == 1 || q.mode == 3);
             nq++;
             if (q.mode == 2) {   // "no hits" until k_prelim_wide gets to it (it may not, when wide_cap is too small: the host then re-runs the chunk)
                 nwide++;
@@ -85,6 +88,15 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
         unsigned long long w = atomicAdd(b.counters + C_WIDE, nwide);
         for (uint32_t j = 0; j < sc.qmax; j++)
             if (out[j].mode == 2) { if (w < b.wide_cap) b.wide_items[w] = s * sc.qmax + j; w++; }
+    }
+    if (ncta) {
+        unsigned long long w = atomicAdd(b.counters + C_NCTA, ncta);
+        for (uint32_t j = 0; j < sc.qmax; j++)
+            if (out[j].mode == 1 || out[j].mode == 3) b.cta_items[w++] = s * sc.qmax + j;
+    }
+    for (uint32_t j = 0; j < sc.qmax; j++) {
+        ReplaySlot rs; rs.off = 0; rs.item = s * sc.qmax + j; rs.n_list = 0; rs.state = 1; rs.k = 0;
+        b.nslots[(size_t)s * sc.qmax + j] = rs;
     }
     if (list_need) atomicAdd(b.counters + C_NLIST_NEED, list_need);
     if (npepq) atomicAdd(b.counters + C_PEPQ, npepq);
@@ -152,12 +164,22 @@ __device__ __forceinline__ void bucket_range(const DbView& db, float flo, float 
     // bucket_min holds positive finite m/z values, so float compares equal total_cmp here
     const float t = (flo - db.blut_base) * db.blut_inv_w;
     const int c = t > 1.0f ? (int)fminf(t, (float)(BUCKET_LUT_CELLS - 1)) - 1 : 0;
-    uint32_t pp = __ldg(db.bucket_lut + c);                               // <= partition_point(min < flo)
+    const uint32_t pp0 = __ldg(db.bucket_lut + c);                        // <= partition_point(min < flo)
+    uint32_t pp = pp0;
     while (pp < db.n_bucket && __ldg(db.bucket_min + pp) < flo) pp++;
     left = pp == 0 ? 0 : pp - 1;
     uint32_t r = left;
     while (r < db.n_bucket && __ldg(db.bucket_min + r) <= fhi) r++;
     right = r;
+}
+
+// lower_bound over the PeptideIx column of a page sub-range: first e in [lo, hi) with slice[e].x >= key
+__device__ __forceinline__ uint32_t page_lower_bound(const uint2* slice, uint32_t lo, uint32_t hi, uint32_t key) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(&slice[mid].x) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
 }
 
 // partition_point(|e| e.peptide_index < key) inside one page; uses the per-page PeptideIx grid when built.
@@ -176,6 +198,36 @@ __device__ __forceinline__ uint32_t page_lower_bound_dir(const DbView& db, uint3
     return lo;
 }
 
+// One (peak, fragment charge) probe of matched_peaks_with_isotope (scoring.rs:358-374) against the fragment index: pages from the
+// bucket minima, per page the PeptideIx window (grid cell + short binary search, then the forward walk that ends exactly at
+// inner_right, database.rs:506-511), exact filter (database.rs:514-534), shared-memory count increment (u16 pairs in cnt32).
+__device__ __forceinline__ void index_probe(const DbView& db, const QueryDesc& q, float flo, float fhi, uint32_t* cnt32, uint32_t& matched, uint32_t& pages,
+                                            uint32_t& entries) {
+    uint32_t bl, br;
+    bucket_range(db, flo, fhi, bl, br);
+    for (uint32_t page = bl; page < br; page++) {
+        const uint64_t pbase = (uint64_t)page * db.bucket_size;
+        const uint64_t pend = min(pbase + db.bucket_size, db.n_frag);
+        const uint2* slice = db.frag + pbase;
+        const uint32_t pn = (uint32_t)(pend - pbase);
+        const uint32_t pp = page_lower_bound_dir(db, page, slice, pn, q.pre_lo);
+        const uint32_t il = pp == 0 ? 0 : pp - 1;   // inner_left = partition_point(pep < pre_lo).saturating_sub(1)
+        uint32_t e = il;
+        for (; e < pn; e++) {
+            const uint2 f = __ldg(&slice[e]);
+            if (f.x > q.pre_hi) break;
+            const float fmz = __uint_as_float(f.y);
+            if (f.x >= q.eff_lo && f.x <= q.eff_hi && fmz >= flo && fmz <= fhi) {
+                const uint32_t idx = f.x - q.pre_lo;
+                atomicAdd(&cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                matched++;
+            }
+        }
+        pages++;
+        entries += e - il;
+    }
+}
+
 // ------------------------------------------------------------------------------------- preliminary scoring, narrow
 // One CTA per (spectrum, query); the dense per-window counts live in shared memory. Two interchangeable ways to fill them
 // (identical counts: the matched set is {fragment in index : mz in [flo,fhi](peak*charge), PeptideIx in [eff_lo,eff_hi]}):
@@ -187,19 +239,13 @@ __device__ __forceinline__ uint32_t page_lower_bound_dir(const DbView& db, uint3
 //    interval contains its fragment with two binary searches over per-charge LO/HI bound arrays staged in shared memory
 //    (bounds computed with the reference's f32 ops; both arrays are monotone in the peak mass, which is verified per
 //    spectrum — otherwise the CTA falls back to the index path).
-__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b, uint32_t pmax, uint64_t* nlist,
-                                                                  ReplaySlot* nslots) {
+__device__ __forceinline__ void narrow_cta_query(const DbView& db, const ScorerView& sc, const BatchView& b, uint32_t pmax, uint64_t* nlist, uint32_t item,
+                                                 float* bounds_smem) {
     __shared__ uint32_t cnt32[NARROW_CAP / 2 + 1];
     __shared__ uint32_t s_warp[40];
-    extern __shared__ float bounds_smem[];  // LO[nfc][np] then HI[nfc][np] (peptide-centric path only)
-
-    const uint32_t s = b.order ? b.order[blockIdx.x / sc.qmax] : blockIdx.x / sc.qmax;
-    const uint32_t item = s * sc.qmax + blockIdx.x % sc.qmax;
+    ReplaySlot* const nslots = b.nslots;
+    const uint32_t s = item / sc.qmax;
     const QueryDesc q = b.queries[item];
-    if (q.mode != 1 && q.mode != 3) {
-        if (threadIdx.x == 0) { nslots[item].off = 0; nslots[item].item = item; nslots[item].n_list = 0; nslots[item].state = 1; nslots[item].k = 0; }
-        return;
-    }
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = PRELIM_THREADS / 32;
     const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
     const uint32_t nwords = (q.potential + 1) >> 1;
@@ -294,37 +340,26 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
             const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
             float flo, fhi;
             tol_bounds(sc.fragment_tol, mass, flo, fhi);
-            uint32_t bl, br;
-            bucket_range(db, flo, fhi, bl, br);
-            for (uint32_t page = bl; page < br; page++) {
-                const uint64_t pbase = (uint64_t)page * db.bucket_size;
-                const uint64_t pend = min(pbase + db.bucket_size, db.n_frag);
-                const uint2* slice = db.frag + pbase;
-                const uint32_t pn = (uint32_t)(pend - pbase);
-                // inner_left = partition_point(pep < pre_lo).saturating_sub(1); then walk forward: the walk ends exactly at
-                // inner_right = inner_left + partition_point(pep <= pre_hi) (database.rs:506-511), no second search needed
-                const uint32_t pp = page_lower_bound_dir(db, page, slice, pn, q.pre_lo);
-                const uint32_t il = pp == 0 ? 0 : pp - 1;
-                uint32_t e = il;
-                for (; e < pn; e++) {
-                    const uint2 f = __ldg(&slice[e]);
-                    if (f.x > q.pre_hi) break;
-                    const float fmz = __uint_as_float(f.y);
-                    if (f.x >= q.eff_lo && f.x <= q.eff_hi && fmz >= flo && fmz <= fhi) {
-                        const uint32_t idx = f.x - q.pre_lo;
-                        atomicAdd(&cnt32[idx >> 1], 1u << ((idx & 1) * 16));
-                        my_matched++;
-                    }
-                }
-                my_pages++;
-                my_entries += e - il;
-            }
+            index_probe(db, q, flo, fhi, cnt32, my_matched, my_pages, my_entries);
         }
     }
-    const uint32_t matched_total = block_sum_u32(my_matched, s_warp);
-    const uint32_t pages_total = block_sum_u32(my_pages, s_warp);
-    const uint32_t entries_total = block_sum_u32(my_entries, s_warp);
+    // one block reduction for the three per-CTA sums (matched is needed by every thread, the work counters by thread 0 only)
+    __shared__ uint32_t s_red[3][PRELIM_THREADS / 32];
+    {
+        uint32_t a = my_matched, p = my_pages, en = my_entries;
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            p += __shfl_down_sync(0xffffffffu, p, o);
+            en += __shfl_down_sync(0xffffffffu, en, o);
+        }
+        if (lane == 0) { s_red[0][warp] = a; s_red[1][warp] = p; s_red[2][warp] = en; }
+    }
+    __syncthreads();
+    uint32_t matched_total = 0;
+    for (uint32_t w = 0; w < nwarps; w++) matched_total += s_red[0][w];
     if (tid == 0) {
+        uint32_t pages_total = 0, entries_total = 0;
+        for (uint32_t w = 0; w < nwarps; w++) { pages_total += s_red[1][w]; entries_total += s_red[2][w]; }
         atomicAdd(b.counters + C_TASKS, (unsigned long long)ntask);
         if (pages_total) atomicAdd(b.counters + C_PAGES, (unsigned long long)pages_total);
         if (entries_total) atomicAdd(b.counters + C_ENTRIES, (unsigned long long)entries_total);
@@ -397,6 +432,97 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
     }
 }
 
+// Queries counted by a whole CTA (windows of WARPQ_CAP+1..NARROW_CAP peptides, and the peptide-centric path): a fixed-size grid walks the
+// compacted list k_setup_queries wrote.
+__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b, uint32_t pmax, uint64_t* nlist) {
+    extern __shared__ float bounds_smem[];  // LO[nfc][np] then HI[nfc][np] (peptide-centric path only)
+    const uint32_t total = (uint32_t)min(b.counters[C_NCTA], (unsigned long long)b.n * sc.qmax);
+    for (uint32_t i = blockIdx.x; i < total; i += gridDim.x) {
+        narrow_cta_query(db, sc, b, pmax, nlist, b.cta_items[i], bounds_smem);
+        __syncthreads();   // shared arrays are reused by the next query
+    }
+}
+
+// One WARP per (spectrum, query) for windows of at most WARPQ_CAP peptides — the common case of a narrow search. The index path of
+// narrow_cta_query without any block-wide barrier: each lane owns (peak, fragment charge) probes t = lane, lane + 32, ..., the dense u16
+// counts of the window live in the warp's slice of shared memory, sums are warp shuffles, and the ordered key list for k_replay
+// is emitted with ballots. grid = (ceil(n / WARPQ_WARPS) in precursor order, query slot): slot-major, so CTAs of slots no spectrum uses
+// (e.g. the charge fold of known-charge spectra) sit at the end of the grid and leave after one cached load.
+__global__ void __launch_bounds__(WARPQ_WARPS * 32, WARPQ_MIN_CTAS) k_prelim_narrow_warp(DbView db, ScorerView sc, BatchView b, uint64_t* nlist) {
+    __shared__ uint32_t cnt_all[WARPQ_WARPS][WARPQ_CAP / 2];
+    if (b.counters[C_COUNT + blockIdx.y] == 0ull) return;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t pos = blockIdx.x * WARPQ_WARPS + warp;
+    if (pos >= b.n) return;
+    const uint32_t s = b.order ? b.order[pos] : pos;
+    const uint32_t item = s * sc.qmax + blockIdx.y;
+    const QueryDesc q = b.queries[item];
+    if (q.mode != 4) return;
+    uint32_t* const cnt32 = cnt_all[warp];
+    const uint32_t n = q.potential, k = min(n, sc.kparam);
+    for (uint32_t i = lane; i < (n + 1) >> 1; i += 32) cnt32[i] = 0;
+    unsigned long long loff = 0;
+    if (n > k) {   // key-list space for the trim, bump-allocated from the chunk's arena
+        if (lane == 0) loff = atomicAdd(b.counters + C_NLIST, (unsigned long long)n);
+        loff = __shfl_sync(0xffffffffu, loff, 0);
+    }
+    __syncwarp();
+    const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
+    const uint32_t nfc = q.nfc, ntask = np * nfc;
+    uint32_t matched = 0, pages = 0, entries = 0;
+    for (uint32_t t = lane; t < ntask; t += 32) {
+        const uint32_t p = t / nfc, fc = t - p * nfc + 1;
+        const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
+        float flo, fhi;
+        tol_bounds(sc.fragment_tol, mass, flo, fhi);
+        index_probe(db, q, flo, fhi, cnt32, matched, pages, entries);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        matched += __shfl_xor_sync(0xffffffffu, matched, o);
+        pages += __shfl_xor_sync(0xffffffffu, pages, o);
+        entries += __shfl_xor_sync(0xffffffffu, entries, o);
+    }
+    __syncwarp();   // all shared-memory increments of the warp are visible below
+    if (lane == 0) {
+        atomicAdd(b.counters + C_TASKS, (unsigned long long)ntask);
+        if (pages) atomicAdd(b.counters + C_PAGES, (unsigned long long)pages);
+        if (entries) atomicAdd(b.counters + C_ENTRIES, (unsigned long long)entries);
+        if (matched) atomicAdd(b.counters + C_MATCHED, (unsigned long long)matched);
+    }
+    QueryHits* h = b.hits + item;
+    ReplaySlot* slot = b.nslots + item;   // preset by k_setup_queries to "nothing to replay"
+    if (matched == 0 || (n > k && loff + n > b.nlist_cap)) {
+        // scoring.rs:376-378 returns the untrimmed all-default Vec; or the arena is too small (the host sees C_NLIST_NEED > capacity
+        // and re-runs the chunk): leave "no hits"
+        if (lane == 0) { h->n = 0; h->default_run = n; h->matched_peaks = 0; h->scored_candidates = 0; }
+        return;
+    }
+    // trim_hits (scoring.rs:322-329), stage 1: the keys in dense order — the literal first k slots, then every later slot with
+    // matched > 0 (zeros can never displace the heap root). k_replay performs the exact heap replay, one thread per query.
+    auto cnt = [&](uint32_t i) -> uint32_t { return (cnt32[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu; };
+    uint32_t nzc = 0;
+    uint64_t* dst = n <= k ? b.hit_keys + (size_t)item * sc.kparam : nlist + loff;   // n <= k: nothing to trim, the dense order is the result
+    for (uint32_t i = lane; i < k; i += 32) {
+        const uint32_t c = cnt(i);
+        nzc += c != 0;
+        dst[i] = c ? prescore_key(c, q.pre_lo + i, q.charge, q.iso) : PRESCORE_DEFAULT;
+    }
+    uint32_t wbase = k;
+    for (uint32_t base = k; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t c = i < n ? cnt(i) : 0;
+        nzc += c != 0;
+        const uint32_t ball = __ballot_sync(0xffffffffu, c != 0);
+        if (c) dst[wbase + __popc(ball & ((1u << lane) - 1))] = prescore_key(c, q.pre_lo + i, q.charge, q.iso);
+        wbase += __popc(ball);
+    }
+    for (int o = 16; o > 0; o >>= 1) nzc += __shfl_xor_sync(0xffffffffu, nzc, o);
+    if (lane == 0) {
+        h->n = k; h->default_run = 0; h->matched_peaks = matched; h->scored_candidates = nzc;
+        if (n > k) { slot->off = loff; slot->n_list = wbase; slot->state = 0; slot->k = k; }
+    }
+}
+
 // --------------------------------------------------------------------------------------- preliminary scoring, wide
 // Open-search windows (> NARROW_CAP peptides; ±500 Da spans ~40 % of a human index) make the dense count array megabytes long.
 // Instead of a global scratch + L2/DRAM atomics, the window is processed in TILES of WIDE_TILE consecutive PeptideIx whose u16
@@ -437,14 +563,6 @@ struct WideSmem {
     uint32_t s_item, s_slot, s_level, s_listn, s_serial, s_nranges, s_nvis, s_fast;
 };
 
-// lower_bound over the PeptideIx column of a page sub-range: first e in [lo, hi) with slice[e].x >= key
-__device__ __forceinline__ uint32_t page_lower_bound(const uint2* slice, uint32_t lo, uint32_t hi, uint32_t key) {
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (__ldg(&slice[mid].x) < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
 
 __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, ScorerView sc, BatchView b, uint32_t n_items, uint64_t* wlist,
                                                                    WideSlot* wslots) {
@@ -877,11 +995,15 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
 // Heaps live in shared memory, interleaved by thread. Used by both preliminary-scoring kernels.
 constexpr int REPLAY_THREADS = 128;
 __global__ void __launch_bounds__(REPLAY_THREADS) k_replay(ScorerView sc, BatchView b, const uint64_t* lists, const ReplaySlot* slots, uint32_t n_slots,
-                                                           const unsigned long long* n_slots_dev) {
+                                                           const unsigned long long* n_slots_dev, uint32_t n_spectra) {
     extern __shared__ uint64_t rheap[];  // [kparam][REPLAY_THREADS]
-    const uint32_t slot = blockIdx.x * REPLAY_THREADS + threadIdx.x;
+    uint32_t slot = blockIdx.x * REPLAY_THREADS + threadIdx.x;
     if (n_slots_dev != nullptr) n_slots = (uint32_t)min((unsigned long long)n_slots, *n_slots_dev);   // slots actually filled (device-side count)
     if (slot >= n_slots) return;
+    // per-item slots (narrow kernels): walk them query-slot-major, so the lanes of a warp hold queries of the same slot — with known-charge
+    // spectra only slot 0 has work, and item-major order would leave two lanes in three idle
+    // (and in precursor order: neighbouring windows have similar sizes, so the lanes of a warp replay lists of similar length)
+    if (n_spectra) { const uint32_t pos = slot % n_spectra; slot = (b.order ? b.order[pos] : pos) * sc.qmax + slot / n_spectra; }
     const ReplaySlot ws = slots[slot];
     if (ws.state != 0) return;
     const uint64_t* list = lists + ws.off;

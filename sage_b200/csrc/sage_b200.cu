@@ -458,7 +458,7 @@ struct Lane {
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_masses = nullptr, ev_intens = nullptr;
     DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_dbgk, d_dbgm, d_sort, d_sorttmp, d_wlist, d_wslots,
-        d_witems, d_nlist, d_nslots;
+        d_witems, d_citems, d_nlist, d_nslots;
     PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
     DevBuf d_frags;
     ChunkState chunk;
@@ -470,7 +470,7 @@ struct Lane {
     bool f_pinned = false, c_pinned = false;
     void release() {
         for (DevBuf* b : {&d_small, &d_masses, &d_intens, &d_queries, &d_hits, &d_keys, &d_features, &d_counts, &d_counters, &d_dbgk, &d_dbgm, &d_sort, &d_sorttmp,
-                          &d_wlist, &d_wslots, &d_witems, &d_nlist, &d_nslots, &d_frags}) b->release();
+                          &d_wlist, &d_wslots, &d_witems, &d_citems, &d_nlist, &d_nslots, &d_frags}) b->release();
         for (PinBuf* b : {&h_small, &h_masses, &h_intens, &h_features, &h_counts, &h_counters}) b->release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (ev_masses) cudaEventDestroy(ev_masses);
@@ -687,7 +687,7 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
         if ((r = L.d_keys.reserve(C.nitems * sv.kparam * 8))) return r;
         if ((r = L.d_features.reserve((size_t)n * sv.report_psms * sizeof(FeatureOut)))) return r;
         if ((r = L.d_counts.reserve(4 * (size_t)n))) return r;
-        if ((r = L.d_counters.reserve(8 * C_COUNT))) return r;
+        if ((r = L.d_counters.reserve(8 * (C_COUNT + (size_t)sv.qmax)))) return r;   // + one in-use flag per query slot
         if ((r = L.h_counters.reserve(8 * C_COUNT + 32))) return r;
         if (npk && !is_pinned(src_i)) {
             if ((r = L.h_intens.reserve(4 * npk))) return r;
@@ -750,7 +750,7 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     CUDA_TRY(cudaStreamWaitEvent(st, S->lanes[(&L - S->lanes) ^ 1].ev[4], 0));
     CUDA_TRY(cudaStreamWaitEvent(st, L.ev_masses, 0));
     CUDA_TRY(cudaEventRecord(L.ev[6], st));
-    CUDA_TRY(cudaMemsetAsync(L.d_counters.p, 0, 8 * C_COUNT, st));
+    CUDA_TRY(cudaMemsetAsync(L.d_counters.p, 0, 8 * (C_COUNT + (size_t)sv.qmax), st));
     const bool annotate = sv.annotate && S->frag_dst != nullptr;
     if (annotate) {   // fragment offsets are global across the chunks of one call: start this chunk's counter at what was used so far
         if ((rc = L.d_frags.reserve(S->frag_cap * sizeof(sage_b200_fragment) + 64))) return rc;
@@ -787,6 +787,9 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
         if ((rc = L.d_wlist.reserve((size_t)C.wide_cap * WIDE_LMAX * 8))) return rc;
         if ((rc = L.d_wslots.reserve((size_t)C.wide_cap * sizeof(WideSlot)))) return rc;
     }
+    if ((rc = L.d_citems.reserve(4 * C.nitems))) return rc;
+    bv.cta_items = L.d_citems.as<uint32_t>();
+    bv.nslots = L.d_nslots.as<ReplaySlot>();
     bv.wide_items = L.d_witems.as<uint32_t>();
     bv.wide_cap = C.wide_cap;
     bv.nlist_cap = C.nlist_cap;
@@ -802,19 +805,21 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     // ---- preliminary scoring. Both kernels are always queued: CTAs whose query belongs to the other kernel (or to nobody) exit at once.
     const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
     CUDA_TRY(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-    k_prelim_narrow<<<(unsigned)C.nitems, PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>(), L.d_nslots.as<ReplaySlot>());
+    k_prelim_narrow_warp<<<dim3((n + WARPQ_WARPS - 1) / WARPQ_WARPS, sv.qmax), WARPQ_WARPS * 32, 0, st>>>(db->v, svq, bv, L.d_nlist.as<uint64_t>());
+    CUDA_TRY(cudaGetLastError());
+    k_prelim_narrow<<<(unsigned)std::min<uint64_t>(C.nitems, (uint64_t)db->sm_count * 6), PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>());
     CUDA_TRY(cudaGetLastError());
     k_replay<<<(unsigned)((C.nitems + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, L.d_nlist.as<uint64_t>(), L.d_nslots.as<ReplaySlot>(),
-                                                                                                       (uint32_t)C.nitems, nullptr);
+                                                                                                       (uint32_t)C.nitems, nullptr, n);
     CUDA_TRY(cudaGetLastError());
-    launches += 2;
+    launches += 3;
     if (C.wide_cap) {
         const int ctas = (int)std::min<uint64_t>((uint64_t)db->sm_count, C.wide_cap);
         CUDA_TRY(cudaFuncSetAttribute(k_prelim_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WideSmem)));
         k_prelim_wide<<<ctas, WIDE_THREADS, sizeof(WideSmem), st>>>(db->v, sv, bv, (uint32_t)C.nitems, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>());
         CUDA_TRY(cudaGetLastError());
         k_replay<<<(unsigned)((C.wide_cap + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(
-            sv, bv, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>(), C.wide_cap, L.d_counters.as<unsigned long long>() + C_WIDE);
+            sv, bv, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>(), C.wide_cap, L.d_counters.as<unsigned long long>() + C_WIDE, 0u);
         CUDA_TRY(cudaGetLastError());
         launches += 2;
     }
