@@ -33,14 +33,26 @@ __device__ __forceinline__ int f32_key(float x) {
     return b ^ (int)(((unsigned)(b >> 31)) >> 1);
 }
 
+// x / c, correctly rounded, for the two constants of Tolerance::bounds (1e6, 100): q0 = x * rn(1/c), one FMA for the exact residual, one FMA
+// to correct. Bit-identical to IEEE division for EVERY float with 1e-20 <= |x| <= 1e30 (exhaustively checked against x / c on the CPU by
+// tests/test_div_const.py: 1.39e9 values per constant); anything outside that range takes the real division.
+__device__ __forceinline__ float div_const_rn(float x, float c, float rc) {
+    const float ax = fabsf(x);
+    if (ax >= 1e-20f && ax <= 1e30f) {
+        const float q0 = __fmul_rn(x, rc);
+        return __fmaf_rn(__fmaf_rn(-q0, c, x), rc, q0);
+    }
+    return __fdiv_rn(x, c);
+}
+
 // Tolerance::bounds (mass.rs:21-35)
 __device__ __forceinline__ void tol_bounds(const Tol& t, float c, float& lo, float& hi) {
     if (t.kind == 0) {
-        lo = __fadd_rn(c, __fdiv_rn(__fmul_rn(c, t.lo), 1000000.0f));
-        hi = __fadd_rn(c, __fdiv_rn(__fmul_rn(c, t.hi), 1000000.0f));
+        lo = __fadd_rn(c, div_const_rn(__fmul_rn(c, t.lo), 1000000.0f, 1.0f / 1000000.0f));
+        hi = __fadd_rn(c, div_const_rn(__fmul_rn(c, t.hi), 1000000.0f, 1.0f / 1000000.0f));
     } else if (t.kind == 1) {
-        lo = __fadd_rn(c, __fdiv_rn(__fmul_rn(c, t.lo), 100.0f));
-        hi = __fadd_rn(c, __fdiv_rn(__fmul_rn(c, t.hi), 100.0f));
+        lo = __fadd_rn(c, div_const_rn(__fmul_rn(c, t.lo), 100.0f, 1.0f / 100.0f));
+        hi = __fadd_rn(c, div_const_rn(__fmul_rn(c, t.hi), 100.0f, 1.0f / 100.0f));
     } else {
         lo = __fadd_rn(c, t.lo);
         hi = __fadd_rn(c, t.hi);

@@ -146,6 +146,28 @@ __device__ __forceinline__ void lut_build(const float* arr, uint32_t n, const Lu
         start[c] = (uint16_t)lo;
     }
 }
+// Same table for an ASCENDING array in O(cells + n): with cell(m) = max{c : c == 0 or edge(c) <= m}, arr[i] < edge(c) <=> cell(arr[i]) < c
+// (edges are monotone in c), so start[c] = first i with cell(arr[i]) >= c: element j fills the cells in (cell(arr[j-1]), cell(arr[j])].
+__device__ __forceinline__ void lut_build_sorted(const float* arr, uint32_t n, const LutParams& L, uint16_t* start, uint32_t t0, uint32_t stride,
+                                                 uint32_t cells) {
+    if (!(L.inv_w > 0.0f)) {
+        for (uint32_t c = t0; c < cells; c += stride) start[c] = 0;
+        return;
+    }
+    const float w = 1.0f / L.inv_w;   // lut_edge(L, c) == L.base + (float)c * w
+    auto cell_of = [&](float m) -> int {
+        const float t = (m - L.base) * L.inv_w;
+        int c = t > 0.0f ? (int)fminf(t, (float)(cells - 1)) : 0;
+        while (c + 1 < (int)cells && L.base + (float)(c + 1) * w <= m) c++;
+        while (c > 0 && L.base + (float)c * w > m) c--;
+        return c;
+    };
+    for (uint32_t j = t0; j <= n; j += stride) {
+        const int c_prev = j == 0 ? -1 : cell_of(arr[j - 1]);
+        const int c_here = j == n ? (int)cells - 1 : cell_of(arr[j]);
+        for (int c = c_prev + 1; c <= c_here; c++) start[c] = (uint16_t)j;
+    }
+}
 // A position s with arr[i] < x for all i < s (conservative: one cell early to absorb float rounding of the cell index).
 __device__ __forceinline__ uint32_t lut_start(const LutParams& L, const uint16_t* start, float x, uint32_t cells = LUT_CELLS) {
     const float t = (x - L.base) * L.inv_w;
@@ -1152,7 +1174,9 @@ __device__ __forceinline__ void score_candidate_warp(const DbView& db, const Sco
             idx = ki;
             while (idx >= nions) { idx -= nions; kind_i++; }   // <= n_kinds - 1 iterations
             is_n = (db.nterm_mask >> kind_i) & 1;
-            const float mz = __fdiv_rn(__ldg(ions + ki), (float)fc);  // scoring.rs:707   (ions[kind_i * nions + idx] == ions[ki])
+            // scoring.rs:707 fragment / charge (ions[kind_i * nions + idx] == ions[ki]): x / 1 and x / 2 are exact as x and x * 0.5 (|x| >= 2^-125)
+            const float ion = __ldg(ions + ki);
+            const float mz = fc == 1 ? ion : (fc == 2 && fabsf(ion) >= 1e-30f) ? __fmul_rn(ion, 0.5f) : __fdiv_rn(ion, (float)fc);
             pk = sp.use_lut ? select_most_intense_peak_lut(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol, sp.lp, sp.lut)
                             : select_most_intense_peak(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol);
             if (pk >= 0 && mark == nullptr) {
@@ -1288,7 +1312,7 @@ __device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t
     }
     if (__syncthreads_or(bad)) return false;
     lp = lut_params(masses[0], masses[np - 1], SPEC_LUT_CELLS);
-    lut_build(masses, np, lp, lut, threadIdx.x, blockDim.x, SPEC_LUT_CELLS);
+    lut_build_sorted(masses, np, lp, lut, threadIdx.x, blockDim.x, SPEC_LUT_CELLS);   // masses verified ascending above
     __syncthreads();
     return true;
 }
