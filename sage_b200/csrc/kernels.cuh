@@ -187,11 +187,28 @@ __device__ __forceinline__ void bucket_range(const DbView& db, float flo, float 
     const float t = (flo - db.blut_base) * db.blut_inv_w;
     const int c = t > 1.0f ? (int)fminf(t, (float)(BUCKET_LUT_CELLS - 1)) - 1 : 0;
     const uint32_t pp0 = __ldg(db.bucket_lut + c);                        // <= partition_point(min < flo)
+    // partition_point(min < flo): the element that stops the scan is min[pp] itself, and (for flo <= fhi) min[pp - 1] < flo <= fhi needs
+    // no second look, so the scan for `right` resumes at pp with the value already in hand
     uint32_t pp = pp0;
-    while (pp < db.n_bucket && __ldg(db.bucket_min + pp) < flo) pp++;
+    float v = 0.0f;
+    bool have = false;
+    while (pp < db.n_bucket) {
+        v = __ldg(db.bucket_min + pp);
+        if (!(v < flo)) { have = true; break; }
+        pp++;
+    }
     left = pp == 0 ? 0 : pp - 1;
-    uint32_t r = left;
-    while (r < db.n_bucket && __ldg(db.bucket_min + r) <= fhi) r++;
+    uint32_t r;
+    if (pp > 0 && flo <= fhi) {
+        r = pp;
+        if (have && v <= fhi) {
+            r++;
+            while (r < db.n_bucket && __ldg(db.bucket_min + r) <= fhi) r++;
+        }
+    } else {
+        r = left;
+        while (r < db.n_bucket && __ldg(db.bucket_min + r) <= fhi) r++;
+    }
     right = r;
 }
 
@@ -1031,21 +1048,29 @@ __global__ void __launch_bounds__(REPLAY_THREADS) k_replay(ScorerView sc, BatchV
     const uint64_t* list = lists + ws.off;
     const uint32_t k = ws.k, tid = threadIdx.x;
     auto H = [&](uint32_t i) -> uint64_t& { return rheap[i * REPLAY_THREADS + tid]; };
-    auto sift = [&](uint32_t index) {
-        while (index * 2 + 1 < k) {
-            uint32_t smallest = index, l = index * 2 + 1, r = index * 2 + 2;
-            if (H(l) < H(smallest)) smallest = l;
-            if (r < k && H(r) < H(smallest)) smallest = r;
-            if (smallest != index) { const uint64_t t = H(smallest); H(smallest) = H(index); H(index) = t; index = smallest; }
-            else break;
+    // sift_down (heap.rs:31-60) of `val` from `index`, written with a hole: children smaller than val move up, val lands where the swaps
+    // of the reference would have carried it (same path: the smaller child, the left one on ties, and only if it is < val)
+    auto sift = [&](uint32_t index, uint64_t val) {
+        for (;;) {
+            const uint32_t l = index * 2 + 1;
+            if (l >= k) break;
+            uint32_t c = l;
+            uint64_t cv = H(l);
+            if (l + 1 < k) { const uint64_t cr = H(l + 1); if (cr < cv) { cv = cr; c = l + 1; } }
+            if (!(cv < val)) break;
+            H(index) = cv;
+            index = c;
         }
+        H(index) = val;
     };
     for (uint32_t i = 0; i < k; i++) H(i) = __ldg(list + i);
-    for (uint32_t i = k / 2; i-- > 0;) sift(i);
+    for (uint32_t i = k / 2; i-- > 0;) sift(i, H(i));
     uint64_t root = H(0);
+    uint64_t nxt = k < ws.n_list ? __ldg(list + k) : 0;
     for (uint32_t j = k; j < ws.n_list; j++) {
-        const uint64_t kq = __ldg(list + j);
-        if (kq > root) { H(0) = kq; sift(0); root = H(0); }
+        const uint64_t kq = nxt;
+        if (j + 1 < ws.n_list) nxt = __ldg(list + j + 1);   // in flight while the heap is updated
+        if (kq > root) { sift(0, kq); root = H(0); }
     }
     uint64_t* keys = b.hit_keys + (size_t)ws.item * sc.kparam;
     for (uint32_t i = 0; i < k; i++) keys[i] = H(i);
