@@ -12,7 +12,8 @@ fixed (weak scaling: every rank scores its own 50k spectra against a replicated 
              events on the launching stream (sage_b200_batch_run), max over ranks.
   e2e        spectra/s through the C-ABI call sage_b200_score_batch with pinned HOST buffers: H2D of the spectra and D2H of the
              Feature rows inside the timed region.
-  roofline   dominant kernel (preliminary scoring): algorithmic bytes / CUDA-event duration vs measured HBM peak.
+  roofline   the kernel that takes longest in a step (k_score on cfg2, k_prelim_wide on cfg4): its share of the SURVEY.md §8d algorithmic bytes /
+             its CUDA-event duration vs the measured HBM peak; `kernels` lists the same for every kernel of the step, `step` for the whole step.
   cpu_baseline  the CPU oracle (bit-faithful port of sage-core's path; OpenMP over spectra) on this box's host cores.
 """
 import argparse
@@ -118,12 +119,12 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def committed_traffic(workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+def committed_traffic(workload, kernel):
+    """dram bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture (profiles/traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload)
+            return (json.load(open(p)).get(workload) or {}).get(kernel)
         except Exception:
             return None
     return None
@@ -278,7 +279,7 @@ def main():
     with ClockSampler(local_rank) as clocks:
         # ---- timed: K steps with the spectra resident in HBM; CUDA events on the launching stream (inside the library)
         barrier()
-        dev_ms, prelim_ms, score_ms, setup_ms = 0.0, 0.0, 0.0, 0.0
+        dev_ms, prelim_ms, score_ms, setup_ms, count_ms = 0.0, 0.0, 0.0, 0.0, 0.0
         t0 = time.perf_counter()
         for _ in range(args.steps):
             scorer.run()
@@ -287,6 +288,7 @@ def main():
             prelim_ms += c["ms_prelim"]
             score_ms += c["ms_score"]
             setup_ms += c["ms_setup"]
+            count_ms += c["ms_prelim_count"]
         barrier()
         wall_resident = time.perf_counter() - t0
         last = scorer.counters()
@@ -307,12 +309,26 @@ def main():
     psms = int(counts.sum())
 
     peak, peak_src = measured_hbm_peak()
-    prelim_launch_s = prelim_ms / 1000.0 / args.steps
-    achieved = last["prelim_bytes"] / prelim_launch_s / 1e9 if prelim_launch_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_prelim_wide" if last["wide_queries"] else "k_prelim_narrow", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": committed_traffic(args.workload), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(last["prelim_bytes"]), "launch_ms": prelim_launch_s * 1e3,
-                "note": "narrow windows are dependent-probe (latency) bound, not stream bound; see DESIGN.md"}
+    # Kernels of one step, each with its CUDA-event time (per step) and its share of the SURVEY.md §8d algorithmic bytes; the roofline object
+    # describes the one that takes longest. Open search: k_prelim_wide (timed together with its small replay kernel).
+    count_s, replay_s, score_s = count_ms / 1000.0 / args.steps, (prelim_ms - count_ms) / 1000.0 / args.steps, score_ms / 1000.0 / args.steps
+    if last["wide_queries"]:
+        kernels = [("k_prelim_wide", prelim_ms / 1000.0 / args.steps, last["prelim_bytes"]), ("k_score", score_s, last["score_bytes"])]
+    else:
+        kernels = [("k_prelim_narrow_warp", count_s, last["prelim_bytes"]), ("k_replay", replay_s, 0), ("k_score", score_s, last["score_bytes"])]
+    per_kernel = [{"kernel": k, "launch_ms": t * 1e3, "algorithmic_bytes_per_launch": int(nb), "achieved": (nb / t / 1e9 if t > 0 else 0.0),
+                   "frac": (nb / t / 1e9 / peak if t > 0 else 0.0), "traffic": committed_traffic(args.workload, k)} for k, t, nb in kernels]
+    dom = max(per_kernel, key=lambda r: r["launch_ms"])
+    step_s = dev_s / args.steps
+    notes = {"k_score": "instruction-issue bound (ncu: ~89 % issue-slot utilisation, DRAM < 5 %): per candidate ~2(L-1)Z sorted-array lookups in shared memory; "
+                        "its algorithmic bytes (candidate records + intensities) are small, see DESIGN.md",
+             "k_prelim_narrow_warp": "dependent-probe (latency / divergent-issue) bound, not stream bound; see DESIGN.md",
+             "k_prelim_wide": "streams the page slices of the open-search window once; see DESIGN.md"}
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": dom["traffic"], "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                "launch_ms": dom["launch_ms"], "note": notes.get(dom["kernel"], ""), "kernels": per_kernel,
+                "step": {"algorithmic_bytes": int(last["algorithmic_bytes"]), "device_ms": step_s * 1e3,
+                         "achieved": last["algorithmic_bytes"] / step_s / 1e9, "frac": last["algorithmic_bytes"] / step_s / 1e9 / peak}}
     result = {"metric": "spectra/sec", "value": value, "unit": "spectra/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
               "ms_per_step": dev_s * 1000.0 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
               "data": "synthetic", "config": config,
@@ -320,7 +336,7 @@ def main():
                       "ms_per_step": wall_e2e * 1000.0 / args.steps},
               "gpu_launches": int(last["kernel_launches"]) * args.steps * 2 * args.gpus,
               "roofline": roofline, "clocks": clocks.summary(),
-              "phases_ms_per_step": {"setup": setup_ms / args.steps, "prelim": prelim_ms / args.steps, "score": score_ms / args.steps,
+              "phases_ms_per_step": {"setup": setup_ms / args.steps, "prelim": prelim_ms / args.steps, "prelim_count": count_ms / args.steps, "score": score_ms / args.steps,
                                      "resident_wall": wall_resident * 1000.0 / args.steps, "e2e_h2d": e2e_c["ms_h2d"], "e2e_d2h": e2e_c["ms_d2h"]},
               "work_per_step": {k: int(last[k]) for k in ("queries", "tasks", "pages", "entries_scanned", "matched_fragments", "candidates_scored", "psms",
                                                           "algorithmic_bytes", "wide_queries", "wide_overflows", "pep_queries", "pep_fallbacks")},

@@ -130,11 +130,13 @@ typedef struct {
         pep_queries /* narrow queries counted peptide-centrically (pages/entries_scanned are then not visited) */, pep_fallbacks,
         wide_overflows /* open-search queries whose survivor list overflowed (replayed inside the counting kernel) */;
     uint64_t algorithmic_bytes;    /* SURVEY.md §8d formula, whole batch */
-    uint64_t prelim_bytes;         /* the part of it the preliminary-scoring kernel(s) move */
+    uint64_t prelim_bytes;         /* the part of it the preliminary-scoring kernel(s) move: peak masses, bucket / page probes, entries scanned */
+    uint64_t score_bytes;          /* the part k_score moves: peak intensities, candidate peptide records, PSM rows */
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied across PCIe for the batch */
     uint64_t kernel_launches;
     uint64_t chunk_retries;        /* chunks re-run because a device work list was sized too small (first batches of a scorer) */
     float ms_total, ms_h2d, ms_setup, ms_prelim, ms_score, ms_d2h; /* summed over chunks */
+    float ms_prelim_count;         /* the part of ms_prelim before the heap-replay kernels: k_prelim_narrow_warp + k_prelim_narrow */
 } sage_b200_counters;
 
 int sage_b200_device_count(void);

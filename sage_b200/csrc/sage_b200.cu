@@ -455,7 +455,7 @@ struct ChunkState {
 struct Lane {
     cudaStream_t stream = nullptr;   // kernels + D2H
     cudaStream_t copy = nullptr;     // H2D: masses first (all the counting kernels need), intensities behind them, overlapping setup + preliminary scoring
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[9] = {};   // 0/1 H2D, 6 run start, 2 setup end, 8 counting kernels end, 3 replay end, 4 k_score end, 7/5 D2H
     cudaEvent_t ev_masses = nullptr, ev_intens = nullptr;
     DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_dbgk, d_dbgm, d_sort, d_sorttmp, d_wlist, d_wslots,
         d_witems, d_citems, d_nlist, d_nslots;
@@ -809,6 +809,7 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     CUDA_TRY(cudaGetLastError());
     k_prelim_narrow<<<(unsigned)std::min<uint64_t>(C.nitems, (uint64_t)db->sm_count * 6), PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>());
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(L.ev[8], st));   // narrow counting kernels done (the open-search kernel, when present, is timed with the replays)
     k_replay<<<(unsigned)((C.nitems + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, L.d_nlist.as<uint64_t>(), L.d_nslots.as<ReplaySlot>(),
                                                                                                        (uint32_t)C.nitems, nullptr, n);
     CUDA_TRY(cudaGetLastError());
@@ -907,6 +908,7 @@ static int lane_finish(sage_b200_scorer* S, Lane& L) {
         const unsigned long long* hc = (const unsigned long long*)L.h_counters.p;
         cudaEventElapsedTime(&ms, L.ev[6], L.ev[2]); T.ms_setup += ms;
         cudaEventElapsedTime(&ms, L.ev[2], L.ev[3]); T.ms_prelim += ms;
+        cudaEventElapsedTime(&ms, L.ev[2], L.ev[8]); T.ms_prelim_count += ms;
         cudaEventElapsedTime(&ms, L.ev[3], L.ev[4]); T.ms_score += ms;
         cudaEventElapsedTime(&ms, L.ev[6], L.ev[4]); T.ms_total += ms;
         T.spectra += C.n; T.peaks += C.npk; T.queries += hc[C_QUERIES]; T.tasks += hc[C_TASKS]; T.pages += hc[C_PAGES]; T.entries_scanned += hc[C_ENTRIES];
@@ -942,6 +944,7 @@ static void finish_counters(sage_b200_scorer* S) {
     const DbView& v = S->db->v;
     const uint64_t lp = ceil_log2_u64(v.n_pep), lb = ceil_log2_u64(v.n_bucket), ls = ceil_log2_u64(v.bucket_size);
     L.prelim_bytes = 4 * L.peaks + 8 * lb * L.tasks + 8 * ls * L.pages + 8 * L.entries_scanned;
+    L.score_bytes = 4 * L.peaks + 4 * L.peptide_record_floats + 64 * L.psms;
     L.algorithmic_bytes = 8 * L.peaks + 8 * lp * L.queries + 8 * lb * L.tasks + 8 * ls * L.pages + 8 * L.entries_scanned + 4 * L.peptide_record_floats + 64 * L.psms;
 }
 
