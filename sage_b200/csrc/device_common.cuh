@@ -19,6 +19,7 @@ constexpr int MAX_KINDS = 6;
 constexpr uint32_t WARPQ_CAP = 1024;       // precursor windows up to this many peptides are counted by one warp (u16 counts: 2 KB of smem per warp)
 constexpr int WARPQ_WARPS = 2;             // queries (warps) per CTA of k_prelim_narrow_warp
 constexpr int WARPQ_MIN_CTAS = 24;         // CTAs per SM the register budget is held to
+constexpr uint32_t PEP_LUT_CELLS = 65536;
 constexpr uint32_t BUCKET_LUT_CELLS = 32768;   // ~5 cells per page on a 2M-peptide index: the LUT start is within one page of the answer
 
 // mass.rs:5-8
@@ -190,6 +191,8 @@ struct DbView {
     uint32_t grid_shift, grid_n;
     const uint32_t* bucket_lut; // [BUCKET_LUT_CELLS]: #{bucket_min < edge(c)}, conservative start for the bucket search
     float blut_base, blut_inv_w;
+    const uint32_t* pep_lut;    // [PEP_LUT_CELLS + 1]: #{pep_mono < edge(c)} (last entry n_pep): brackets the precursor-window searches of k_setup_queries
+    float plut_base, plut_inv_w;
     uint64_t n_frag;
     uint8_t kinds[MAX_KINDS];
 };

@@ -17,6 +17,27 @@ namespace sb {
 // ------------------------------------------------------------------------------------------------ setup
 // One thread per spectrum: enumerate the (charge, isotope) queries of Scorer::initial_hits and resolve each
 // precursor window to a PeptideIx range (two binary searches over peptides[].monoisotopic).
+// #{i : mono[i] < x} (le == false) or #{i : mono[i] <= x} (le == true) in f32::total_cmp order. The LUT cell of x brackets the answer to three
+// cells (one early / one late absorb the float rounding of the cell index), the binary search over the bracket uses the exact keys.
+__device__ __forceinline__ uint32_t pep_partition(const DbView& db, float x, bool le) {
+    uint32_t lo = 0, hi = db.n_pep;
+    if (db.pep_lut != nullptr) {
+        const float t = (x - db.plut_base) * db.plut_inv_w;
+        if (t == t) {
+            const int c = (int)fminf(fmaxf(floorf(t), -2.0f), (float)PEP_LUT_CELLS + 2.0f);
+            lo = __ldg(db.pep_lut + min(max(c - 1, 0), (int)PEP_LUT_CELLS));
+            hi = __ldg(db.pep_lut + min(max(c + 2, 0), (int)PEP_LUT_CELLS));
+        }
+    }
+    const int kx = f32_key(x);
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const int k = f32_key(__ldg(db.pep_mono + mid));
+        if (le ? k <= kx : k < kx) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t* sort_key, uint32_t* sort_val) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n) return;
@@ -46,10 +67,11 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
             const float qmass = __fsub_rn(precursor_mass, __fmul_rn((float)iso, NEUTRON));  // scoring.rs:344
             float plo, phi;
             tol_bounds(ptol, qmass, plo, phi);
-            const int klo = f32_key(plo), khi = f32_key(phi);
-            uint32_t left, right;
-            binary_search_slice(db.n_pep, [&](uint32_t i) { return f32_key(__ldg(db.pep_mono + i)) < klo; },
-                                [&](uint32_t i) { return f32_key(__ldg(db.pep_mono + i)) <= khi; }, left, right);
+            // binary_search_slice (database.rs:549-561): left = partition_point(< lo).saturating_sub(1); right = left + partition_point(
+            // slice[left..], <= hi) = max(left, global partition_point(<= hi))
+            const uint32_t ppl = pep_partition(db, plo, false);
+            const uint32_t left = ppl == 0 ? 0 : ppl - 1;
+            const uint32_t right = max(left, pep_partition(db, phi, true));
             QueryDesc q;
             q.pre_lo = left;
             q.pre_hi = right;
@@ -1195,9 +1217,9 @@ __device__ __forceinline__ void score_candidate_warp(const DbView& db, const Sco
                 case 3: ki = f / 3; fc = f - ki * 3 + 1; break;
                 default: ki = f / nfc; fc = f - ki * nfc + 1; break;
             }
-            uint32_t kind_i = 0;
-            idx = ki;
-            while (idx >= nions) { idx -= nions; kind_i++; }   // <= n_kinds - 1 iterations
+            uint32_t kind_i = ki >= nions;   // two ion kinds (b/y) in practice: one compare; more kinds finish in the loop
+            idx = ki - (kind_i ? nions : 0);
+            while (idx >= nions) { idx -= nions; kind_i++; }   // <= n_kinds - 2 iterations
             is_n = (db.nterm_mask >> kind_i) & 1;
             // scoring.rs:707 fragment / charge (ions[kind_i * nions + idx] == ions[ki]): x / 1 and x / 2 are exact as x and x * 0.5 (|x| >= 2^-125)
             const float ion = __ldg(ions + ki);
@@ -1343,7 +1365,7 @@ __device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t
 }
 
 // One CTA per spectrum.
-__global__ void __launch_bounds__(SCORE_THREADS, 14) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
+__global__ void __launch_bounds__(SCORE_THREADS, 12) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
                                                          uint64_t* dbg_keys /*nullable: initial_hits dump*/, uint32_t* dbg_meta, FragmentOut* frag_out /*nullable*/,
                                                          unsigned long long frag_cap, uint32_t quick_mode /*0 score, 1 keep all prelim, 2 low-memory*/,
                                                          uint8_t* keep /*quick_score: one byte per peptide*/) {
@@ -1875,6 +1897,24 @@ __global__ void k_build_page_grid(DbView db, uint32_t grid_shift, uint32_t grid_
     uint32_t pos = pn;
     if (key64 <= 0xFFFFFFFFull) pos = page_lower_bound(db.frag + pbase, 0, pn, (uint32_t)key64);
     grid[j] = (uint16_t)pos;
+}
+// *bad |= the array is not ascending / positive / NaN-free (the pep LUT is only used for arrays the reference's binary search is well defined on)
+__global__ void k_check_ascending(uint32_t n, const float* a, uint32_t* bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = a[i];
+    if (!(x > 0.0f) || !(x < 3.0e38f) || (i > 0 && !(x >= a[i - 1]))) *bad = 1u;
+}
+__global__ void k_build_pep_lut(DbView db, float base, float inv_w, uint32_t* lut) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > PEP_LUT_CELLS) return;
+    uint32_t lo = c == PEP_LUT_CELLS ? db.n_pep : 0;
+    if (c > 0 && c < PEP_LUT_CELLS && inv_w > 0.0f) {
+        const float e = base + (float)c * (1.0f / inv_w);
+        uint32_t hi = db.n_pep;
+        while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (db.pep_mono[m] < e) lo = m + 1; else hi = m; }
+    }
+    lut[c] = lo;
 }
 __global__ void k_build_bucket_lut(DbView db, float base, float inv_w, uint32_t* lut) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;

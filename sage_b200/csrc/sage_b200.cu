@@ -104,7 +104,7 @@ static bool is_pinned(const void* p) {
 struct sage_b200_db {
     int device = 0;
     DbView v{};
-    void *d_page_grid = nullptr, *d_bucket_lut = nullptr;
+    void *d_page_grid = nullptr, *d_bucket_lut = nullptr, *d_pep_lut = nullptr;
     void *d_frag = nullptr, *d_bucket_min = nullptr, *d_pep_mono = nullptr, *d_ion_off = nullptr, *d_ions = nullptr, *d_pep_len = nullptr,
          *d_pep_flags = nullptr, *d_pep_missed = nullptr;
     uint64_t total_residues = 0, device_bytes = 0;
@@ -223,7 +223,7 @@ extern "C" int sage_b200_device_count(void) {
 extern "C" void sage_b200_db_destroy(sage_b200_db* db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    void* ps[] = {db->d_page_grid, db->d_bucket_lut, db->d_frag, db->d_bucket_min, db->d_pep_mono, db->d_ion_off, db->d_ions, db->d_pep_len, db->d_pep_flags, db->d_pep_missed};
+    void* ps[] = {db->d_page_grid, db->d_bucket_lut, db->d_pep_lut, db->d_frag, db->d_bucket_min, db->d_pep_mono, db->d_ion_off, db->d_ions, db->d_pep_len, db->d_pep_flags, db->d_pep_missed};
     for (void* p : ps)
         if (p) cudaFree(p);
     delete db;
@@ -232,7 +232,7 @@ extern "C" void sage_b200_db_destroy(sage_b200_db* db) {
 // Search directories over the finished index (see DbView). Skipped (plain binary searches are used) when the shapes do not fit.
 static int db_build_directories(sage_b200_db* db) {
     DbView& v = db->v;
-    v.page_grid = nullptr; v.bucket_lut = nullptr;
+    v.page_grid = nullptr; v.bucket_lut = nullptr; v.pep_lut = nullptr;
     if (v.n_frag == 0 || v.n_bucket == 0 || v.n_pep == 0 || (getenv("SAGE_B200_NO_DIRECTORIES") && getenv("SAGE_B200_NO_DIRECTORIES")[0] == '1')) return 0;
     int rc;
     if (v.bucket_size <= 65535u) {
@@ -262,7 +262,30 @@ static int db_build_directories(sage_b200_db* db) {
         CUDA_TRY(cudaGetLastError());
         v.blut_base = ends[0]; v.blut_inv_w = inv_w;
     }
+    // precursor-mass LUT over peptides[].monoisotopic (sorted ascending; needs positive finite ends like the bucket LUT)
+    float pe[2] = {0.f, 0.f};
+    CUDA_TRY(cudaMemcpy(&pe[0], db->d_pep_mono, 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&pe[1], (const float*)db->d_pep_mono + (v.n_pep - 1), 4, cudaMemcpyDeviceToHost));
+    const float pw = (pe[1] - pe[0]) / (float)PEP_LUT_CELLS;
+    bool plut_ok = pe[0] > 0.0f && std::isfinite(pe[1]) && pw > 0.0f && pw < 3.0e38f;
+    if (plut_ok) {   // only for a table the reference's binary search is well defined on: ascending, positive, finite
+        uint32_t* d_bad = nullptr;
+        uint32_t h_bad = 1;
+        CUDA_TRY(cudaMalloc(&d_bad, 4));
+        cudaMemset(d_bad, 0, 4);
+        k_check_ascending<<<(v.n_pep + 255) / 256, 256>>>(v.n_pep, (const float*)db->d_pep_mono, d_bad);
+        cudaMemcpy(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost);
+        cudaFree(d_bad);
+        plut_ok = h_bad == 0;
+    }
+    if (plut_ok) {
+        if ((rc = dmalloc(db, &db->d_pep_lut, 4 * (PEP_LUT_CELLS + 1)))) return rc;
+        k_build_pep_lut<<<(PEP_LUT_CELLS + 256) / 256, 256>>>(v, pe[0], 1.0f / pw, (uint32_t*)db->d_pep_lut);
+        CUDA_TRY(cudaGetLastError());
+        v.plut_base = pe[0]; v.plut_inv_w = 1.0f / pw;
+    }
     CUDA_TRY(cudaDeviceSynchronize());
+    if (plut_ok) v.pep_lut = (const uint32_t*)db->d_pep_lut;
     if (db->d_page_grid) v.page_grid = (const uint16_t*)db->d_page_grid;
     if (lut_ok) v.bucket_lut = (const uint32_t*)db->d_bucket_lut;
     return 0;
@@ -768,11 +791,13 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     if (svq.pep_cap == 0) pep_smem = 0;
     if (pep_smem > 24 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_prelim_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pep_smem));
     uint32_t *sk_in = nullptr, *sk_out = nullptr, *sv_in = nullptr, *sv_out = nullptr;
+    int sort_bits = 1;   // keys are PeptideIx < n_pep (spectra without a query sort last within those bits: the order only matters for locality)
+    while (sort_bits < 32 && (db->v.n_pep >> sort_bits)) sort_bits++;
     size_t sort_tmp = 0;
     if (S->sort_spectra && n > 1) {  // process spectra in ascending precursor-window order: neighbouring CTAs then touch the same index lines
         if ((rc = L.d_sort.reserve(16 * (size_t)n))) return rc;
         sk_in = L.d_sort.as<uint32_t>(); sk_out = sk_in + n; sv_in = sk_out + n; sv_out = sv_in + n;
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, sort_bits, st));
         if ((rc = L.d_sorttmp.reserve(sort_tmp + 16))) return rc;
     }
     // Work-list capacities come from what earlier chunks needed (S->nlist_per_spectrum / wide_per_spectrum) or, on a re-run, from the
@@ -796,7 +821,7 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv, sk_in, sv_in);
     CUDA_TRY(cudaGetLastError());
     if (sk_in) {
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(L.d_sorttmp.p, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, 32, st));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(L.d_sorttmp.p, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, sort_bits, st));
         bv.order = sv_out;
     }
     CUDA_TRY(cudaEventRecord(L.ev[2], st));
