@@ -273,7 +273,9 @@ __device__ __forceinline__ void index_probe(const DbView& db, const QueryDesc& q
         const uint32_t pn = (uint32_t)(pend - pbase);
         const uint32_t pp = page_lower_bound_dir(db, page, slice, pn, q.pre_lo);
         const uint32_t il = pp == 0 ? 0 : pp - 1;   // inner_left = partition_point(pep < pre_lo).saturating_sub(1)
-        uint32_t e = il;
+        // the reference also visits entry il = pp - 1; its PeptideIx is < pre_lo <= eff_lo, so it can never pass the filter: it is counted
+        // in `entries` below but not fetched, and the walk starts at the lower bound itself
+        uint32_t e = pp;
         for (; e < pn; e++) {
             const uint2 f = __ldg(&slice[e]);
             if (f.x > q.pre_hi) break;
@@ -1488,7 +1490,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, 12) k_score(DbView db, ScorerVi
         sv.np = np;
         sv.use_lut = spectrum_lut_setup(masses, np, lut, sv.lp);
         for (;;) {  // warps pull candidates dynamically (their cost varies with peptide length / charge / matches)
-            uint32_t c = lane == 0 ? atomicAdd(&s_next, 1u) : 0u;
+            uint32_t c = 0;
+            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(smem_u32(&s_next)) : "memory");   // plain ATOMS: no warp-aggregation prologue
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= ncand) break;
             score_candidate_warp(db, sc, cur[c], sv, recs + c, nullptr);

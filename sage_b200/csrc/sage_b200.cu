@@ -237,7 +237,7 @@ static int db_build_directories(sage_b200_db* db) {
     int rc;
     if (v.bucket_size <= 65535u) {
         // cells per page ~ bucket_size / entries-per-cell: the in-cell search that follows a grid lookup is a chain of dependent loads
-        uint32_t epc = 4;   // measured on cfg2: 32 -> 4 entries per cell = -3 % preliminary-scoring time for +3 % index memory
+        uint32_t epc = 2;   // measured on cfg2 (preliminary scoring, ms): 32 entries per cell 1.87, 8: 1.83, 4: 1.82, 2: 1.81 (CTA kernel); 0.905 -> 0.876 (warp kernel); +6 % index memory
         if (const char* e = getenv("SAGE_B200_GRID_ENTRIES")) epc = (uint32_t)std::min(1024, std::max(1, atoi(e)));
         uint32_t cells = 64;
         while (cells < 16384 && (uint64_t)cells * epc < v.bucket_size) cells <<= 1;
