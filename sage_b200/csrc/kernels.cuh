@@ -15,6 +15,9 @@
 namespace sb {
 
 // ------------------------------------------------------------------------------------------------ setup
+#ifndef SAGE_B200_HALFWARP_SCORE
+#define SAGE_B200_HALFWARP_SCORE 0   // experimental half-warp-per-candidate scoring (see score_candidate_half); off: not measured yet
+#endif
 // One thread per spectrum: enumerate the (charge, isotope) queries of Scorer::initial_hits and resolve each
 // precursor window to a PeptideIx range (two binary searches over peptides[].monoisotopic).
 // #{i : mono[i] < x} (le == false) or #{i : mono[i] <= x} (le == true) in f32::total_cmp order. The LUT cell of x brackets the answer to three
@@ -1307,6 +1310,80 @@ __device__ __forceinline__ uint32_t append_hits(uint64_t* buf, uint32_t len, uin
 
 struct FragmentOut { int32_t kind, charge, ordinal; float intensity, mz_calculated, mz_experimental; };  // == sage_b200_fragment
 
+#if SAGE_B200_HALFWARP_SCORE
+// EXPERIMENTAL (not built by default, unmeasured): score_candidate_warp with a HALF-warp per candidate. A tryptic candidate has ~45 lookups:
+// two 32-lane rounds leave the second mostly empty, three 16-lane rounds fill 94 % of the lanes, and the two halves of a warp share every
+// issued instruction (prologue, lookups, the in-order f32 fold). All *_sync primitives name only the caller's half (hmask), so the halves
+// may run different candidates / iteration counts. Order of the fold is unchanged: ascending f within a round, rounds ascending.
+__device__ __forceinline__ void score_candidate_half(const DbView& db, const ScorerView& sc, uint64_t key, const SpecView& sp, ScoreRec* out) {
+    const uint32_t lane = threadIdx.x & 31, hl = lane & 15, hbase = lane & 16;
+    const uint32_t hmask = 0xFFFFu << hbase;
+    const uint32_t pep = key_peptide(key), charge = key_charge(key);
+    const uint32_t L = __ldg(db.pep_len + pep);
+    const uint32_t nions = L - 1;
+    const uint32_t nfc = max_fragment_charge(sc.max_fragment_charge_opt, charge) - 1;
+    const float* ions = db.ions + __ldg(db.ion_off + pep);
+    const uint32_t per_kind = nions * nfc, total = per_kind * db.n_kinds;
+    uint32_t mb = 0, my = 0;
+    float sb = 0.f, sy = 0.f, ppm = 0.f;
+    Run brun = {0, 0, 0, 0}, yrun = {0, 0, 0, 0};
+    for (uint32_t base = 0; base < total; base += 16) {
+        const uint32_t f = base + hl;
+        int pk = -1;
+        float term = 0.f, inten = 0.f;
+        uint32_t idx = 0;
+        bool is_n = false;
+        if (f < total) {
+            uint32_t ki, fc;
+            switch (nfc) {
+                case 1: ki = f; fc = 1; break;
+                case 2: ki = f >> 1; fc = (f & 1) + 1; break;
+                case 3: ki = f / 3; fc = f - ki * 3 + 1; break;
+                default: ki = f / nfc; fc = f - ki * nfc + 1; break;
+            }
+            uint32_t kind_i = ki >= nions;
+            idx = ki - (kind_i ? nions : 0);
+            while (idx >= nions) { idx -= nions; kind_i++; }
+            is_n = (db.nterm_mask >> kind_i) & 1;
+            const float ion = __ldg(ions + ki);
+            const float mz = fc == 1 ? ion : (fc == 2 && fabsf(ion) >= 1e-30f) ? __fmul_rn(ion, 0.5f) : __fdiv_rn(ion, (float)fc);   // scoring.rs:707
+            pk = sp.use_lut ? select_most_intense_peak_lut(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol, sp.lp, sp.lut)
+                            : select_most_intense_peak(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol);
+            if (pk >= 0) {
+                const float peak_mass = sp.masses[pk];
+                inten = sp.intens[pk];
+                term = __fdiv_rn(__fmul_rn(__fmul_rn(inten, fabsf(__fsub_rn(mz, peak_mass))), 2E6f), __fadd_rn(mz, peak_mass));   // scoring.rs:719-720
+            }
+        }
+        uint32_t mask = (__ballot_sync(hmask, pk >= 0) >> hbase) & 0xFFFFu;
+        const uint32_t maskn = (__ballot_sync(hmask, pk >= 0 && is_n) >> hbase) & 0xFFFFu;
+        mb += __popc(maskn);
+        my += __popc(mask & ~maskn);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float t = __shfl_sync(hmask, term, (int)hbase + src);
+            const float it = __shfl_sync(hmask, inten, (int)hbase + src);
+            const uint32_t ib = __shfl_sync(hmask, idx, (int)hbase + src);
+            ppm = __fadd_rn(ppm, t);
+            if ((maskn >> src) & 1) { sb = __fadd_rn(sb, it); brun.matched(ib); }
+            else { sy = __fadd_rn(sy, it); yrun.matched(ib); }
+        }
+    }
+    if (hl == 0) {
+        ScoreRec r;
+        r.peptide = pep; r.charge = charge; r.iso = key_iso(key);
+        r.matched_b = mb & 0xFFFF; r.matched_y = my & 0xFFFF; r.summed_b = sb; r.summed_y = sy;
+        r.longest_b = brun.longest; r.longest_y = yrun.longest;
+        r.hyperscore = 0.0;
+        r.ppm_difference = ppm;
+        r.valid = 0;
+        r.plen = L;
+        *out = r;
+    }
+}
+#endif
+
 // Fragments of one reported PSM (scoring.rs:738-751), written by one warp in the reference's order (kind, ion index, charge) to
 // out[0 .. matched_b + matched_y). Same lookups as score_candidate_warp on the same spectrum state.
 __device__ __forceinline__ void annotate_candidate_warp(const DbView& db, const ScorerView& sc, uint32_t pep, uint32_t charge, const SpecView& sp,
@@ -1490,11 +1567,19 @@ __global__ void __launch_bounds__(SCORE_THREADS, 12) k_score(DbView db, ScorerVi
         sv.np = np;
         sv.use_lut = spectrum_lut_setup(masses, np, lut, sv.lp);
         for (;;) {  // warps pull candidates dynamically (their cost varies with peptide length / charge / matches)
+#if SAGE_B200_HALFWARP_SCORE
+            uint32_t c = 0;
+            if ((lane & 15) == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(smem_u32(&s_next)) : "memory");
+            c = __shfl_sync(0xFFFFu << (lane & 16), c, (int)(lane & 16));
+            if (c >= ncand) break;
+            score_candidate_half(db, sc, cur[c], sv, recs + c);
+#else
             uint32_t c = 0;
             if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(smem_u32(&s_next)) : "memory");   // plain ATOMS: no warp-aggregation prologue
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= ncand) break;
             score_candidate_warp(db, sc, cur[c], sv, recs + c, nullptr);
+#endif
         }
         if (tid == 0) s_nvalid = 0;
         __syncthreads();
