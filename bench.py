@@ -334,7 +334,7 @@ def main():
               "data": "synthetic", "config": config,
               "e2e": {"value": e2e_value, "unit": "spectra/s", "h2d_bytes_per_step": int(e2e_c["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_c["d2h_bytes"]),
                       "ms_per_step": wall_e2e * 1000.0 / args.steps},
-              "gpu_launches": int(last["kernel_launches"]) * args.steps * 2 * args.gpus,
+              "gpu_launches": (int(last["kernel_launches"]) + int(e2e_c["kernel_launches"])) * args.steps * args.gpus,   # own kernels in both timed regions (cub sorts not counted)
               "roofline": roofline, "clocks": clocks.summary(),
               "phases_ms_per_step": {"setup": setup_ms / args.steps, "prelim": prelim_ms / args.steps, "prelim_count": count_ms / args.steps, "score": score_ms / args.steps,
                                      "resident_wall": wall_resident * 1000.0 / args.steps, "e2e_h2d": e2e_c["ms_h2d"], "e2e_d2h": e2e_c["ms_d2h"]},
