@@ -213,6 +213,14 @@ int sage_b200_process_spectra(int device, const sage_b200_processor_params* proc
 int sage_b200_find_reporter_ions(int device, uint64_t n, const uint64_t* peak_offsets, const float* masses, const float* intensities, const float* labels,
                                  uint64_t n_labels, sage_b200_tolerance label_tolerance, float* out);
 
+/* Which build of glibc's log() the host libm is (replaces Rust's f64::ln, scoring.rs:179-201 / :512): the kernels reproduce that function
+ * operation by operation so that hyperscore, poisson and ranks under near-ties carry the same bits as the CPU path on this host.
+ * 0 = x86-64 glibc on a CPU with FMA+AVX2 (`__log_fma`), 1 = the uncontracted build (`__log_sse2`/`__log_avx`, musl, aarch64),
+ * -1 = neither matched std::log on the probe inputs (the device then uses variant 0; f64 fields agree to <= 1 ulp). */
+int sage_b200_host_log_variant(void);
+/* Test hook: out[i] = the device's evaluation of log(x[i]) with `variant` (0/1) — compared bit for bit with the host libm by tests/test_glibc_log.py. */
+int sage_b200_device_log(int device, int variant, const double* x, uint64_t n, double* out);
+
 /* Page-locked host buffers: spectra/feature arrays placed here are copied by DMA without a staging memcpy. */
 void* sage_b200_host_alloc(size_t bytes);
 void sage_b200_host_free(void* p);

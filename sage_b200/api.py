@@ -88,6 +88,7 @@ EXPORTED_SYMBOLS = [
     "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_scorer_set_option", "sage_b200_score_batch", "sage_b200_batch_upload", "sage_b200_batch_run",
     "sage_b200_batch_download", "sage_b200_score_batch_multi", "sage_b200_quick_score", "sage_b200_initial_hits", "sage_b200_counters_get",
     "sage_b200_process_spectra", "sage_b200_find_reporter_ions", "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
+    "sage_b200_host_log_variant", "sage_b200_device_log",
 ]
 
 _lib = None
@@ -130,6 +131,19 @@ def _check(rc: int):
 
 def device_count() -> int:
     return int(load_library().sage_b200_device_count())
+
+
+def host_log_variant() -> int:
+    """Which build of glibc's log() the host libm is (0 FMA-contracted, 1 plain, -1 unknown); the kernels reproduce that one (glibc_log.cuh)."""
+    return int(load_library().sage_b200_host_log_variant())
+
+
+def device_log(x: np.ndarray, variant: int, device: int = 0) -> np.ndarray:
+    """The device's evaluation of f64 log for every x (test hook for the glibc log() emulation)."""
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.zeros_like(x)
+    _check(load_library().sage_b200_device_log(C.c_int(device), C.c_int(variant), _ptr(x), C.c_uint64(len(x)), _ptr(out)))
+    return out
 
 
 def _ptr(a):

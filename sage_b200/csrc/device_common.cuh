@@ -13,6 +13,11 @@ constexpr int K_MAX = 128;            // max preliminary candidates kept per spe
 constexpr uint32_t NARROW_CAP = 8192; // precursor windows up to this many peptides are counted in shared memory
 constexpr int PRELIM_THREADS = 256;
 constexpr int SCORE_THREADS = 128;  // measured on cfg2: 128 (1.66 ms) beats 256 (1.95 ms) and 64 (1.75 ms); must stay >= K_MAX for the rank sort
+#ifndef SAGE_B200_SCORE_MIN_CTAS
+#define SAGE_B200_SCORE_MIN_CTAS 8
+#endif
+constexpr int SCORE_MIN_CTAS = SAGE_B200_SCORE_MIN_CTAS;   // k_score CTAs per SM the register budget is held to (A/B: profiles/r02_*)
+constexpr uint32_t SCORE_TILE_DEFAULT = 2048;              // tasks (theoretical-fragment lookups) per shared-memory tile of k_score
 constexpr int MAX_KINDS = 6;
 // k_prelim_narrow_warp: measured on cfg2 (prelim ms): cap 1024 x 2 warps x 24 CTAs/SM 1.04 | cap 512 1.09 | cap 256 1.35 | cap 2048 1.60 (its
 // 192 KB of shared memory per SM leaves too little L1 for the index lines) | 4 warps 1.06 | 8 warps 1.08
@@ -215,6 +220,8 @@ struct ScorerView {
     uint32_t wide_lmax;        // survivor-list capacity per query (<= WIDE_LMAX; smaller only in tests)
     const double* lnfact_tab;  // lnfact(n) for n < lnfact_n, computed on the host with libm log (scoring.rs:170-177)
     uint32_t lnfact_n;
+    uint32_t log_variant;      // which build of glibc's log() the device reproduces (glibc_log.cuh): 0 = FMA-contracted, 1 = plain
+    uint32_t score_tile;       // tasks per tile of score_candidates_flat (multiple of 128)
 };
 
 struct BatchView {

@@ -11,13 +11,11 @@
 // All of this is integer/f32 gather-reduce work bound by memory latency/bandwidth; tensor cores are not used.
 #pragma once
 #include "device_common.cuh"
+#include "glibc_log.cuh"
 
 namespace sb {
 
 // ------------------------------------------------------------------------------------------------ setup
-#ifndef SAGE_B200_HALFWARP_SCORE
-#define SAGE_B200_HALFWARP_SCORE 0   // experimental half-warp-per-candidate scoring (see score_candidate_half); off: not measured yet
-#endif
 // One thread per spectrum: enumerate the (charge, isotope) queries of Scorer::initial_hits and resolve each
 // precursor window to a PeptideIx range (two binary searches over peptides[].monoisotopic).
 // #{i : mono[i] < x} (le == false) or #{i : mono[i] <= x} (le == true) in f32::total_cmp order. The LUT cell of x brackets the answer to three
@@ -1159,20 +1157,23 @@ __device__ __forceinline__ int select_most_intense_peak_lut(const float* masses,
     return best;
 }
 
+// f64::ln as the host libm computes it (glibc_log.cuh): variant selected by the host probe
+__device__ __forceinline__ double ref_ln(const ScorerView& sc, double x) { return glog::glibc_log_v(x, (int)sc.log_variant); }
 // lnfact (scoring.rs:170-177)
 __device__ __forceinline__ double lnfact(const ScorerView& sc, uint32_t n) {
     if (n < sc.lnfact_n) return __ldg(sc.lnfact_tab + n);
     if (n == 0) return 1.0;
     const double x = (double)n;
-    return x * log(x) - x + 0.5 * log(x) + 0.5 * log(3.14159265358979323846 * 2.0 * x);
+    return x * ref_ln(sc, x) - x + 0.5 * ref_ln(sc, x) + 0.5 * ref_ln(sc, 3.14159265358979323846 * 2.0 * x);
 }
 // ScoreType::score (scoring.rs:179-201)
 __device__ __forceinline__ double hyperscore_of(const ScorerView& sc, uint32_t mb, uint32_t my, float sb, float sy) {
     double s;
     if (sc.score_type == 0) {
         const double i = (double)__fadd_rn(sb, 1.0f) * (double)__fadd_rn(sy, 1.0f);
-        s = log(i) + lnfact(sc, mb) + lnfact(sc, my);
+        s = ref_ln(sc, i) + lnfact(sc, mb) + lnfact(sc, my);
     } else {
+        // f32::ln_1p is libm's log1pf; CUDA's f64 log1p rounded to f32 agrees except for rare 1-ulp (f32) cases (documented in DESIGN.md)
         const float si = __fadd_rn(sb, sy);
         s = (double)(float)log1p((double)si) + lnfact(sc, mb) + lnfact(sc, my);
     }
@@ -1262,18 +1263,12 @@ __device__ __forceinline__ void score_candidate_warp(const DbView& db, const Sco
         r.peptide = pep; r.charge = charge; r.iso = key_iso(key);
         r.matched_b = mb & 0xFFFF; r.matched_y = my & 0xFFFF; r.summed_b = sb; r.summed_y = sy;
         r.longest_b = brun.longest; r.longest_y = yrun.longest;
-        r.hyperscore = 0.0;          // finalised one candidate per thread (finalize_rec): keeps the f64 log off the warp-serial path
+        r.hyperscore = 0.0;          // (this warp-per-candidate variant only serves remove_matched_peaks / tests; score_candidates_flat fills real records)
         r.ppm_difference = ppm;
         r.valid = 0;
         r.plen = L;
         *out = r;
     }
-}
-
-__device__ __forceinline__ void finalize_rec(const ScorerView& sc, ScoreRec& r) {
-    r.hyperscore = hyperscore_of(sc, r.matched_b, r.matched_y, r.summed_b, r.summed_y);               // scoring.rs:756
-    r.ppm_difference = __fdiv_rn(r.ppm_difference, __fadd_rn(r.summed_b, r.summed_y));                // scoring.rs:759
-    r.valid = ((r.matched_b + r.matched_y) & 0xFFFF) >= sc.min_matched_peaks;                          // scoring.rs:491
 }
 
 struct FeatureOut {  // layout == sage_b200_feature
@@ -1310,79 +1305,145 @@ __device__ __forceinline__ uint32_t append_hits(uint64_t* buf, uint32_t len, uin
 
 struct FragmentOut { int32_t kind, charge, ordinal; float intensity, mz_calculated, mz_experimental; };  // == sage_b200_fragment
 
-#if SAGE_B200_HALFWARP_SCORE
-// EXPERIMENTAL (not built by default, unmeasured): score_candidate_warp with a HALF-warp per candidate. A tryptic candidate has ~45 lookups:
-// two 32-lane rounds leave the second mostly empty, three 16-lane rounds fill 94 % of the lanes, and the two halves of a warp share every
-// issued instruction (prologue, lookups, the in-order f32 fold). All *_sync primitives name only the caller's half (hmask), so the halves
-// may run different candidates / iteration counts. Order of the fold is unchanged: ascending f within a round, rounds ascending.
-__device__ __forceinline__ void score_candidate_half(const DbView& db, const ScorerView& sc, uint64_t key, const SpecView& sp, ScoreRec* out) {
-    const uint32_t lane = threadIdx.x & 31, hl = lane & 15, hbase = lane & 16;
-    const uint32_t hmask = 0xFFFFu << hbase;
-    const uint32_t pep = key_peptide(key), charge = key_charge(key);
-    const uint32_t L = __ldg(db.pep_len + pep);
-    const uint32_t nions = L - 1;
-    const uint32_t nfc = max_fragment_charge(sc.max_fragment_charge_opt, charge) - 1;
-    const float* ions = db.ions + __ldg(db.ion_off + pep);
-    const uint32_t per_kind = nions * nfc, total = per_kind * db.n_kinds;
+// score_candidate (scoring.rs:675-767) for ALL candidates of a spectrum at once. A candidate is L-1 ions x kinds x fragment charges sorted-array
+// lookups (~45 for a tryptic peptide at z = 2); one warp per candidate leaves a third of the lanes idle and pays every prologue per candidate.
+// Here the lookups of the <= k candidates are flattened into one task list t = base[c] + f (f = (kind*nions + idx)*nfc + fc-1, the reference's
+// loop order), processed in tiles of `tile` tasks:
+//   phase B  every lane owns one task: candidate header from smem (cursor advanced incrementally, tasks of a lane ascend), theoretical m/z
+//            from the ion table, select_most_intense_peak through the spectrum LUT, ppm term; matched tasks leave (term, intensity) in smem
+//            and one bit in a per-tile mask (warp ballot).
+//   fold     thread c folds candidate c's matched tasks in ascending f — exactly the reference's order of `ppm_difference +=`, `summed_b/y +=`,
+//            Run::matched — keeping its partial sums in registers from tile to tile (tiles need not align with candidates).
+// Results are bit-identical to score_candidate_warp (same f32 operations in the same order).
+struct __align__(16) CandHdr { uint32_t ion_off, base, next; uint16_t nions; uint8_t nfc, pad; };
+
+__device__ __forceinline__ void score_candidates_flat(const DbView& db, const ScorerView& sc, const uint64_t* cur, uint32_t ncand, const SpecView& sp,
+                                                      CandHdr* hdr /*[kparam + 1]*/, float* t_term, float* t_int, uint32_t* t_mask, uint32_t tile,
+                                                      ScoreRec* recs, double* hkey, uint32_t* s_scan /*[SCORE_THREADS / 32]*/) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SCORE_THREADS / 32;
+    // ---- phase A: candidate headers + exclusive scan of the task counts
+    uint64_t key = 0;
+    uint32_t L = 0, nions = 0, nfc = 1, total = 0, ion_off = 0;
+    if (tid < ncand) {
+        key = cur[tid];
+        const uint32_t pep = key_peptide(key);
+        L = __ldg(db.pep_len + pep);
+        nions = L - 1;
+        nfc = max_fragment_charge(sc.max_fragment_charge_opt, key_charge(key)) - 1;
+        total = nions * nfc * db.n_kinds;
+        ion_off = __ldg(db.ion_off + pep);
+    }
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    uint32_t base = incl - total, T = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < nwarps; w++) {
+        const uint32_t x = s_scan[w];
+        if (w < warp) base += x;
+        T += x;
+    }
+    if (tid < ncand) { CandHdr h; h.ion_off = ion_off; h.base = base; h.next = base + total; h.nions = (uint16_t)nions; h.nfc = (uint8_t)nfc; h.pad = 0; hdr[tid] = h; }
+    if (tid == 0) { CandHdr h; h.ion_off = 0; h.base = T; h.next = 0xFFFFFFFFu; h.nions = 0; h.nfc = 1; h.pad = 0; hdr[ncand] = h; }   // sentinel: stops every cursor
+    // fold state of candidate tid (registers, carried across tiles)
     uint32_t mb = 0, my = 0;
     float sb = 0.f, sy = 0.f, ppm = 0.f;
     Run brun = {0, 0, 0, 0}, yrun = {0, 0, 0, 0};
-    for (uint32_t base = 0; base < total; base += 16) {
-        const uint32_t f = base + hl;
-        int pk = -1;
-        float term = 0.f, inten = 0.f;
-        uint32_t idx = 0;
-        bool is_n = false;
-        if (f < total) {
-            uint32_t ki, fc;
-            switch (nfc) {
-                case 1: ki = f; fc = 1; break;
-                case 2: ki = f >> 1; fc = (f & 1) + 1; break;
-                case 3: ki = f / 3; fc = f - ki * 3 + 1; break;
-                default: ki = f / nfc; fc = f - ki * nfc + 1; break;
-            }
-            uint32_t kind_i = ki >= nions;
-            idx = ki - (kind_i ? nions : 0);
-            while (idx >= nions) { idx -= nions; kind_i++; }
-            is_n = (db.nterm_mask >> kind_i) & 1;
-            const float ion = __ldg(ions + ki);
-            const float mz = fc == 1 ? ion : (fc == 2 && fabsf(ion) >= 1e-30f) ? __fmul_rn(ion, 0.5f) : __fdiv_rn(ion, (float)fc);   // scoring.rs:707
-            pk = sp.use_lut ? select_most_intense_peak_lut(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol, sp.lp, sp.lut)
-                            : select_most_intense_peak(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol);
-            if (pk >= 0) {
-                const float peak_mass = sp.masses[pk];
-                inten = sp.intens[pk];
-                term = __fdiv_rn(__fmul_rn(__fmul_rn(inten, fabsf(__fsub_rn(mz, peak_mass))), 2E6f), __fadd_rn(mz, peak_mass));   // scoring.rs:719-720
-            }
+    for (uint32_t t0 = 0; t0 < T; t0 += tile) {
+        const uint32_t tn = min(tile, T - t0);
+        __syncthreads();   // headers written / previous tile's fold done with the tile arrays
+        // ---- phase B: each warp takes a contiguous run of the tile (a multiple of 32 slots), lanes = consecutive tasks
+        const uint32_t chunk = (((tn + nwarps - 1) / nwarps) + 31) & ~31u;
+        const uint32_t w_lo = warp * chunk, w_hi = min(tn, w_lo + chunk);
+        uint32_t c = 0;
+        CandHdr h = hdr[0];
+        if (w_lo < w_hi) {   // cursor start: largest c with base[c] <= first task of this lane (binary search over the <= 128 headers)
+            const uint32_t t_first = t0 + min(w_lo + lane, w_hi - 1);
+            uint32_t lo = 0, hi = ncand;   // invariant: base[lo] <= t_first (base[0] = 0), answer in [lo, hi)
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (hdr[mid].base <= t_first) lo = mid; else hi = mid; }
+            c = lo;
+            h = hdr[c];
         }
-        uint32_t mask = (__ballot_sync(hmask, pk >= 0) >> hbase) & 0xFFFFu;
-        const uint32_t maskn = (__ballot_sync(hmask, pk >= 0 && is_n) >> hbase) & 0xFFFFu;
-        mb += __popc(maskn);
-        my += __popc(mask & ~maskn);
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float t = __shfl_sync(hmask, term, (int)hbase + src);
-            const float it = __shfl_sync(hmask, inten, (int)hbase + src);
-            const uint32_t ib = __shfl_sync(hmask, idx, (int)hbase + src);
-            ppm = __fadd_rn(ppm, t);
-            if ((maskn >> src) & 1) { sb = __fadd_rn(sb, it); brun.matched(ib); }
-            else { sy = __fadd_rn(sy, it); yrun.matched(ib); }
+        for (uint32_t s0 = w_lo; s0 < w_hi; s0 += 32) {
+            const uint32_t slot = s0 + lane, t = t0 + slot;
+            bool hit = false;
+            if (slot < w_hi) {
+                while (t >= h.next) { c++; h = hdr[c]; }   // skips zero-length candidates; the sentinel's next = 2^32 - 1 > t
+                const uint32_t f = t - h.base;
+                uint32_t ki, fc;
+                switch (h.nfc) {
+                    case 1: ki = f; fc = 1; break;
+                    case 2: ki = f >> 1; fc = (f & 1) + 1; break;
+                    case 3: ki = f / 3; fc = f - ki * 3 + 1; break;
+                    default: ki = f / h.nfc; fc = f - ki * h.nfc + 1; break;
+                }
+                // scoring.rs:707 fragment / charge: x / 1 and x / 2 are exact as x and x * 0.5 (|x| >= 2^-125)
+                const float ion = __ldg(db.ions + h.ion_off + ki);
+                const float mz = fc == 1 ? ion : (fc == 2 && fabsf(ion) >= 1e-30f) ? __fmul_rn(ion, 0.5f) : __fdiv_rn(ion, (float)fc);
+                const int pk = sp.use_lut ? select_most_intense_peak_lut(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol, sp.lp, sp.lut)
+                                          : select_most_intense_peak(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol);
+                if (pk >= 0) {
+                    const float peak_mass = sp.masses[pk], inten = sp.intens[pk];
+                    // scoring.rs:719-720: peak_intensity * (mz - peak_mass).abs() * 2E6 / (mz + peak_mass)
+                    t_term[slot] = __fdiv_rn(__fmul_rn(__fmul_rn(inten, fabsf(__fsub_rn(mz, peak_mass))), 2E6f), __fadd_rn(mz, peak_mass));
+                    t_int[slot] = inten;
+                    hit = true;
+                }
+            }
+            const uint32_t ball = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) t_mask[s0 >> 5] = ball;
+        }
+        __syncthreads();
+        // ---- fold: thread c walks the set bits of candidate c's slice of the tile in ascending task order
+        if (tid < ncand && total) {
+            const uint32_t a = max(base, t0), b = min(base + total, t0 + tn);
+            if (a < b) {
+                const uint32_t sa = a - t0, se = b - t0 - 1;   // first / last slot (inclusive)
+                for (uint32_t w = sa >> 5; w <= se >> 5; w++) {
+                    uint32_t m = t_mask[w];
+                    if (w == sa >> 5) m &= 0xffffffffu << (sa & 31);
+                    if (w == se >> 5) m &= 0xffffffffu >> (31 - (se & 31));
+                    while (m) {
+                        const uint32_t slot = (w << 5) + (uint32_t)__ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t f = t0 + slot - base;
+                        uint32_t ki;
+                        switch (nfc) {
+                            case 1: ki = f; break;
+                            case 2: ki = f >> 1; break;
+                            case 3: ki = f / 3; break;
+                            default: ki = f / nfc; break;
+                        }
+                        uint32_t kind_i = ki >= nions;   // two ion kinds (b/y) in practice: one compare; more kinds finish in the loop
+                        uint32_t idx = ki - (kind_i ? nions : 0);
+                        while (idx >= nions) { idx -= nions; kind_i++; }
+                        const float it = t_int[slot];
+                        ppm = __fadd_rn(ppm, t_term[slot]);
+                        if ((db.nterm_mask >> kind_i) & 1) { mb++; sb = __fadd_rn(sb, it); brun.matched(idx); }
+                        else { my++; sy = __fadd_rn(sy, it); yrun.matched(idx); }
+                    }
+                }
+            }
         }
     }
-    if (hl == 0) {
+    if (tid < ncand) {
         ScoreRec r;
-        r.peptide = pep; r.charge = charge; r.iso = key_iso(key);
+        r.peptide = key_peptide(key); r.charge = key_charge(key); r.iso = key_iso(key);
         r.matched_b = mb & 0xFFFF; r.matched_y = my & 0xFFFF; r.summed_b = sb; r.summed_y = sy;
         r.longest_b = brun.longest; r.longest_y = yrun.longest;
-        r.hyperscore = 0.0;
-        r.ppm_difference = ppm;
-        r.valid = 0;
+        r.hyperscore = hyperscore_of(sc, r.matched_b, r.matched_y, sb, sy);                  // scoring.rs:756
+        r.ppm_difference = __fdiv_rn(ppm, __fadd_rn(sb, sy));                                // scoring.rs:759
+        r.valid = ((r.matched_b + r.matched_y) & 0xFFFF) >= sc.min_matched_peaks;            // scoring.rs:491
         r.plen = L;
-        *out = r;
+        recs[tid] = r;
+        hkey[tid] = r.valid ? r.hyperscore : -INFINITY;   // sort key: valid scores are finite (non-finite -> 255.0), so -inf never outranks one
     }
 }
-#endif
 
 // Fragments of one reported PSM (scoring.rs:738-751), written by one warp in the reference's order (kind, ion index, charge) to
 // out[0 .. matched_b + matched_y). Same lookups as score_candidate_warp on the same spectrum state.
@@ -1444,12 +1505,12 @@ __device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t
 }
 
 // One CTA per spectrum.
-__global__ void __launch_bounds__(SCORE_THREADS, 12) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
+__global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
                                                          uint64_t* dbg_keys /*nullable: initial_hits dump*/, uint32_t* dbg_meta, FragmentOut* frag_out /*nullable*/,
                                                          unsigned long long frag_cap, uint32_t quick_mode /*0 score, 1 keep all prelim, 2 low-memory*/,
                                                          uint8_t* keep /*quick_score: one byte per peptide*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: masses_raw[pmax+4] intens_raw[pmax+4] cur[lcap] tot[lcap] recs[kparam] order[kparam] lut[1024] mark[pmax]   (pmax % 4 == 0)
+    // layout: masses_raw[pmax+4] intens_raw[pmax+4] cur[lcap] tot[lcap] recs[kparam] order[kparam] lut[1024] mark[pmax] + the tile arrays below  (pmax % 4 == 0)
     float* masses_raw = reinterpret_cast<float*>(smem_raw);
     float* intens_raw = masses_raw + pmax + 4;
     uint64_t* cur = reinterpret_cast<uint64_t*>(intens_raw + pmax + 4);
@@ -1458,7 +1519,14 @@ __global__ void __launch_bounds__(SCORE_THREADS, 12) k_score(DbView db, ScorerVi
     uint32_t* order = reinterpret_cast<uint32_t*>(recs + sc.kparam);
     uint16_t* lut = reinterpret_cast<uint16_t*>(order + sc.kparam);
     uint8_t* mark = reinterpret_cast<uint8_t*>(lut + SPEC_LUT_CELLS);
-    __shared__ uint32_t s_ntot, s_ncand, s_np, s_nvalid, s_next;
+    // flattened candidate scoring (score_candidates_flat): headers[kparam + 1] | sort keys[kparam] | term[tile] | intensity[tile] | mask[tile / 32]
+    CandHdr* hdr = reinterpret_cast<CandHdr*>(smem_raw + (((size_t)(mark + pmax) - (size_t)smem_raw + 15) & ~(size_t)15));
+    double* hkey = reinterpret_cast<double*>(hdr + sc.kparam + 1);
+    float* t_term = reinterpret_cast<float*>(hkey + sc.kparam);
+    float* t_int = t_term + sc.score_tile;
+    uint32_t* t_mask = reinterpret_cast<uint32_t*>(t_int + sc.score_tile);
+    __shared__ uint32_t s_scan[SCORE_THREADS / 32];
+    __shared__ uint32_t s_ntot, s_ncand, s_np, s_nvalid;
     __shared__ unsigned long long s_matched_peaks, s_scored;
     __shared__ float s_tic;
 
@@ -1473,7 +1541,6 @@ __global__ void __launch_bounds__(SCORE_THREADS, 12) k_score(DbView db, ScorerVi
     float* masses = masses_raw + head;
     float* intens = intens_raw + head;
     if (tid == 0) {   // one thread initialises the barrier and issues both copies; everyone else first touches s_bar after the prologue's barrier
-        s_next = 0;
         mbar_init(&s_bar, 1);
         if (np) {
             mbar_arrive_expect_tx(&s_bar, 2 * bytes);
@@ -1551,6 +1618,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, 12) k_score(DbView db, ScorerVi
     }
     if (np) mbar_wait(&s_bar, 0);   // peaks have landed in shared memory
     const uint32_t ncand = s_ncand;
+    // quick_score accumulates into keep[] across chunks; a chunk whose work lists overflowed (the host re-runs it with exact sizes) has partial hit
+    // sets and must not leave marks behind. Both counters are final after k_setup_queries.
+    const bool lists_fit = b.counters[C_NLIST_NEED] <= b.nlist_cap && b.counters[C_WIDE] <= (unsigned long long)b.wide_cap;
+    if (quick_mode != 0 && !lists_fit) return;
     if (quick_mode == 1) {   // Scorer::quick_score, prefilter_low_memory == false (scoring.rs:291-296): every preliminary peptide is kept
         for (uint32_t i = tid; i < ncand; i += SCORE_THREADS) keep[key_peptide(cur[i])] = 1;
         return;
@@ -1566,25 +1637,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, 12) k_score(DbView db, ScorerVi
         np = s_np;
         sv.np = np;
         sv.use_lut = spectrum_lut_setup(masses, np, lut, sv.lp);
-        for (;;) {  // warps pull candidates dynamically (their cost varies with peptide length / charge / matches)
-#if SAGE_B200_HALFWARP_SCORE
-            uint32_t c = 0;
-            if ((lane & 15) == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(smem_u32(&s_next)) : "memory");
-            c = __shfl_sync(0xFFFFu << (lane & 16), c, (int)(lane & 16));
-            if (c >= ncand) break;
-            score_candidate_half(db, sc, cur[c], sv, recs + c);
-#else
-            uint32_t c = 0;
-            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(smem_u32(&s_next)) : "memory");   // plain ATOMS: no warp-aggregation prologue
-            c = __shfl_sync(0xffffffffu, c, 0);
-            if (c >= ncand) break;
-            score_candidate_warp(db, sc, cur[c], sv, recs + c, nullptr);
-#endif
-        }
         if (tid == 0) s_nvalid = 0;
-        __syncthreads();
-        if (tid < ncand) finalize_rec(sc, recs[tid]);
-        if (tid == 0) s_next = 0;
+        score_candidates_flat(db, sc, cur, ncand, sv, hdr, t_term, t_int, t_mask, sc.score_tile, recs, hkey, s_scan);
         __syncthreads();
         if (quick_mode == 2) {
             // Scorer::quick_score, low-memory branch (scoring.rs:270-290): bounded_min_heapify(score_vector, report_psms) compares Score
@@ -1608,11 +1662,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, 12) k_score(DbView db, ScorerVi
         if (tid < ncand) {
             my_floats = 2 * recs[tid].plen + 2;
             if (recs[tid].valid) {
-                const double h = recs[tid].hyperscore;
+                const double h = hkey[tid];   // == hyperscore; entries below min_matched_peaks hold -inf and never count
                 uint32_t pos = 0;
                 for (uint32_t j = 0; j < ncand; j++) {
-                    if (!recs[j].valid) continue;
-                    const double hj = recs[j].hyperscore;
+                    const double hj = hkey[j];
                     pos += (hj > h) || (hj == h && j < tid);
                 }
                 order[pos] = tid;
@@ -1632,7 +1685,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 12) k_score(DbView db, ScorerVi
             const double next = tid + 1 < nvalid ? recs[order[tid + 1]].hyperscore : 0.0;
             const double best = recs[order[0]].hyperscore;
             const uint32_t k = (r.matched_b + r.matched_y) & 0xFFFF;
-            const double log10_poisson = ((double)k * log(lambda) - lambda - lnfact(sc, k)) / 2.302585092994045684;
+            const double log10_poisson = ((double)k * ref_ln(sc, lambda) - lambda - lnfact(sc, k)) / 2.302585092994045684;
             const float precursor_mass = __fmul_rn(mzp, (float)r.charge);
             const float iso = __fmul_rn((float)r.iso, NEUTRON);
             const float mono = db.pep_mono[r.peptide];

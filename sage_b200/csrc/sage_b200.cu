@@ -460,6 +460,58 @@ extern "C" int sage_b200_db_export_index(const sage_b200_db* db, uint32_t* fragm
     return 0;
 }
 
+// Dynamic shared-memory opt-in of the kernels that need more than 48 KB: set ONCE per device to the device maximum (the attribute is per-function,
+// per-device state; setting it per launch to the launch's own size would let two scorers with different shapes undo each other's setting).
+static int ensure_kernel_attributes(int device) {
+    static std::mutex mu;
+    static bool done[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device >= 0 && device < 64 && done[device]) return 0;
+    int optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    auto raise = [&](const void* fn) -> cudaError_t {   // dynamic limit = opt-in maximum minus the kernel's static shared memory
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    };
+    CUDA_TRY(raise((const void*)k_prelim_narrow));
+    CUDA_TRY(raise((const void*)k_replay));
+    CUDA_TRY(raise((const void*)k_prelim_wide));
+    CUDA_TRY(raise((const void*)k_score));
+    CUDA_TRY(raise((const void*)k_process_ms2));
+    if (device >= 0 && device < 64) done[device] = true;
+    return 0;
+}
+
+// Which build of glibc's log() is the host libm (glibc_log.cuh)? Both variants are evaluated on the CPU and compared with std::log bit for bit
+// on a few thousand inputs of the kinds the path feeds it: hyperscore products, lambda, arguments near 1 (the only region where the two
+// variants differ). Returns 0 (FMA-contracted), 1 (plain), or -1 when neither matches (non-glibc libm: the device then uses variant 0 and
+// hyperscore / poisson agree with the host to <= 1 ulp instead of bit for bit).
+extern "C" int sage_b200_host_log_variant(void) {
+    static int cached = -2;
+    if (cached != -2) return cached;
+    uint64_t st = 0x9E3779B97F4A7C15ull;
+    auto next = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    bool ok[2] = {true, true};
+    for (int i = 0; i < 6000; i++) {
+        const uint64_t u = next();
+        double x;
+        switch (i % 3) {
+            case 0: x = (double)((float)(u & 0xffffff) * 0.37f + 1.0f) * (double)((float)((u >> 24) & 0xffffff) * 1.91f + 1.0f); break;
+            case 1: x = 0.93 + (double)(u >> 11) * 0x1p-53 * 0.15; break;
+            default: x = (double)(u >> 11) * 0x1p-53 * 64.0; break;
+        }
+        volatile double vx = x;   // keep the compiler from folding std::log
+        const double ref = std::log(vx);
+        const double a = glog::glibc_log<true>(x), b = glog::glibc_log<false>(x);
+        if (memcmp(&a, &ref, 8)) ok[0] = false;
+        if (memcmp(&b, &ref, 8)) ok[1] = false;
+    }
+    cached = ok[0] ? 0 : (ok[1] ? 1 : -1);
+    return cached;
+}
+
 // ------------------------------------------------------------------------------------------------ scorer
 struct ChunkState {
     bool loaded = false;
@@ -534,6 +586,7 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     if (p->precursor_tol.kind < 0 || p->precursor_tol.kind > 2 || p->fragment_tol.kind < 0 || p->fragment_tol.kind > 2) return fail(SAGE_B200_EINVAL, "bad tolerance kind");
     if (p->score_type > 1) return fail(SAGE_B200_EINVAL, "bad score_type");
     CUDA_TRY(cudaSetDevice(db->device));
+    { int rc_attr = ensure_kernel_attributes(db->device); if (rc_attr) return rc_attr; }
     sage_b200_scorer* s = new sage_b200_scorer();
     s->db = db;
     s->params = *p;
@@ -573,6 +626,9 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
         v.lnfact_tab = s->d_lnfact.as<double>();
         v.lnfact_n = N;
     }
+    v.log_variant = (uint32_t)std::max(0, sage_b200_host_log_variant());
+    v.score_tile = SCORE_TILE_DEFAULT;
+    if (const char* e = getenv("SAGE_B200_SCORE_TILE")) v.score_tile = (uint32_t)std::min(8192, std::max(128, atoi(e))) & ~127u;
     if (const char* e = getenv("SAGE_B200_SORT")) s->sort_spectra = atoi(e);
     for (Lane& L : s->lanes) {
         CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
@@ -608,6 +664,16 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
         if (value < 0) return fail(SAGE_B200_EINVAL, "worklist_reset takes a non-negative entry count");
         s->nlist_per_spectrum = (double)value;
         s->wide_per_spectrum = 0.0;
+        return 0;
+    }
+    if (!strcmp(name, "score_tile")) {  // tasks per shared-memory tile of k_score's flattened candidate scoring (tests use small tiles to cross tile borders)
+        if (value < 128 || value > 8192 || (value & 127)) return fail(SAGE_B200_EINVAL, "score_tile must be a multiple of 128 in 128..8192");
+        s->sv.score_tile = (uint32_t)value;
+        return 0;
+    }
+    if (!strcmp(name, "log_variant")) {  // test hook: 0 = glibc log() as built with FMA contraction, 1 = without (default: whichever the host libm is)
+        if (value < 0 || value > 1) return fail(SAGE_B200_EINVAL, "log_variant must be 0 or 1");
+        s->sv.log_variant = (uint32_t)value;
         return 0;
     }
     if (!strcmp(name, "pep_cap")) {  // 0 (default) = always probe the fragment index (reference loop order)
@@ -700,7 +766,8 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
             h_ims[i] = sp->inverse_ion_mobility ? sp->inverse_ion_mobility[c0 + i] : NAN;
         }
         memcpy(hs + C.o_chg, sp->precursor_charge + c0, n);
-        C.smem = (size_t)(C.pmax + 4) * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + 2 * SPEC_LUT_CELLS + C.pmax + 16;
+        C.smem = (size_t)(C.pmax + 4) * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + 2 * SPEC_LUT_CELLS + C.pmax + 16   // peaks, lists, records, LUT, marks
+                 + (size_t)(sv.kparam + 1) * sizeof(CandHdr) + (size_t)sv.kparam * 8 + (size_t)sv.score_tile * 8 + sv.score_tile / 8 + 16;      // score_candidates_flat
         if (C.smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", C.pmax);
         C.nitems = (size_t)n * sv.qmax;
         if (C.nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
@@ -789,7 +856,6 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     if (mfc - 1 > 8) pep_smem = 200 * 1024;
     if (pep_smem > 96 * 1024) { svq.pep_cap = 0; pep_smem = 0; }
     if (svq.pep_cap == 0) pep_smem = 0;
-    if (pep_smem > 24 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_prelim_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pep_smem));
     uint32_t *sk_in = nullptr, *sk_out = nullptr, *sv_in = nullptr, *sv_out = nullptr;
     int sort_bits = 1;   // keys are PeptideIx < n_pep (spectra without a query sort last within those bits: the order only matters for locality)
     while (sort_bits < 32 && (db->v.n_pep >> sort_bits)) sort_bits++;
@@ -829,7 +895,6 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
 
     // ---- preliminary scoring. Both kernels are always queued: CTAs whose query belongs to the other kernel (or to nobody) exit at once.
     const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
-    CUDA_TRY(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
     k_prelim_narrow_warp<<<dim3((n + WARPQ_WARPS - 1) / WARPQ_WARPS, sv.qmax), WARPQ_WARPS * 32, 0, st>>>(db->v, svq, bv, L.d_nlist.as<uint64_t>());
     CUDA_TRY(cudaGetLastError());
     k_prelim_narrow<<<(unsigned)std::min<uint64_t>(C.nitems, (uint64_t)db->sm_count * 6), PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>());
@@ -841,7 +906,6 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     launches += 3;
     if (C.wide_cap) {
         const int ctas = (int)std::min<uint64_t>((uint64_t)db->sm_count, C.wide_cap);
-        CUDA_TRY(cudaFuncSetAttribute(k_prelim_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WideSmem)));
         k_prelim_wide<<<ctas, WIDE_THREADS, sizeof(WideSmem), st>>>(db->v, sv, bv, (uint32_t)C.nitems, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>());
         CUDA_TRY(cudaGetLastError());
         k_replay<<<(unsigned)((C.wide_cap + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(
@@ -853,7 +917,6 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
 
     // ---- candidate scoring + feature assembly (first reader of the intensities)
     CUDA_TRY(cudaStreamWaitEvent(st, L.ev_intens, 0));
-    CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));
     k_score<<<n, SCORE_THREADS, C.smem, st>>>(db->v, sv, bv, L.d_features.as<FeatureOut>(), L.d_counts.as<uint32_t>(), C.pmax,
                                              dbg ? L.d_dbgk.as<uint64_t>() : nullptr, dbg ? L.d_dbgm.as<uint32_t>() : nullptr,
                                              annotate ? L.d_frags.as<FragmentOut>() : nullptr, (unsigned long long)S->frag_cap, S->quick_mode,
@@ -1232,7 +1295,7 @@ extern "C" int sage_b200_process_spectra(int device, const sage_b200_processor_p
     if (npk) { TRY_P(cudaMemcpy(d_mz, raw->mz + pk0, 4 * npk, cudaMemcpyHostToDevice)); TRY_P(cudaMemcpy(d_int, raw->intensity + pk0, 4 * npk, cudaMemcpyHostToDevice)); }
     TRY_P(cudaMemcpy(d_chg, raw->precursor_charge, n, cudaMemcpyHostToDevice));
     ProcParams pp{(uint32_t)std::min<uint64_t>(pr->take_top_n, 0xFFFFFFFFull), pr->deisotope ? 1u : 0u, pr->min_deisotope_mz};
-    TRY_P(cudaFuncSetAttribute(k_process_ms2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc_attr = ensure_kernel_attributes(device); if (rc_attr) { cleanup(); return rc_attr; } }
     k_process_ms2<<<(unsigned)n, 32, smem>>>(pp, (uint32_t)n, (const uint32_t*)d_off, (const float*)d_mz, (const float*)d_int, (const uint8_t*)d_chg, pmax, p2,
                                             (float*)d_om, (float*)d_oi, (uint32_t*)d_cnt, (float*)d_tic);
     TRY_P(cudaGetLastError());
@@ -1283,6 +1346,30 @@ extern "C" int sage_b200_find_reporter_ions(int device, uint64_t n, const uint64
     TRY_R(cudaMemcpy(out, d_o, 4 * total, cudaMemcpyDeviceToHost));
 #undef TRY_R
     cleanup();
+    return 0;
+}
+
+__global__ void k_device_log(int variant, const double* x, uint64_t n, double* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = glog::glibc_log_v(x[i], variant);
+}
+extern "C" int sage_b200_device_log(int device, int variant, const double* x, uint64_t n, double* out) {
+    if (n == 0) return 0;
+    if (!x || !out || variant < 0 || variant > 1) return fail(SAGE_B200_EINVAL, "device_log: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SAGE_B200_ECUDA, "no CUDA device available: sage_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(SAGE_B200_EINVAL, "device out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    double *dx = nullptr, *dy = nullptr;
+    CUDA_TRY(cudaMalloc(&dx, 8 * n));
+    if (cudaMalloc(&dy, 8 * n) != cudaSuccess) { cudaFree(dx); return fail(SAGE_B200_ECUDA, "device_log: cudaMalloc failed"); }
+    cudaError_t e = cudaMemcpy(dx, x, 8 * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_device_log<<<(unsigned)((n + 255) / 256), 256>>>(variant, dx, n, dy);
+        e = cudaMemcpy(out, dy, 8 * n, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dx); cudaFree(dy);
+    if (e != cudaSuccess) return fail(SAGE_B200_ECUDA, "device_log failed: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -1,5 +1,8 @@
 """Shared helpers for the parity tests: build the oracle DB and the device DB from the same peptide table, and compare
-Feature tables field by field (bit-exact for integer/f32 fields, 1e-6 relative for the f64 log-based scores)."""
+Feature tables field by field. Integer and f32 fields are always compared bit for bit. The f64 scores (hyperscore, delta_next,
+delta_best, poisson) are compared BIT FOR BIT too whenever the library reports that it reproduces this host's libm log()
+(sage_b200_host_log_variant() >= 0: the kernels evaluate glibc's algorithm, glibc_log.cuh); only the OpenMS score type (f32 log1p)
+and hosts with an unknown libm fall back to north_star's 1e-6 relative tolerance."""
 import numpy as np
 
 from oracle import oracle as O
@@ -39,7 +42,14 @@ def bits(a):
     return a
 
 
-def assert_features_equal(gf, gc, of, oc, report_psms, what=""):
+def f64_exact_default():
+    from sage_b200 import api
+    return api.host_log_variant() >= 0
+
+
+def assert_features_equal(gf, gc, of, oc, report_psms, what="", f64_exact=None):
+    if f64_exact is None:
+        f64_exact = f64_exact_default()
     assert np.array_equal(gc, oc), f"{what}: PSM counts differ at spectra {np.nonzero(gc != oc)[0][:10]}"
     n = len(gc)
     sel = (np.arange(n * report_psms) % report_psms) < np.repeat(gc, report_psms)
@@ -56,8 +66,12 @@ def assert_features_equal(gf, gc, of, oc, report_psms, what=""):
             raise AssertionError(f"{what}: field {f} differs at rows {bad}: gpu={a[bad]} oracle={b[bad]} (spectra {g['spectrum'][bad]})")
     for f in F64_FIELDS:
         a, b = g[f], o[f]
-        ok = np.isclose(a, b, rtol=F64_RTOL, atol=F64_ATOL) | (a == b) | (np.isnan(a) & np.isnan(b))
+        if f64_exact:
+            ok = (np.ascontiguousarray(a).view(np.uint64) == np.ascontiguousarray(b).view(np.uint64)) | (np.isnan(a) & np.isnan(b))
+        else:
+            ok = np.isclose(a, b, rtol=F64_RTOL, atol=F64_ATOL) | (a == b) | (np.isnan(a) & np.isnan(b))
         if not np.all(ok):
             bad = np.nonzero(~ok)[0][:5]
-            raise AssertionError(f"{what}: field {f} differs at rows {bad}: gpu={a[bad]} oracle={b[bad]}")
+            raise AssertionError(f"{what}: field {f} differs at rows {bad} ({'bit-exact' if f64_exact else 'rtol 1e-6'} compare, {int((~ok).sum())} rows): "
+                                 f"gpu={[float(x).hex() for x in a[bad]]} oracle={[float(x).hex() for x in b[bad]]}")
     return int(sel.sum())

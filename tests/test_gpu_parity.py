@@ -29,7 +29,8 @@ def run_both(odb, gdb, spectra, pep_caps=(2048, 0), **kw):
         if cap is not None:
             sc.set_option("pep_cap", cap)
         gf, gc = sc.score_batch(spectra)
-        n = assert_features_equal(gf, gc, of, oc, kw.get("report_psms", 1), what=str({"pep_cap": cap, **{k: v for k, v in kw.items() if "tol" not in k}}))
+        n = assert_features_equal(gf, gc, of, oc, kw.get("report_psms", 1), what=str({"pep_cap": cap, **{k: v for k, v in kw.items() if "tol" not in k}}),
+                                  f64_exact=None if kw.get("score_type", 0) == 0 else False)   # OpenMS: f32 log1p, not reproduced bit for bit
     return sc, n, octr
 
 
