@@ -175,6 +175,11 @@ int sage_b200_score_batch(sage_b200_scorer* scorer, const sage_b200_spectra* spe
 int sage_b200_score_batch_multi(sage_b200_scorer* const* scorers, int n_scorers, const sage_b200_spectra* spectra, sage_b200_feature* features,
                                 uint32_t* counts);
 
+/* Pins the calling host thread to the CPUs of the NUMA node next to `device` (PCI topology from sysfs): call it on the thread that will
+ * allocate pinned buffers for and submit batches to that GPU (score_batch_multi does it for its own worker threads; a rayon pool would do it in
+ * its start handler). Returns the NUMA node, or -1 when the topology is unknown (nothing changed). */
+int sage_b200_bind_thread_to_device(int device);
+
 /* Scorer::quick_score over a batch (scoring.rs:255-298; prefilter of runner.rs:143-278). keep has one byte per peptide of the db and is
  * OR-ed (the reference stores `true` into &[AtomicBool]). prefilter_low_memory selects the branch of scoring.rs:270. */
 int sage_b200_quick_score(sage_b200_scorer* scorer, const sage_b200_spectra* spectra, int prefilter_low_memory, uint8_t* keep);
@@ -218,7 +223,9 @@ int sage_b200_find_reporter_ions(int device, uint64_t n, const uint64_t* peak_of
  * 0 = x86-64 glibc on a CPU with FMA+AVX2 (`__log_fma`), 1 = the uncontracted build (`__log_sse2`/`__log_avx`, musl, aarch64),
  * -1 = neither matched std::log on the probe inputs (the device then uses variant 0; f64 fields agree to <= 1 ulp). */
 int sage_b200_host_log_variant(void);
-/* Test hook: out[i] = the device's evaluation of log(x[i]) with `variant` (0/1) — compared bit for bit with the host libm by tests/test_glibc_log.py. */
+/* 1 when the host libm's log1pf (Rust's f32::ln_1p: OpenMS hyperscore, scoring.rs:190-197) is the glibc / fdlibm function the kernels reproduce. */
+int sage_b200_host_log1pf_exact(void);
+/* Test hook: out[i] = the device's evaluation of log(x[i]) with `variant` (0/1), or of (double)log1pf((float)x[i]) with variant 2 — compared bit for bit with the host libm by tests/test_glibc_log.py. */
 int sage_b200_device_log(int device, int variant, const double* x, uint64_t n, double* out);
 
 /* Page-locked host buffers: spectra/feature arrays placed here are copied by DMA without a staging memcpy. */

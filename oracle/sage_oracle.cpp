@@ -25,6 +25,7 @@
 // Each function cites the reference file:line it follows (paths relative to
 // /root/reference/crates/sage/src unless stated).
 
+#include <parallel/algorithm>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -623,17 +624,20 @@ static void build_from_peptides(DB& db, std::vector<Peptide>&& peptides, const B
             }
         }
     }
-    // par_sort_unstable_by fragment_mz total_cmp. Tie order is unobservable through
-    // page_search (pure set semantics), we use (mz, peptide) for determinism.
-    std::sort(db.fragments.begin(), db.fragments.end(), [](const Theoretical& a, const Theoretical& b) {
+    // par_sort_unstable_by fragment_mz total_cmp (rayon: parallel here too, the order is total so the result does not depend on the
+    // schedule). Tie order is unobservable through page_search (pure set semantics), we use (mz, peptide) for determinism.
+    __gnu_parallel::sort(db.fragments.begin(), db.fragments.end(), [](const Theoretical& a, const Theoretical& b) {
         int c = total_cmp(a.fragment_mz, b.fragment_mz);
         if (c) return c < 0;
         return a.peptide_index < b.peptide_index;
     });
-    db.min_value.clear();
-    for (size_t s = 0; s < db.fragments.size(); s += db.bucket_size) {
+    const size_t nb = (db.fragments.size() + db.bucket_size - 1) / db.bucket_size;
+    db.min_value.assign(nb, 0.0f);
+#pragma omp parallel for schedule(dynamic, 64)   // par_chunks_mut(bucket_size) (database.rs:337-346)
+    for (long long bi = 0; bi < (long long)nb; bi++) {
+        size_t s = (size_t)bi * db.bucket_size;
         size_t e = std::min(db.fragments.size(), s + db.bucket_size);
-        db.min_value.push_back(db.fragments[s].fragment_mz);
+        db.min_value[bi] = db.fragments[s].fragment_mz;
         std::stable_sort(db.fragments.begin() + s, db.fragments.begin() + e,
                          [](const Theoretical& a, const Theoretical& b) { return a.peptide_index < b.peptide_index; });
     }
@@ -897,7 +901,7 @@ struct Scorer {  // :210-232
         const Peptide& pep = db->peptides[score.peptide];
         uint8_t mfc = so::max_fragment_charge(max_fragment_charge, score.precursor_charge);
         Run b_run, y_run;
-        std::vector<float> ions;
+        static thread_local std::vector<float> ions;   // the reference's IonSeries is an iterator: no allocation per candidate
         if (ctr) { ctr->candidates_scored++; ctr->peptide_record_floats += 2 * pep.sequence.size() + 2; }
         for (int kind : db->ion_kinds) {
             ion_series(pep, kind, ions);

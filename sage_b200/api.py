@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = [
     "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_scorer_set_option", "sage_b200_score_batch", "sage_b200_batch_upload", "sage_b200_batch_run",
     "sage_b200_batch_download", "sage_b200_score_batch_multi", "sage_b200_quick_score", "sage_b200_initial_hits", "sage_b200_counters_get",
     "sage_b200_process_spectra", "sage_b200_find_reporter_ions", "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
-    "sage_b200_host_log_variant", "sage_b200_device_log",
+    "sage_b200_host_log_variant", "sage_b200_host_log1pf_exact", "sage_b200_device_log", "sage_b200_bind_thread_to_device",
 ]
 
 _lib = None
@@ -133,9 +133,19 @@ def device_count() -> int:
     return int(load_library().sage_b200_device_count())
 
 
+def bind_thread_to_device(device: int) -> int:
+    """Pins the calling thread to the CPUs of the GPU's NUMA node (-1: topology unknown, nothing changed)."""
+    return int(load_library().sage_b200_bind_thread_to_device(C.c_int(device)))
+
+
 def host_log_variant() -> int:
     """Which build of glibc's log() the host libm is (0 FMA-contracted, 1 plain, -1 unknown); the kernels reproduce that one (glibc_log.cuh)."""
     return int(load_library().sage_b200_host_log_variant())
+
+
+def host_log1pf_exact() -> bool:
+    """True when the host libm's log1pf is the function the kernels reproduce for the OpenMS score type."""
+    return bool(load_library().sage_b200_host_log1pf_exact())
 
 
 def device_log(x: np.ndarray, variant: int, device: int = 0) -> np.ndarray:

@@ -32,5 +32,26 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return _OUT
 
 
+_SYNTH_SRC = os.path.join(_PKG, "csrc", "synth_expand.cpp")
+_SYNTH_OUT = os.path.join(_PKG, "lib", "libsage_synth.so")
+
+
+def synth_library_path() -> str:
+    return _SYNTH_OUT
+
+
+def build_synth_library(force: bool = False) -> str:
+    """Host-only helper of synth.py (synthetic benchmark / test data; no CUDA, not on the search path)."""
+    os.makedirs(os.path.dirname(_SYNTH_OUT), exist_ok=True)
+    if not force and os.path.exists(_SYNTH_OUT) and os.path.getmtime(_SYNTH_OUT) >= os.path.getmtime(_SYNTH_SRC):
+        return _SYNTH_OUT
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    subprocess.check_call(["/usr/bin/g++", "-O3", "-std=c++17", "-fopenmp", "-shared", "-fPIC", "-o", _SYNTH_OUT, _SYNTH_SRC], env=env)
+    return _SYNTH_OUT
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
+    print(build_synth_library(force=True))

@@ -17,7 +17,14 @@ constexpr int SCORE_THREADS = 128;  // measured on cfg2: 128 (1.66 ms) beats 256
 #define SAGE_B200_SCORE_MIN_CTAS 8
 #endif
 constexpr int SCORE_MIN_CTAS = SAGE_B200_SCORE_MIN_CTAS;   // k_score CTAs per SM the register budget is held to (A/B: profiles/r02_*)
-constexpr uint32_t SCORE_TILE_DEFAULT = 2048;              // tasks (theoretical-fragment lookups) per shared-memory tile of k_score
+#ifndef SAGE_B200_SCORE_TILE
+#define SAGE_B200_SCORE_TILE 1024
+#endif
+#ifndef SAGE_B200_SCORE_UNROLL
+#define SAGE_B200_SCORE_UNROLL 1
+#endif
+constexpr uint32_t SCORE_UNROLL = SAGE_B200_SCORE_UNROLL;   // tasks per lane and iteration of k_score's phase B (1 or 2; measured, profiles/r02_*)
+constexpr uint32_t SCORE_TILE = SAGE_B200_SCORE_TILE;      // tasks (theoretical-fragment lookups) per shared-memory tile of k_score (multiple of 256)
 constexpr int MAX_KINDS = 6;
 // k_prelim_narrow_warp: measured on cfg2 (prelim ms): cap 1024 x 2 warps x 24 CTAs/SM 1.04 | cap 512 1.09 | cap 256 1.35 | cap 2048 1.60 (its
 // 192 KB of shared memory per SM leaves too little L1 for the index lines) | 4 warps 1.06 | 8 warps 1.08
@@ -221,7 +228,7 @@ struct ScorerView {
     const double* lnfact_tab;  // lnfact(n) for n < lnfact_n, computed on the host with libm log (scoring.rs:170-177)
     uint32_t lnfact_n;
     uint32_t log_variant;      // which build of glibc's log() the device reproduces (glibc_log.cuh): 0 = FMA-contracted, 1 = plain
-    uint32_t score_tile;       // tasks per tile of score_candidates_flat (multiple of 128)
+    uint32_t score_fast;       // 1 (default): straight-line task body of k_score where its preconditions hold; 0: always the generic body (tests)
 };
 
 struct BatchView {

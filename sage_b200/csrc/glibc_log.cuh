@@ -147,6 +147,94 @@ SB_HD double glibc_log(double x) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// log1pf(x) exactly as glibc computes it (sysdeps/ieee754/flt-32/s_log1pf.c, the fdlibm algorithm; x86-64 glibc ships ONE build of it, plain
+// SSE arithmetic without contraction — checked against the disassembly of Ubuntu GLIBC 2.39's __log1pf). Rust's f32::ln_1p, which the reference's
+// OpenMS hyperscore uses (scoring.rs:190-197), is this function. tests/test_glibc_log.py compares the host evaluation below with libm's
+// log1pf on EVERY float (2^32 inputs), and the device evaluation on a sample.
+#if defined(__CUDA_ARCH__)
+SB_HD float gf_add(float a, float b) { return __fadd_rn(a, b); }
+SB_HD float gf_sub(float a, float b) { return __fsub_rn(a, b); }
+SB_HD float gf_mul(float a, float b) { return __fmul_rn(a, b); }
+SB_HD float gf_div(float a, float b) { return __fdiv_rn(a, b); }
+SB_HD int32_t gf_bits(float x) { return __float_as_int(x); }
+SB_HD float gf_flt(int32_t u) { return __int_as_float(u); }
+#else
+SB_HD float gf_add(float a, float b) { volatile float r = a + b; return r; }
+SB_HD float gf_sub(float a, float b) { volatile float r = a - b; return r; }
+SB_HD float gf_mul(float a, float b) { volatile float r = a * b; return r; }
+SB_HD float gf_div(float a, float b) { volatile float r = a / b; return r; }
+SB_HD int32_t gf_bits(float x) { int32_t u; memcpy(&u, &x, 4); return u; }
+SB_HD float gf_flt(int32_t u) { float x; memcpy(&x, &u, 4); return x; }
+#endif
+
+SB_HD float glibc_log1pf(float x) {
+    const float ln2_hi = gf_flt(0x3f317180), ln2_lo = gf_flt(0x3717f7d1);
+    const float Lp1 = gf_flt(0x3f2aaaab), Lp2 = gf_flt(0x3ecccccd), Lp3 = gf_flt(0x3e924925), Lp4 = gf_flt(0x3e638e29), Lp5 = gf_flt(0x3e3a3325),
+                Lp6 = gf_flt(0x3e1cd04f), Lp7 = gf_flt(0x3e178897);
+    const int32_t hx = gf_bits(x), ax = hx & 0x7fffffff;
+    int32_t k = 1, hu = 0;
+    float f = 0.0f, c = 0.0f, u;
+    if (hx < 0x3ed413d7) {                       // x < 0.41422
+        if (ax >= 0x3f800000) {                  // x <= -1.0
+            if (x == -1.0f) return gf_flt((int32_t)0xff800000);   // log1p(-1) = -inf
+            return gf_flt(0x7fc00000);           // log1p(x < -1) = NaN (sign / payload not reproduced)
+        }
+        if (ax < 0x31000000) {                   // |x| < 2^-29
+            if (ax < 0x24800000) return x;       // |x| < 2^-54
+            return gf_sub(x, gf_mul(gf_mul(x, x), 0.5f));
+        }
+        if (hx > 0 || hx <= (int32_t)0xbe95f61f) { k = 0; f = x; hu = 1; }   // -0.2929 < x < 0.41422
+    }
+    if (hx >= 0x7f800000) return gf_add(x, x);
+    if (k != 0) {
+        if (hx < 0x5a000000) {
+            u = gf_add(1.0f, x);
+            hu = gf_bits(u);
+            k = (hu >> 23) - 127;
+            c = k > 0 ? gf_sub(1.0f, gf_sub(u, x)) : gf_sub(x, gf_sub(u, 1.0f));   // correction term
+            c = gf_div(c, u);
+        } else {
+            u = x;
+            hu = gf_bits(u);
+            k = (hu >> 23) - 127;
+            c = 0.0f;
+        }
+        hu &= 0x007fffff;
+        if (hu < 0x3504f7) {
+            u = gf_flt(hu | 0x3f800000);         // normalize u
+        } else {
+            k += 1;
+            u = gf_flt(hu | 0x3f000000);         // normalize u / 2
+            hu = (0x00800000 - hu) >> 2;
+        }
+        f = gf_sub(u, 1.0f);
+    }
+    const float hfsq = gf_mul(gf_mul(0.5f, f), f);
+    const float kf = (float)k;
+    if (hu == 0) {                               // |f| < 2^-20
+        if (f == 0.0f) {
+            if (k == 0) return 0.0f;
+            c = gf_add(c, gf_mul(kf, ln2_lo));
+            return gf_add(gf_mul(kf, ln2_hi), c);
+        }
+        const float R = gf_mul(hfsq, gf_sub(1.0f, gf_mul(Lp1, f)));   // (float)0.66666666666666666 == Lp1
+        if (k == 0) return gf_sub(f, R);
+        return gf_sub(gf_mul(kf, ln2_hi), gf_sub(gf_sub(R, gf_add(gf_mul(kf, ln2_lo), c)), f));
+    }
+    const float s = gf_div(f, gf_add(2.0f, f));
+    const float z = gf_mul(s, s);
+    float R = gf_mul(z, Lp7);
+    R = gf_mul(z, gf_add(Lp6, R));
+    R = gf_mul(z, gf_add(Lp5, R));
+    R = gf_mul(z, gf_add(Lp4, R));
+    R = gf_mul(z, gf_add(Lp3, R));
+    R = gf_mul(z, gf_add(Lp2, R));
+    R = gf_mul(z, gf_add(Lp1, R));
+    if (k == 0) return gf_sub(f, gf_sub(hfsq, gf_mul(s, gf_add(hfsq, R))));
+    return gf_sub(gf_mul(kf, ln2_hi), gf_sub(gf_sub(hfsq, gf_add(gf_mul(s, gf_add(hfsq, R)), gf_add(gf_mul(kf, ln2_lo), c))), f));
+}
+
 SB_HD double glibc_log_v(double x, int variant) { return variant == 1 ? glibc_log<false>(x) : glibc_log<true>(x); }
 
 }}  // namespace sb::glog

@@ -169,26 +169,29 @@ __device__ __forceinline__ void lut_build(const float* arr, uint32_t n, const Lu
         start[c] = (uint16_t)lo;
     }
 }
-// Same table for an ASCENDING array in O(cells + n): with cell(m) = max{c : c == 0 or edge(c) <= m}, arr[i] < edge(c) <=> cell(arr[i]) < c
-// (edges are monotone in c), so start[c] = first i with cell(arr[i]) >= c: element j fills the cells in (cell(arr[j-1]), cell(arr[j])].
-__device__ __forceinline__ void lut_build_sorted(const float* arr, uint32_t n, const LutParams& L, uint16_t* start, uint32_t t0, uint32_t stride,
-                                                 uint32_t cells) {
+// Same table for an ASCENDING array that carries a +inf sentinel at arr[n]: every thread owns a run of consecutive cells, finds the first
+// one's count by binary search and walks forward for the others (start[c] is non-decreasing in c). O(cells / threads * log n + n) per thread
+// with uniform trip counts; the values are those of lut_build by construction (same edge expression, same `<`).
+__device__ __forceinline__ void lut_build_walk(const float* arr, uint32_t n, const LutParams& L, uint16_t* start, uint32_t t0, uint32_t stride,
+                                               uint32_t cells) {
+    const uint32_t per = (cells + stride - 1) / stride;
+    const uint32_t c0 = t0 * per, c1 = min(cells, c0 + per);
     if (!(L.inv_w > 0.0f)) {
-        for (uint32_t c = t0; c < cells; c += stride) start[c] = 0;
+        for (uint32_t c = c0; c < c1; c++) start[c] = 0;
         return;
     }
-    const float w = 1.0f / L.inv_w;   // lut_edge(L, c) == L.base + (float)c * w
-    auto cell_of = [&](float m) -> int {
-        const float t = (m - L.base) * L.inv_w;
-        int c = t > 0.0f ? (int)fminf(t, (float)(cells - 1)) : 0;
-        while (c + 1 < (int)cells && L.base + (float)(c + 1) * w <= m) c++;
-        while (c > 0 && L.base + (float)c * w > m) c--;
-        return c;
-    };
-    for (uint32_t j = t0; j <= n; j += stride) {
-        const int c_prev = j == 0 ? -1 : cell_of(arr[j - 1]);
-        const int c_here = j == n ? (int)cells - 1 : cell_of(arr[j]);
-        for (int c = c_prev + 1; c <= c_here; c++) start[c] = (uint16_t)j;
+    if (c0 >= c1) return;
+    uint32_t i = 0;
+    if (c0 > 0) {
+        const float e = lut_edge(L, c0);
+        uint32_t hi = n;
+        while (i < hi) { const uint32_t m = (i + hi) >> 1; if (arr[m] < e) i = m + 1; else hi = m; }
+    }
+    start[c0] = (uint16_t)i;
+    for (uint32_t c = c0 + 1; c < c1; c++) {
+        const float e = lut_edge(L, c);
+        while (arr[i] < e) i++;   // arr[n] = +inf stops the walk
+        start[c] = (uint16_t)i;
     }
 }
 // A position s with arr[i] < x for all i < s (conservative: one cell early to absorb float rounding of the cell index).
@@ -1173,9 +1176,9 @@ __device__ __forceinline__ double hyperscore_of(const ScorerView& sc, uint32_t m
         const double i = (double)__fadd_rn(sb, 1.0f) * (double)__fadd_rn(sy, 1.0f);
         s = ref_ln(sc, i) + lnfact(sc, mb) + lnfact(sc, my);
     } else {
-        // f32::ln_1p is libm's log1pf; CUDA's f64 log1p rounded to f32 agrees except for rare 1-ulp (f32) cases (documented in DESIGN.md)
+        // f32::ln_1p is libm's log1pf: reproduced operation by operation (glibc_log.cuh, checked against glibc on every float)
         const float si = __fadd_rn(sb, sy);
-        s = (double)(float)log1p((double)si) + lnfact(sc, mb) + lnfact(sc, my);
+        s = (double)glog::glibc_log1pf(si) + lnfact(sc, mb) + lnfact(sc, my);
     }
     return isfinite(s) ? s : 255.0;
 }
@@ -1310,17 +1313,58 @@ struct FragmentOut { int32_t kind, charge, ordinal; float intensity, mz_calculat
 // Here the lookups of the <= k candidates are flattened into one task list t = base[c] + f (f = (kind*nions + idx)*nfc + fc-1, the reference's
 // loop order), processed in tiles of `tile` tasks:
 //   phase B  every lane owns one task: candidate header from smem (cursor advanced incrementally, tasks of a lane ascend), theoretical m/z
-//            from the ion table, select_most_intense_peak through the spectrum LUT, ppm term; matched tasks leave (term, intensity) in smem
-//            and one bit in a per-tile mask (warp ballot).
+//            from the ion table, Tolerance::bounds, first peak >= lo through the spectrum LUT. A task whose peak lies inside the window is a
+//            hit: one bit in the per-tile mask (warp ballot) and an entry in the warp's compact hit list.
+//   phase B' the warp walks its hit list densely (about one task in five hits; doing this inside phase B would run the matched branch with
+//            2-3 of 32 lanes): most intense peak of the window (last of equals), ppm term, (term, intensity) to smem.
 //   fold     thread c folds candidate c's matched tasks in ascending f — exactly the reference's order of `ppm_difference +=`, `summed_b/y +=`,
 //            Run::matched — keeping its partial sums in registers from tile to tile (tiles need not align with candidates).
-// Results are bit-identical to score_candidate_warp (same f32 operations in the same order).
+// FAST (uniform per spectrum: LUT usable, ppm fragment tolerance of sane magnitude) is the straight-line version of the task body: division-free
+// bounds and fragment / charge for charges 1..3 (div_const_rn: bit-identical to IEEE division, tests/test_div_const.py), sentinel-terminated
+// scans; tasks outside its preconditions (ion outside [1, 1e20], more than 3 fragment charges) take the generic body. Results are
+// bit-identical to score_candidate_warp either way (same f32 operations in the same order).
 struct __align__(16) CandHdr { uint32_t ion_off, base, next; uint16_t nions; uint8_t nfc, pad; };
 
+__device__ __forceinline__ bool fast_tol_ok(float t) { const float a = fabsf(t); return t == 0.0f || (a >= 1e-9f && a <= 1e6f); }
+
+// Shared-memory tile of score_candidates_flat. Static (compile-time addresses: no base-pointer arithmetic in the task loop).
+struct ScoreTile {
+    CandHdr hdr[K_MAX + 1];        // candidate headers + sentinel
+    double hkey[K_MAX];            // sort keys of build_features (hyperscore, -inf when below min_matched_peaks)
+    float term[SCORE_TILE];        // phase B: m/z of a hit; phase B': its ppm term
+    float inten[SCORE_TILE];       // phase B: index of the first in-window peak; phase B': matched intensity
+    uint32_t mask[SCORE_TILE / 32];
+    uint16_t hits[SCORE_TILE];     // per-warp compact lists of hit slots (bit 15: already final, skip in phase B')
+    uint16_t lut[SPEC_LUT_CELLS];  // spectrum LUT (spectrum_lut_setup)
+    uint32_t scan[SCORE_THREADS / 32];
+};
+
+// One task of phase B, FAST preconditions checked by the caller (nfc <= 3, ion in [1, 1e20]): returns true when the tolerance window of the
+// theoretical fragment holds at least one peak; mz / first in-window peak are left in `mz`, `idx`.
+__device__ __forceinline__ bool fast_task(float ion, uint32_t fc, float tlo, float thi, const SpecView& sp, const uint16_t* lut, const float* pm, float& mz,
+                                          uint32_t& idx) {
+    // scoring.rs:707 fragment / charge: x / 1, x / 2 exact as x, x * 0.5; x / 3 through div_const_rn's two FMAs
+    const float q3 = __fmul_rn(ion, 1.0f / 3.0f);
+    const float third = __fmaf_rn(__fmaf_rn(-q3, 3.0f, ion), 1.0f / 3.0f, q3);
+    mz = fc == 1 ? ion : (fc == 2 ? __fmul_rn(ion, 0.5f) : third);
+    // Tolerance::bounds, ppm (mass.rs:21-35): c + c*t/1e6 with the division as in div_const_rn (|c*t| is inside its proven range)
+    const float pl = __fmul_rn(mz, tlo), ph = __fmul_rn(mz, thi);
+    const float ql = __fmul_rn(pl, 1.0f / 1000000.0f), qh = __fmul_rn(ph, 1.0f / 1000000.0f);
+    const float lo = __fadd_rn(mz, __fmaf_rn(__fmaf_rn(-ql, 1000000.0f, pl), 1.0f / 1000000.0f, ql));
+    const float hi = __fadd_rn(mz, __fmaf_rn(__fmaf_rn(-qh, 1000000.0f, ph), 1.0f / 1000000.0f, qh));
+    // select_most_intense_peak (spectrum.rs:134-159), first half: the first peak >= lo (LUT start one cell early, then the exact values)
+    const float tt = __fmul_rn(__fsub_rn(lo, sp.lp.base), sp.lp.inv_w);
+    const int cc = tt > 1.0f ? (int)fminf(tt, (float)(SPEC_LUT_CELLS - 1)) - 1 : 0;
+    idx = lut[cc];
+    while (pm[idx] < lo) idx++;   // masses[np] = +inf ends the scan
+    return pm[idx] <= hi;
+}
+
+template <bool FAST>
 __device__ __forceinline__ void score_candidates_flat(const DbView& db, const ScorerView& sc, const uint64_t* cur, uint32_t ncand, const SpecView& sp,
-                                                      CandHdr* hdr /*[kparam + 1]*/, float* t_term, float* t_int, uint32_t* t_mask, uint32_t tile,
-                                                      ScoreRec* recs, double* hkey, uint32_t* s_scan /*[SCORE_THREADS / 32]*/) {
+                                                      ScoreTile& S, ScoreRec* recs) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SCORE_THREADS / 32;
+    constexpr uint32_t tile = SCORE_TILE;
     // ---- phase A: candidate headers + exclusive scan of the task counts
     uint64_t key = 0;
     uint32_t L = 0, nions = 0, nfc = 1, total = 0, ion_off = 0;
@@ -1339,64 +1383,140 @@ __device__ __forceinline__ void score_candidates_flat(const DbView& db, const Sc
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= (uint32_t)o) incl += v;
     }
-    if (lane == 31) s_scan[warp] = incl;
+    if (lane == 31) S.scan[warp] = incl;
     __syncthreads();
     uint32_t base = incl - total, T = 0;
 #pragma unroll
     for (uint32_t w = 0; w < nwarps; w++) {
-        const uint32_t x = s_scan[w];
+        const uint32_t x = S.scan[w];
         if (w < warp) base += x;
         T += x;
     }
-    if (tid < ncand) { CandHdr h; h.ion_off = ion_off; h.base = base; h.next = base + total; h.nions = (uint16_t)nions; h.nfc = (uint8_t)nfc; h.pad = 0; hdr[tid] = h; }
-    if (tid == 0) { CandHdr h; h.ion_off = 0; h.base = T; h.next = 0xFFFFFFFFu; h.nions = 0; h.nfc = 1; h.pad = 0; hdr[ncand] = h; }   // sentinel: stops every cursor
+    if (tid < ncand) { CandHdr h; h.ion_off = ion_off; h.base = base; h.next = base + total; h.nions = (uint16_t)nions; h.nfc = (uint8_t)nfc; h.pad = 0; S.hdr[tid] = h; }
+    if (tid == 0) { CandHdr h; h.ion_off = 0; h.base = T; h.next = 0xFFFFFFFFu; h.nions = 0; h.nfc = 1; h.pad = 0; S.hdr[ncand] = h; }   // sentinel: stops every cursor
     // fold state of candidate tid (registers, carried across tiles)
     uint32_t mb = 0, my = 0;
     float sb = 0.f, sy = 0.f, ppm = 0.f;
     Run brun = {0, 0, 0, 0}, yrun = {0, 0, 0, 0};
+    const float tlo = sc.fragment_tol.lo, thi = sc.fragment_tol.hi;
+    const float* const pm = sp.masses;
+    const float* const pi = sp.intens;
+    // generic task body: any tolerance kind, any charge, with or without the LUT; writes the final (term, intensity)
+    auto generic_task = [&](const CandHdr& h, uint32_t f, uint32_t slot) -> bool {
+        uint32_t ki, fc;
+        switch (h.nfc) {
+            case 1: ki = f; fc = 1; break;
+            case 2: ki = f >> 1; fc = (f & 1) + 1; break;
+            case 3: ki = f / 3; fc = f - ki * 3 + 1; break;
+            default: ki = f / h.nfc; fc = f - ki * h.nfc + 1; break;
+        }
+        // scoring.rs:707 fragment / charge: x / 1 and x / 2 are exact as x and x * 0.5 (|x| >= 2^-125)
+        const float ion = __ldg(db.ions + h.ion_off + ki);
+        const float mz = fc == 1 ? ion : (fc == 2 && fabsf(ion) >= 1e-30f) ? __fmul_rn(ion, 0.5f) : __fdiv_rn(ion, (float)fc);
+        const int pk = sp.use_lut ? select_most_intense_peak_lut(pm, pi, sp.np, mz, sc.fragment_tol, sp.lp, S.lut)
+                                  : select_most_intense_peak(pm, pi, sp.np, mz, sc.fragment_tol);
+        if (pk < 0) return false;
+        const float peak_mass = pm[pk], inten = pi[pk];
+        // scoring.rs:719-720: peak_intensity * (mz - peak_mass).abs() * 2E6 / (mz + peak_mass)
+        S.term[slot] = __fdiv_rn(__fmul_rn(__fmul_rn(inten, fabsf(__fsub_rn(mz, peak_mass))), 2E6f), __fadd_rn(mz, peak_mass));
+        S.inten[slot] = inten;
+        return true;
+    };
     for (uint32_t t0 = 0; t0 < T; t0 += tile) {
         const uint32_t tn = min(tile, T - t0);
         __syncthreads();   // headers written / previous tile's fold done with the tile arrays
-        // ---- phase B: each warp takes a contiguous run of the tile (a multiple of 32 slots), lanes = consecutive tasks
-        const uint32_t chunk = (((tn + nwarps - 1) / nwarps) + 31) & ~31u;
-        const uint32_t w_lo = warp * chunk, w_hi = min(tn, w_lo + chunk);
-        uint32_t c = 0;
-        CandHdr h = hdr[0];
+        // ---- phase B: each warp takes a contiguous run of the tile; per iteration a lane owns SCORE_UNROLL tasks 32 apart (with 2: two
+        // independent dependency chains, both ion loads issued before either is used)
+        constexpr uint32_t STEP = 32 * SCORE_UNROLL;
+        const uint32_t chunk = (((tn + nwarps - 1) / nwarps) + STEP - 1) & ~(STEP - 1);
+        const uint32_t w_lo = min(tn, warp * chunk), w_hi = min(tn, w_lo + chunk);
+        uint32_t c = 0, wcount = 0;
+        CandHdr h = S.hdr[0];
         if (w_lo < w_hi) {   // cursor start: largest c with base[c] <= first task of this lane (binary search over the <= 128 headers)
             const uint32_t t_first = t0 + min(w_lo + lane, w_hi - 1);
             uint32_t lo = 0, hi = ncand;   // invariant: base[lo] <= t_first (base[0] = 0), answer in [lo, hi)
-            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (hdr[mid].base <= t_first) lo = mid; else hi = mid; }
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.hdr[mid].base <= t_first) lo = mid; else hi = mid; }
             c = lo;
-            h = hdr[c];
+            h = S.hdr[c];
         }
-        for (uint32_t s0 = w_lo; s0 < w_hi; s0 += 32) {
-            const uint32_t slot = s0 + lane, t = t0 + slot;
-            bool hit = false;
-            if (slot < w_hi) {
-                while (t >= h.next) { c++; h = hdr[c]; }   // skips zero-length candidates; the sentinel's next = 2^32 - 1 > t
-                const uint32_t f = t - h.base;
-                uint32_t ki, fc;
-                switch (h.nfc) {
-                    case 1: ki = f; fc = 1; break;
-                    case 2: ki = f >> 1; fc = (f & 1) + 1; break;
-                    case 3: ki = f / 3; fc = f - ki * 3 + 1; break;
-                    default: ki = f / h.nfc; fc = f - ki * h.nfc + 1; break;
-                }
-                // scoring.rs:707 fragment / charge: x / 1 and x / 2 are exact as x and x * 0.5 (|x| >= 2^-125)
-                const float ion = __ldg(db.ions + h.ion_off + ki);
-                const float mz = fc == 1 ? ion : (fc == 2 && fabsf(ion) >= 1e-30f) ? __fmul_rn(ion, 0.5f) : __fdiv_rn(ion, (float)fc);
-                const int pk = sp.use_lut ? select_most_intense_peak_lut(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol, sp.lp, sp.lut)
-                                          : select_most_intense_peak(sp.masses, sp.intens, sp.np, mz, sc.fragment_tol);
-                if (pk >= 0) {
-                    const float peak_mass = sp.masses[pk], inten = sp.intens[pk];
-                    // scoring.rs:719-720: peak_intensity * (mz - peak_mass).abs() * 2E6 / (mz + peak_mass)
-                    t_term[slot] = __fdiv_rn(__fmul_rn(__fmul_rn(inten, fabsf(__fsub_rn(mz, peak_mass))), 2E6f), __fadd_rn(mz, peak_mass));
-                    t_int[slot] = inten;
-                    hit = true;
+        for (uint32_t s0 = w_lo; s0 < w_hi; s0 += STEP) {
+            const uint32_t slotA = s0 + lane, slotB = slotA + 32;
+            const bool inA = slotA < w_hi, inB = SCORE_UNROLL == 2 && slotB < w_hi;
+            bool hitA = false, hitB = false, finalA = false, finalB = false;   // final: (term, intensity) already written (generic body)
+            // headers of both tasks (the cursor only moves forward: task B lies 32 behind task A of the next iteration)
+            uint32_t fA = 0, fB = 0;
+            CandHdr hA = h, hB = h;
+            if (inA) {
+                const uint32_t t = t0 + slotA;
+                while (t >= h.next) { c++; h = S.hdr[c]; }   // skips zero-length candidates; the sentinel's next = 2^32 - 1 > t
+                hA = h; fA = t - h.base;
+            }
+            if (inB) {
+                const uint32_t t = t0 + slotB;
+                while (t >= h.next) { c++; h = S.hdr[c]; }
+                hB = h; fB = t - h.base;
+            }
+            if (FAST) {
+                // f = (kind*nions + idx)*nfc + fc-1, nfc in 1..3: branch-free decode; both loads in flight before the first use
+                const bool okA = inA && hA.nfc <= 3, okB = inB && hB.nfc <= 3;
+                const uint32_t kiA = hA.nfc == 1 ? fA : (hA.nfc == 2 ? fA >> 1 : __umulhi(fA, 0xAAAAAAABu) >> 1);
+                const uint32_t kiB = hB.nfc == 1 ? fB : (hB.nfc == 2 ? fB >> 1 : __umulhi(fB, 0xAAAAAAABu) >> 1);
+                const float ionA = okA ? __ldg(db.ions + hA.ion_off + kiA) : 0.0f;
+                const float ionB = okB ? __ldg(db.ions + hB.ion_off + kiB) : 0.0f;
+                const bool fastA = okA && ionA >= 1.0f && ionA <= 1e20f, fastB = okB && ionB >= 1.0f && ionB <= 1e20f;
+                float mzA = 0.f, mzB = 0.f;
+                uint32_t idxA = 0, idxB = 0;
+                if (fastA) hitA = fast_task(ionA, fA - kiA * hA.nfc + 1, tlo, thi, sp, S.lut, pm, mzA, idxA);
+                if (fastB) hitB = fast_task(ionB, fB - kiB * hB.nfc + 1, tlo, thi, sp, S.lut, pm, mzB, idxB);
+                if (hitA) { S.term[slotA] = mzA; S.inten[slotA] = __uint_as_float(idxA); }
+                if (hitB) { S.term[slotB] = mzB; S.inten[slotB] = __uint_as_float(idxB); }
+                if (inA && !fastA) hitA = finalA = generic_task(hA, fA, slotA);   // outside the fast preconditions (rare)
+                if (inB && !fastB) hitB = finalB = generic_task(hB, fB, slotB);
+            } else {
+                if (inA) hitA = generic_task(hA, fA, slotA);
+                if (inB) hitB = generic_task(hB, fB, slotB);
+            }
+            const uint32_t ballA = __ballot_sync(0xffffffffu, hitA), ballB = __ballot_sync(0xffffffffu, hitB);
+            if (lane == 0) { S.mask[s0 >> 5] = ballA; if (SCORE_UNROLL == 2) S.mask[(s0 >> 5) + 1] = ballB; }   // (the second word may lie past tn: never read)
+            if (FAST) {
+                const uint32_t lt = (1u << lane) - 1;
+                if (hitA) S.hits[w_lo + wcount + __popc(ballA & lt)] = (uint16_t)(slotA | (finalA ? 0x8000u : 0u));
+                wcount += __popc(ballA);
+                if (SCORE_UNROLL == 2) {
+                    if (hitB) S.hits[w_lo + wcount + __popc(ballB & lt)] = (uint16_t)(slotB | (finalB ? 0x8000u : 0u));
+                    wcount += __popc(ballB);
                 }
             }
-            const uint32_t ball = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) t_mask[s0 >> 5] = ball;
+        }
+        if (FAST) {
+            // ---- phase B': the warp's hits, one per lane
+            __syncwarp();
+            for (uint32_t e = lane; e < wcount; e += 32) {
+                const uint32_t ent = S.hits[w_lo + e];
+                if (ent & 0x8000u) continue;
+                const uint32_t slot = ent;
+                const float mz = S.term[slot];
+                uint32_t idx = __float_as_uint(S.inten[slot]);
+                const float ph = __fmul_rn(mz, thi), qh = __fmul_rn(ph, 1.0f / 1000000.0f);
+                const float hi = __fadd_rn(mz, __fmaf_rn(__fmaf_rn(-qh, 1000000.0f, ph), 1.0f / 1000000.0f, qh));
+                // spectrum.rs:146-157: max_int starts at 0.0, `>=` keeps the last of equal maxima; a window of negative intensities matches nothing
+                int best = -1;
+                float max_int = 0.0f;
+                float m;
+                do {
+                    const float it = pi[idx];
+                    if (it >= max_int) { max_int = it; best = (int)idx; }
+                    m = pm[++idx];
+                } while (m <= hi);
+                if (best >= 0) {
+                    const float peak_mass = pm[best];
+                    // scoring.rs:719-720: peak_intensity * (mz - peak_mass).abs() * 2E6 / (mz + peak_mass)
+                    S.term[slot] = __fdiv_rn(__fmul_rn(__fmul_rn(max_int, fabsf(__fsub_rn(mz, peak_mass))), 2E6f), __fadd_rn(mz, peak_mass));
+                    S.inten[slot] = max_int;
+                } else {
+                    atomicAnd(&S.mask[slot >> 5], ~(1u << (slot & 31)));   // not a match after all
+                }
+            }
         }
         __syncthreads();
         // ---- fold: thread c walks the set bits of candidate c's slice of the tile in ascending task order
@@ -1405,7 +1525,7 @@ __device__ __forceinline__ void score_candidates_flat(const DbView& db, const Sc
             if (a < b) {
                 const uint32_t sa = a - t0, se = b - t0 - 1;   // first / last slot (inclusive)
                 for (uint32_t w = sa >> 5; w <= se >> 5; w++) {
-                    uint32_t m = t_mask[w];
+                    uint32_t m = S.mask[w];
                     if (w == sa >> 5) m &= 0xffffffffu << (sa & 31);
                     if (w == se >> 5) m &= 0xffffffffu >> (31 - (se & 31));
                     while (m) {
@@ -1422,8 +1542,8 @@ __device__ __forceinline__ void score_candidates_flat(const DbView& db, const Sc
                         uint32_t kind_i = ki >= nions;   // two ion kinds (b/y) in practice: one compare; more kinds finish in the loop
                         uint32_t idx = ki - (kind_i ? nions : 0);
                         while (idx >= nions) { idx -= nions; kind_i++; }
-                        const float it = t_int[slot];
-                        ppm = __fadd_rn(ppm, t_term[slot]);
+                        const float it = S.inten[slot];
+                        ppm = __fadd_rn(ppm, S.term[slot]);
                         if ((db.nterm_mask >> kind_i) & 1) { mb++; sb = __fadd_rn(sb, it); brun.matched(idx); }
                         else { my++; sy = __fadd_rn(sy, it); yrun.matched(idx); }
                     }
@@ -1441,7 +1561,7 @@ __device__ __forceinline__ void score_candidates_flat(const DbView& db, const Sc
         r.valid = ((r.matched_b + r.matched_y) & 0xFFFF) >= sc.min_matched_peaks;            // scoring.rs:491
         r.plen = L;
         recs[tid] = r;
-        hkey[tid] = r.valid ? r.hyperscore : -INFINITY;   // sort key: valid scores are finite (non-finite -> 255.0), so -inf never outranks one
+        S.hkey[tid] = r.valid ? r.hyperscore : -INFINITY;   // sort key: valid scores are finite (non-finite -> 255.0), so -inf never outranks one
     }
 }
 
@@ -1491,7 +1611,7 @@ __device__ __forceinline__ void annotate_candidate_warp(const DbView& db, const 
 
 // Validates that the (possibly peak-depleted) spectrum is ascending, positive and NaN-free and builds the bucket LUT; otherwise the
 // exact binary-search emulation is used for this spectrum.
-__device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t np, uint16_t* lut, LutParams& lp) {
+__device__ __forceinline__ bool spectrum_lut_setup(const float* masses /*masses[np] == +inf*/, uint32_t np, uint16_t* lut, LutParams& lp) {
     bool bad = np == 0 || np >= 65536;
     for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
         const float m = masses[i];
@@ -1499,7 +1619,7 @@ __device__ __forceinline__ bool spectrum_lut_setup(const float* masses, uint32_t
     }
     if (__syncthreads_or(bad)) return false;
     lp = lut_params(masses[0], masses[np - 1], SPEC_LUT_CELLS);
-    lut_build_sorted(masses, np, lp, lut, threadIdx.x, blockDim.x, SPEC_LUT_CELLS);   // masses verified ascending above
+    lut_build_walk(masses, np, lp, lut, threadIdx.x, blockDim.x, SPEC_LUT_CELLS);   // masses verified ascending above; masses[np] == +inf (k_score)
     __syncthreads();
     return true;
 }
@@ -1510,22 +1630,16 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
                                                          unsigned long long frag_cap, uint32_t quick_mode /*0 score, 1 keep all prelim, 2 low-memory*/,
                                                          uint8_t* keep /*quick_score: one byte per peptide*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: masses_raw[pmax+4] intens_raw[pmax+4] cur[lcap] tot[lcap] recs[kparam] order[kparam] lut[1024] mark[pmax] + the tile arrays below  (pmax % 4 == 0)
+    // dynamic layout: masses_raw[pmax+4] intens_raw[pmax+4] cur[lcap] tot[lcap] recs[kparam] order[kparam] mark[pmax]   (pmax % 4 == 0)
     float* masses_raw = reinterpret_cast<float*>(smem_raw);
     float* intens_raw = masses_raw + pmax + 4;
     uint64_t* cur = reinterpret_cast<uint64_t*>(intens_raw + pmax + 4);
     uint64_t* tot = cur + sc.lcap;
     ScoreRec* recs = reinterpret_cast<ScoreRec*>(tot + sc.lcap);
     uint32_t* order = reinterpret_cast<uint32_t*>(recs + sc.kparam);
-    uint16_t* lut = reinterpret_cast<uint16_t*>(order + sc.kparam);
-    uint8_t* mark = reinterpret_cast<uint8_t*>(lut + SPEC_LUT_CELLS);
-    // flattened candidate scoring (score_candidates_flat): headers[kparam + 1] | sort keys[kparam] | term[tile] | intensity[tile] | mask[tile / 32]
-    CandHdr* hdr = reinterpret_cast<CandHdr*>(smem_raw + (((size_t)(mark + pmax) - (size_t)smem_raw + 15) & ~(size_t)15));
-    double* hkey = reinterpret_cast<double*>(hdr + sc.kparam + 1);
-    float* t_term = reinterpret_cast<float*>(hkey + sc.kparam);
-    float* t_int = t_term + sc.score_tile;
-    uint32_t* t_mask = reinterpret_cast<uint32_t*>(t_int + sc.score_tile);
-    __shared__ uint32_t s_scan[SCORE_THREADS / 32];
+    uint8_t* mark = reinterpret_cast<uint8_t*>(order + sc.kparam);
+    __shared__ __align__(16) ScoreTile S;   // static: headers, sort keys, spectrum LUT and the task tile of score_candidates_flat
+    uint16_t* const lut = S.lut;
     __shared__ uint32_t s_ntot, s_ncand, s_np, s_nvalid;
     __shared__ unsigned long long s_matched_peaks, s_scored;
     __shared__ float s_tic;
@@ -1617,6 +1731,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
         if (tid == 0) { dbg_meta[s * 4 + 0] = s_ntot; dbg_meta[s * 4 + 1] = (uint32_t)s_matched_peaks; dbg_meta[s * 4 + 2] = (uint32_t)s_scored; }
     }
     if (np) mbar_wait(&s_bar, 0);   // peaks have landed in shared memory
+    if (tid == 0) masses[np] = INFINITY;   // sentinel behind the last peak (slack of the staging buffer): ends the LUT walk and the peak scans
     const uint32_t ncand = s_ncand;
     // quick_score accumulates into keep[] across chunks; a chunk whose work lists overflowed (the host re-runs it with exact sizes) has partial hit
     // sets and must not leave marks behind. Both counters are final after k_setup_queries.
@@ -1638,7 +1753,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
         sv.np = np;
         sv.use_lut = spectrum_lut_setup(masses, np, lut, sv.lp);
         if (tid == 0) s_nvalid = 0;
-        score_candidates_flat(db, sc, cur, ncand, sv, hdr, t_term, t_int, t_mask, sc.score_tile, recs, hkey, s_scan);
+        if (sv.use_lut && sc.score_fast && sc.fragment_tol.kind == 0 && fast_tol_ok(sc.fragment_tol.lo) && fast_tol_ok(sc.fragment_tol.hi))
+            score_candidates_flat<true>(db, sc, cur, ncand, sv, S, recs);
+        else
+            score_candidates_flat<false>(db, sc, cur, ncand, sv, S, recs);
         __syncthreads();
         if (quick_mode == 2) {
             // Scorer::quick_score, low-memory branch (scoring.rs:270-290): bounded_min_heapify(score_vector, report_psms) compares Score
@@ -1662,10 +1780,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
         if (tid < ncand) {
             my_floats = 2 * recs[tid].plen + 2;
             if (recs[tid].valid) {
-                const double h = hkey[tid];   // == hyperscore; entries below min_matched_peaks hold -inf and never count
+                const double h = S.hkey[tid];   // == hyperscore; entries below min_matched_peaks hold -inf and never count
                 uint32_t pos = 0;
                 for (uint32_t j = 0; j < ncand; j++) {
-                    const double hj = hkey[j];
+                    const double hj = S.hkey[j];
                     pos += (hj > h) || (hj == h && j < tid);
                 }
                 order[pos] = tid;
@@ -1770,6 +1888,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
                 for (uint32_t i = 0; i < w; i++) t = __fadd_rn(t, intens[i]);
                 s_tic = t;
                 s_np = w;
+                masses[w] = INFINITY;   // sentinel follows the shrunken peak list
             }
         }
         __syncthreads();

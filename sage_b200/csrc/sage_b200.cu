@@ -8,7 +8,11 @@
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 
+#include <pthread.h>
+#include <sched.h>
+
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -512,6 +516,29 @@ extern "C" int sage_b200_host_log_variant(void) {
     return cached;
 }
 
+// 1 when the host libm's log1pf (Rust's f32::ln_1p, OpenMS hyperscore) is the fdlibm/glibc function the kernels reproduce (glibc_log.cuh).
+extern "C" int sage_b200_host_log1pf_exact(void) {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    uint64_t st = 0x2545F4914F6CDD1Dull;
+    auto next = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    int ok = 1;
+    for (int i = 0; i < 20000 && ok; i++) {
+        const uint64_t u = next();
+        float x;
+        switch (i % 3) {
+            case 0: x = (float)(u & 0xffffff) * 3.7f; break;                                  // summed intensities
+            case 1: x = (float)((double)(u >> 11) * 0x1p-53 * 2.0 - 0.9); break;            // around the branch points
+            default: { uint32_t b = (uint32_t)(u >> 33); memcpy(&x, &b, 4); break; }          // any non-negative float
+        }
+        volatile float vx = x;
+        const float ref = log1pf(vx), got = glog::glibc_log1pf(x);
+        if (memcmp(&ref, &got, 4) && !(ref != ref && got != got)) ok = 0;
+    }
+    cached = ok;
+    return cached;
+}
+
 // ------------------------------------------------------------------------------------------------ scorer
 struct ChunkState {
     bool loaded = false;
@@ -557,6 +584,7 @@ struct Lane {
 
 struct sage_b200_scorer {
     const sage_b200_db* db = nullptr;
+    int device = 0;   // copy of db->device: scorer_destroy must not touch a db that was destroyed first
     sage_b200_scorer_params params{};
     ScorerView sv{};
     std::mutex mu;
@@ -589,6 +617,7 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     { int rc_attr = ensure_kernel_attributes(db->device); if (rc_attr) return rc_attr; }
     sage_b200_scorer* s = new sage_b200_scorer();
     s->db = db;
+    s->device = db->device;
     s->params = *p;
     ScorerView& v = s->sv;
     v.precursor_tol = {p->precursor_tol.kind, p->precursor_tol.lo, p->precursor_tol.hi};
@@ -627,8 +656,8 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
         v.lnfact_n = N;
     }
     v.log_variant = (uint32_t)std::max(0, sage_b200_host_log_variant());
-    v.score_tile = SCORE_TILE_DEFAULT;
-    if (const char* e = getenv("SAGE_B200_SCORE_TILE")) v.score_tile = (uint32_t)std::min(8192, std::max(128, atoi(e))) & ~127u;
+    v.score_fast = 1;
+    if (const char* e = getenv("SAGE_B200_SCORE_FAST")) v.score_fast = atoi(e) != 0;
     if (const char* e = getenv("SAGE_B200_SORT")) s->sort_spectra = atoi(e);
     for (Lane& L : s->lanes) {
         CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
@@ -666,9 +695,8 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
         s->wide_per_spectrum = 0.0;
         return 0;
     }
-    if (!strcmp(name, "score_tile")) {  // tasks per shared-memory tile of k_score's flattened candidate scoring (tests use small tiles to cross tile borders)
-        if (value < 128 || value > 8192 || (value & 127)) return fail(SAGE_B200_EINVAL, "score_tile must be a multiple of 128 in 128..8192");
-        s->sv.score_tile = (uint32_t)value;
+    if (!strcmp(name, "score_fast")) {  // 0: k_score always takes the generic task body (tests compare both)
+        s->sv.score_fast = value != 0;
         return 0;
     }
     if (!strcmp(name, "log_variant")) {  // test hook: 0 = glibc log() as built with FMA contraction, 1 = without (default: whichever the host libm is)
@@ -686,7 +714,7 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
 
 extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
     if (!s) return;
-    cudaSetDevice(s->db->device);
+    cudaSetDevice(s->device);
     for (Lane& L : s->lanes) L.release();
     if (s->ev_base) cudaEventDestroy(s->ev_base);
     s->d_lnfact.release();
@@ -766,9 +794,8 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
             h_ims[i] = sp->inverse_ion_mobility ? sp->inverse_ion_mobility[c0 + i] : NAN;
         }
         memcpy(hs + C.o_chg, sp->precursor_charge + c0, n);
-        C.smem = (size_t)(C.pmax + 4) * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + 2 * SPEC_LUT_CELLS + C.pmax + 16   // peaks, lists, records, LUT, marks
-                 + (size_t)(sv.kparam + 1) * sizeof(CandHdr) + (size_t)sv.kparam * 8 + (size_t)sv.score_tile * 8 + sv.score_tile / 8 + 16;      // score_candidates_flat
-        if (C.smem > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", C.pmax);
+        C.smem = (size_t)(C.pmax + 4) * 8 + (size_t)sv.lcap * 16 + (size_t)sv.kparam * (sizeof(ScoreRec) + 4) + C.pmax + 32;   // peaks, lists, records, order, marks
+        if (C.smem + sizeof(ScoreTile) > 200 * 1024) return fail(SAGE_B200_ELIMIT, "spectrum with %u peaks exceeds the shared-memory budget", C.pmax);
         C.nitems = (size_t)n * sv.qmax;
         if (C.nitems > 0x7FFFFFFFull) return fail(SAGE_B200_ELIMIT, "too many queries in one chunk");
         int r;
@@ -810,6 +837,7 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     cudaStream_t st = L.stream;
     ChunkState& C = L.chunk;
     if (!C.loaded) return fail(SAGE_B200_EINVAL, "no spectra resident on the device (call batch_upload first)");
+    cudaGetLastError();   // a stale non-sticky error left by another user of the runtime must not be blamed on the launches below
     const uint32_t n = C.n;
     int rc;
     if (dbg) {
@@ -1106,6 +1134,45 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
     return 0;
 }
 
+// Pins the calling host thread to the CPUs of the NUMA node the GPU hangs off (sysfs: PCI device -> numa_node -> cpulist), so that the thread's
+// pinned staging buffers (first touch) and its cudaMemcpyAsync submissions stay on the socket next to the GPU. Returns the node (>= 0), or -1
+// when the topology cannot be read (single-node hosts, containers without sysfs): the thread is left alone.
+extern "C" int sage_b200_bind_thread_to_device(int device) {
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[256];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return -1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    char list[4096] = {0};
+    const size_t got = fread(list, 1, sizeof list - 1, f);
+    fclose(f);
+    if (got == 0) return -1;
+    cpu_set_t cur, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return -1;
+    int n_set = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {   // "0-31,64-95"
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1) b = a;
+        if (k < 1) continue;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++)
+            if (CPU_ISSET(c, &cur)) { CPU_SET(c, &want); n_set++; }   // never widen the affinity the process was given
+    }
+    if (n_set == 0) return -1;
+    if (pthread_setaffinity_np(pthread_self(), sizeof want, &want) != 0) return -1;
+    return node;
+}
+
 // One process, several GPUs: spectra are independent, so the batch is cut into contiguous blocks, block g goes to
 // scorers[g] (each bound to its own device and index replica) on its own host thread; Feature.spectrum stays batch-relative.
 // No collective and no peer traffic: results land directly in the caller's arrays.
@@ -1128,6 +1195,7 @@ extern "C" int sage_b200_score_batch_multi(sage_b200_scorer* const* scorers, int
         const uint64_t a = sp->n * (uint64_t)g / (uint64_t)n_scorers, b = sp->n * (uint64_t)(g + 1) / (uint64_t)n_scorers;
         th.emplace_back([&, g, a, b]() {
             if (a == b) return;
+            sage_b200_bind_thread_to_device(scorers[g]->db->device);   // worker + its staging copies on the GPU's NUMA node
             sage_b200_spectra sub = *sp;   // a view: same arrays, shifted per-spectrum pointers (peak_offsets stay absolute)
             sub.n = b - a;
             sub.peak_offsets = sp->peak_offsets + a;
@@ -1268,6 +1336,7 @@ extern "C" int sage_b200_process_spectra(int device, const sage_b200_processor_p
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SAGE_B200_ECUDA, "no CUDA device available: sage_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(SAGE_B200_EINVAL, "device out of range");
     CUDA_TRY(cudaSetDevice(device));
+    cudaGetLastError();   // a stale non-sticky error left by another user of the runtime must not be blamed on the launches below
     const uint64_t n = raw->n;
     out_peak_offsets[0] = 0;
     if (n == 0) return 0;
@@ -1351,11 +1420,11 @@ extern "C" int sage_b200_find_reporter_ions(int device, uint64_t n, const uint64
 
 __global__ void k_device_log(int variant, const double* x, uint64_t n, double* out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = glog::glibc_log_v(x[i], variant);
+    if (i < n) out[i] = variant == 2 ? (double)glog::glibc_log1pf((float)x[i]) : glog::glibc_log_v(x[i], variant);
 }
 extern "C" int sage_b200_device_log(int device, int variant, const double* x, uint64_t n, double* out) {
     if (n == 0) return 0;
-    if (!x || !out || variant < 0 || variant > 1) return fail(SAGE_B200_EINVAL, "device_log: bad argument");
+    if (!x || !out || variant < 0 || variant > 2) return fail(SAGE_B200_EINVAL, "device_log: bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SAGE_B200_ECUDA, "no CUDA device available: sage_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(SAGE_B200_EINVAL, "device out of range");

@@ -7,6 +7,9 @@ to the reference's digest: both the oracle and the CUDA path consume exactly the
 """
 from __future__ import annotations
 
+import itertools
+import os
+
 import numpy as np
 
 from .api import Peptides, SpectraBatch
@@ -66,12 +69,85 @@ def _reverse_inner(mat, ln):
     return out
 
 
+def _expand_variable_mods(site_mass, max_variable_mods):
+    """Peptide::apply (peptide.rs:258-305): every combination of up to `max_variable_mods` variable modifications on distinct sites
+    (site_mass != 0 marks a site). Returns the base row of every form (the unmodified forms first) and the (form, column) pairs to modify."""
+    n = len(site_mass)
+    is_site = site_mass != 0
+    nsite = is_site.sum(axis=1)
+    maxs = int(nsite.max()) if n else 0
+    order = np.argsort(~is_site, axis=1, kind="stable")[:, :max(maxs, 1)]   # order[i, k] = column of the k-th site of row i
+    base_rows, add_rows, add_cols = [np.arange(n)], [], []
+    form_count = n
+    for k in range(1, max_variable_mods + 1):
+        for slots in itertools.combinations(range(maxs), k):
+            rows = np.nonzero(nsite > slots[-1])[0]
+            if len(rows) == 0:
+                continue
+            base_rows.append(rows)
+            ids = form_count + np.arange(len(rows))
+            for sl in slots:
+                add_rows.append(ids)
+                add_cols.append(order[rows, sl])
+            form_count += len(rows)
+    base = np.concatenate(base_rows)
+    if add_rows:
+        return base, np.concatenate(add_rows), np.concatenate(add_cols)
+    return base, np.zeros(0, np.int64), np.zeros(0, np.int64)
+
+
+_NATIVE = None
+
+
+def _native():
+    """libsage_synth.so (sage_b200/csrc/synth_expand.cpp, built by sage_b200.build): same result as the numpy path, ~100x faster."""
+    global _NATIVE
+    if _NATIVE is None:
+        import ctypes as C
+        from .build import synth_library_path
+        path = synth_library_path()
+        if os.environ.get("SAGE_B200_SYNTH_NUMPY") == "1" or not os.path.exists(path):
+            _NATIVE = False
+        else:
+            lib = C.CDLL(path)
+            lib.synth_expand.restype = C.c_void_p
+            lib.synth_expand.argtypes = [C.c_uint64, C.c_uint32] + [C.c_void_p] * 7 + [C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+            lib.synth_expand_fetch.argtypes = [C.c_void_p] * 7
+            lib.synth_expand_free.argtypes = [C.c_void_p]
+            _NATIVE = lib
+    return _NATIVE or None
+
+
+def _expand_native(lib, mat, ln, static, site_mass, base_mono, decoy, missed, max_mods):
+    import ctypes as C
+    mat, ln = np.ascontiguousarray(mat, np.uint8), np.ascontiguousarray(ln, np.int64)
+    static, site_mass, base_mono = (np.ascontiguousarray(x, np.float32) for x in (static, site_mass, base_mono))
+    decoy, missed = np.ascontiguousarray(decoy, np.uint8), np.ascontiguousarray(missed, np.uint8)
+    n_out, n_res = C.c_uint64(0), C.c_uint64(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    h = lib.synth_expand(len(mat), mat.shape[1], p(mat), p(ln), p(static), p(site_mass), p(base_mono), p(decoy), p(missed), max_mods,
+                         C.c_float(500.0), C.c_float(5000.0), C.byref(n_out), C.byref(n_res))
+    if not h:
+        raise RuntimeError("synth_expand failed (too many forms / residues for u32 offsets)")
+    n, r = n_out.value, n_res.value
+    seq_off, seq, mods = np.zeros(n + 1, np.uint32), np.zeros(r, np.uint8), np.zeros(r, np.float32)
+    mono, dec, mis = np.zeros(n, np.float32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    lib.synth_expand_fetch(h, p(seq_off), p(seq), p(mods), p(mono), p(dec), p(mis))
+    lib.synth_expand_free(h)
+    return Peptides(seq_off=seq_off, seq=seq, mods=mods, nterm=np.full(n, np.nan, np.float32), mono=mono, decoy=dec, missed=mis)
+
+
 def make_peptides(n_target: int = 2_000_000, seed: int = 0x5A6E, missed: int = 1, static_c: bool = False, il_twin_fraction: float = 0.02,
-                  var_mod_m: bool = False) -> Peptides:
-    """Peptide table with ~n_target rows (targets + reversed decoys), sorted like reorder_peptides (database.rs:221-258)."""
+                  var_mod_m: bool = False, var_mods=(), max_variable_mods: int = 2) -> Peptides:
+    """Peptide table sorted like reorder_peptides (database.rs:221-258). `n_target` ~ rows (targets + reversed decoys) BEFORE the variable
+    modifications are enumerated; var_mods = ((residues, mass), ...) adds every combination of up to max_variable_mods modified sites
+    (peptide.rs:258-305), e.g. (("M", 15.9949), ("STY", 79.9663)) turns ~1.9 M rows into ~15 M. var_mod_m is shorthand for M+15.9949 with
+    at most one modified site per form."""
     rng = np.random.default_rng(seed)
+    if var_mod_m and not var_mods:
+        var_mods, max_variable_mods = (("M", 15.9949),), 1
     # ~1 unique peptide (0+1 missed, len 5-50, after dedup) per 5.3 residues; decoys double it
-    n_res = int(n_target * 2.75 * (2.0 if var_mod_m else 1.0) ** -1) + 4096
+    n_res = int(n_target * 2.75) + 4096
     lens = np.maximum(30, rng.lognormal(np.log(375.0), 0.6, size=max(8, n_res // 430))).astype(np.int64)
     prot_off = np.concatenate([[0], np.cumsum(lens)])
     prot = rng.choice(_AA, size=int(prot_off[-1]), p=_FREQ / _FREQ.sum())
@@ -102,31 +178,48 @@ def make_peptides(n_target: int = 2_000_000, seed: int = 0x5A6E, missed: int = 1
     allln = np.concatenate([ln, ln[dkeep]])
     allmm = np.concatenate([mm, mm[dkeep]])
     decoy = np.concatenate([np.zeros(len(mat), np.uint8), np.ones(len(dkeep), np.uint8)])
-    mods = np.zeros(allmat.shape, np.float32)
-    if static_c:
-        mods[allmat == ord("C")] = np.float32(57.0216)
-    if var_mod_m:  # one extra row per peptide containing M, with its first M oxidised (variable mod, max 1 site here)
-        has_m = (allmat == ord("M")).any(axis=1)
-        idx = np.nonzero(has_m)[0]
-        first_m = (allmat[idx] == ord("M")).argmax(axis=1)
-        vm = mods[idx].copy()
-        vm[np.arange(len(idx)), first_m] = np.float32(15.9949)
-        allmat = np.concatenate([allmat, allmat[idx]])
-        allln = np.concatenate([allln, allln[idx]])
-        allmm = np.concatenate([allmm, allmm[idx]])
-        decoy = np.concatenate([decoy, decoy[idx]])
-        mods = np.concatenate([mods, vm])
-    # monoisotopic = H2O + sum(residues) (sequential f32, peptide.rs:361-373) + modification_mass (peptide.rs:129-133)
+    # rows in sequence order: the final stable sort by mass then yields (monoisotopic, sequence, modifications-in-enumeration-order)
+    sorder = np.argsort(np.ascontiguousarray(allmat).view(f"S{MAX_LEN}").ravel(), kind="stable")
+    allmat, allln, allmm, decoy = allmat[sorder], allln[sorder], allmm[sorder], decoy[sorder]
     res = MONO[allmat]
     base = np.cumsum(np.concatenate([np.full((len(allmat), 1), H2O, np.float32), res], axis=1), axis=1, dtype=np.float32)[:, -1]
+    valid = np.arange(MAX_LEN)[None, :] < allln[:, None]
+    static = np.zeros(allmat.shape, np.float32)
+    if static_c:
+        static[allmat == ord("C")] = np.float32(57.0216)
+    if var_mods:
+        # variable mods first, then static mods on the sites still unmodified (peptide.rs:293-300); disjoint residue sets here
+        site_mass = np.zeros(allmat.shape, np.float32)
+        for residues, mass in var_mods:
+            for r in residues:
+                site_mass[(allmat == ord(r)) & (static == 0) & valid] = np.float32(mass)
+        lib = _native()
+        if lib is not None:
+            return _expand_native(lib, allmat, allln, static, site_mass, base, decoy, allmm, int(max_variable_mods))
+        form_base, ar, ac = _expand_variable_mods(site_mass, int(max_variable_mods))
+        nforms = len(form_base)
+        if nforms > 4_000_000:
+            raise RuntimeError("variable-modification tables of this size need the native helper (python -m sage_b200.build)")
+        fmods = static[form_base]
+        fmods[ar, ac] = site_mass[form_base[ar], ac]
+        # modification_mass (peptide.rs:129-133): sequential f32 sum over the residues
+        mono = (base[form_base] + np.cumsum(fmods, axis=1, dtype=np.float32)[:, -1]).astype(np.float32)
+        keep = np.nonzero((mono >= np.float32(500.0)) & (mono <= np.float32(5000.0)))[0]
+        # reorder_peptides: (monoisotopic, sequence == base row, modifications lexicographic); mods >= 0, so big-endian bit patterns sort like values
+        mkey = np.ascontiguousarray(fmods[keep].view(np.uint32).astype(">u4")).view(f"S{4 * MAX_LEN}").ravel()
+        order = keep[np.lexsort((mkey, form_base[keep], mono[keep]))]
+        fb = form_base[order]
+        fvalid = valid[fb]
+        seq_off = np.concatenate([[0], np.cumsum(allln[fb])]).astype(np.uint32)
+        return Peptides(seq_off=seq_off, seq=allmat[fb][fvalid].astype(np.uint8), mods=fmods[order][fvalid].astype(np.float32),
+                        nterm=np.full(len(order), np.nan, np.float32), mono=mono[order], decoy=decoy[fb], missed=allmm[fb])
+    mods = static
+    # monoisotopic = H2O + sum(residues) (sequential f32, peptide.rs:361-373) + modification_mass (peptide.rs:129-133)
     modsum = np.cumsum(mods, axis=1, dtype=np.float32)[:, -1]
     mono = (base + modsum).astype(np.float32)
     keep = (mono >= np.float32(500.0)) & (mono <= np.float32(5000.0))
     allmat, allln, allmm, decoy, mods, mono = allmat[keep], allln[keep], allmm[keep], decoy[keep], mods[keep], mono[keep]
-    # sort by (monoisotopic, sequence, modifications)
-    skey = np.ascontiguousarray(allmat).view(f"S{MAX_LEN}").ravel()
-    mkey = np.ascontiguousarray(mods.view(np.uint32).astype(">u4")).view(f"S{4 * MAX_LEN}").ravel()  # mods >= 0: big-endian bits sort like values
-    order = np.lexsort((mkey, skey, mono))
+    order = np.argsort(mono, kind="stable")   # rows are in sequence order already: (monoisotopic, sequence)
     allmat, allln, allmm, decoy, mods, mono = allmat[order], allln[order], allmm[order], decoy[order], mods[order], mono[order]
     valid = np.arange(MAX_LEN)[None, :] < allln[:, None]
     seq_off = np.concatenate([[0], np.cumsum(allln)]).astype(np.uint32)

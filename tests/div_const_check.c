@@ -1,6 +1,6 @@
-/* Exhaustive check behind div_const_rn (sage_b200/csrc/device_common.cuh): for c in {1e6, 100} and EVERY float x with 1e-20 <= x <= 1e30,
+/* Exhaustive check behind div_const_rn (sage_b200/csrc/device_common.cuh): for c in {1e6, 100, 3} and EVERY float x with 1e-20 <= x <= 1e30,
  * fma(fma(-q0, c, x), rc, q0) with q0 = x * rc, rc = rn(1 / c) equals the IEEE division x / c bit for bit (negative x follows by symmetry of
- * round-to-nearest). Prints "tested <n> bad <m>" per constant; exit status 0 iff both m are 0.  Build: gcc -O2 -fopenmp -ffp-contract=off. */
+ * round-to-nearest). Prints "tested <n> bad <m>" per constant; exit status 0 iff every m is 0.  Build: gcc -O2 -fopenmp -ffp-contract=off. */
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -25,4 +25,5 @@ static unsigned long long check(float c) {
     return bad;
 }
 
-int main(void) { return (check(1000000.0f) | check(100.0f)) != 0; }
+/* 3: fragment / charge for triply charged fragments in k_score's straight-line task body (scoring.rs:707) */
+int main(void) { return (check(1000000.0f) | check(100.0f) | check(3.0f)) != 0; }

@@ -1,8 +1,8 @@
 """Shared helpers for the parity tests: build the oracle DB and the device DB from the same peptide table, and compare
 Feature tables field by field. Integer and f32 fields are always compared bit for bit. The f64 scores (hyperscore, delta_next,
 delta_best, poisson) are compared BIT FOR BIT too whenever the library reports that it reproduces this host's libm log()
-(sage_b200_host_log_variant() >= 0: the kernels evaluate glibc's algorithm, glibc_log.cuh); only the OpenMS score type (f32 log1p)
-and hosts with an unknown libm fall back to north_star's 1e-6 relative tolerance."""
+(sage_b200_host_log_variant() >= 0, and sage_b200_host_log1pf_exact() for the OpenMS score type: the kernels evaluate glibc's algorithms,
+glibc_log.cuh); only hosts with an unknown libm fall back to north_star's 1e-6 relative tolerance."""
 import numpy as np
 
 from oracle import oracle as O
@@ -42,9 +42,9 @@ def bits(a):
     return a
 
 
-def f64_exact_default():
+def f64_exact_default(score_type=0):
     from sage_b200 import api
-    return api.host_log_variant() >= 0
+    return api.host_log_variant() >= 0 and (score_type == 0 or api.host_log1pf_exact())
 
 
 def assert_features_equal(gf, gc, of, oc, report_psms, what="", f64_exact=None):

@@ -1,7 +1,9 @@
 /* CPU restatement (same IEEE-754 binary32 operations, no contraction) of two device-side search accelerators, checked against the plain
  * searches they replace on random inputs:
- *   1. lut_build_sorted (sage_b200/csrc/kernels.cuh): the O(cells + n) construction of start[c] = #{arr[i] < edge(c)} must give the same table as
- *      one binary search per cell (lut_build), for ascending arrays with duplicates and clustered values.
+ *   1. lut_build_walk (sage_b200/csrc/kernels.cuh): start[c] = #{arr[i] < edge(c)} built by 128 "threads", each owning a run of consecutive cells
+ *      (binary search for the first, sentinel-terminated forward walk for the others), must give the same table as one binary search per
+ *      cell (lut_build), for ascending arrays with duplicates and clustered values. (lut_new is the O(cells + n) builder of round 1, kept as a
+ *      second independent construction.)
  *   2. pep_partition: the precursor-mass LUT bracket [lut[c-1], lut[c+2]] must always contain the partition point, i.e. the bracketed binary
  *      search returns the same index as the full one, for query values inside, outside and exactly on array elements.
  * Exit status 0 iff no mismatch.  Build: gcc -O2 -ffp-contract=off. */
@@ -43,11 +45,32 @@ static void lut_new(const float* arr, uint32_t n, float base, float inv_w, uint1
     }
 }
 
+static void lut_walk(const float* arr /* arr[n] = +inf */, uint32_t n, float base, float inv_w, uint16_t* start, uint32_t cells) {   /* lut_build_walk */
+    const uint32_t stride = 128, per = (cells + stride - 1) / stride;
+    for (uint32_t t0 = 0; t0 < stride; t0++) {
+        const uint32_t c0 = t0 * per, c1 = c0 + per < cells ? c0 + per : cells;
+        if (!(inv_w > 0.0f)) { for (uint32_t c = c0; c < c1; c++) start[c] = 0; continue; }
+        if (c0 >= c1) continue;
+        uint32_t i = 0;
+        if (c0 > 0) {
+            const float e = base + (float)c0 * (1.0f / inv_w);
+            uint32_t hi = n;
+            while (i < hi) { const uint32_t m = (i + hi) >> 1; if (arr[m] < e) i = m + 1; else hi = m; }
+        }
+        start[c0] = (uint16_t)i;
+        for (uint32_t c = c0 + 1; c < c1; c++) {
+            const float e = base + (float)c * (1.0f / inv_w);
+            while (arr[i] < e) i++;
+            start[c] = (uint16_t)i;
+        }
+    }
+}
+
 int main(void) {
     unsigned long long bad = 0, cases = 0;
     enum { CELLS = 1024, NMAX = 400 };
-    static float arr[NMAX];
-    static uint16_t a[CELLS], b[CELLS];
+    static float arr[NMAX + 1];
+    static uint16_t a[CELLS], b[CELLS], w[CELLS];
     for (int it = 0; it < 20000; it++) {
         const uint32_t n = 1 + rnd() % NMAX;
         const int mode = it % 4;
@@ -63,10 +86,12 @@ int main(void) {
         const float inv_w = (w0 > 0.0f && w0 < 3.0e38f) ? 1.0f / w0 : 0.0f;
         lut_ref(arr, n, base, inv_w, a, CELLS);
         lut_new(arr, n, base, inv_w, b, CELLS);
-        for (int c = 0; c < CELLS; c++) bad += a[c] != b[c];
+        arr[n] = INFINITY;
+        lut_walk(arr, n, base, inv_w, w, CELLS);
+        for (int c = 0; c < CELLS; c++) bad += (a[c] != b[c]) + (a[c] != w[c]);
         cases++;
     }
-    printf("lut_build_sorted: %llu arrays, %llu mismatching cells\n", cases, bad);
+    printf("lut_build_walk / lut_build_sorted: %llu arrays, %llu mismatching cells\n", cases, bad);
 
     /* ---- pep_partition bracket */
     enum { PCELLS = 65536, NP = 300000 };

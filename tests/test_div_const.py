@@ -1,5 +1,5 @@
-"""The CUDA path replaces the two constant divisions of Tolerance::bounds (mass.rs:21-35: /1e6 for ppm, /100 for pct) by a reciprocal
-multiply with one FMA correction (div_const_rn). That is only legal because it is bit-identical to IEEE division on the whole guarded range:
+"""The CUDA path replaces the two constant divisions of Tolerance::bounds (mass.rs:21-35: /1e6 for ppm, /100 for pct) and fragment / 3
+(scoring.rs:707, triply charged fragments) by a reciprocal multiply with one FMA correction (div_const_rn). That is only legal because it is bit-identical to IEEE division on the whole guarded range:
 this test proves it exhaustively on the CPU (same IEEE-754 binary32 arithmetic, no contraction)."""
 import os
 import subprocess
@@ -15,4 +15,4 @@ def test_fma_corrected_reciprocal_equals_division_for_every_float_in_range():
         out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stdout + out.stderr
         lines = out.stdout.strip().splitlines()
-        assert len(lines) == 2 and all(ln.split()[2] == "1393364419" and ln.endswith("bad 0") for ln in lines), out.stdout
+        assert len(lines) == 3 and all(ln.split()[2] == "1393364419" and ln.endswith("bad 0") for ln in lines), out.stdout

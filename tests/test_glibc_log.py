@@ -41,6 +41,33 @@ def test_host_variant_matches_libm():
     assert int(mism["variant%d" % v]) == 0, out
 
 
+def test_host_log1pf_matches_libm_on_every_float():
+    """CPU, exhaustive: the log1pf the kernels evaluate (OpenMS hyperscore, f32::ln_1p) equals this host's libm log1pf on all 2^32 floats."""
+    from sage_b200 import api
+    assert api.host_log1pf_exact()
+    src = os.path.join(ROOT, "tests", "glibc_log1pf_check.cpp")
+    exe = "/tmp/sage_b200_glibc_log1pf_check"
+    subprocess.check_call(["g++", "-O2", "-fopenmp", "-I", os.path.join(ROOT, "sage_b200", "csrc"), src, "-o", exe])
+    out = subprocess.check_output([exe]).decode()
+    assert "tested 4294967296 bad 0" in out, out
+
+
+@pytest.mark.gpu
+def test_device_log1pf_equals_host_libm():
+    from sage_b200 import api
+    rng = np.random.default_rng(9)
+    x = np.concatenate([rng.integers(0, 1 << 31, 300_000).astype(np.uint32).view(np.float32), (rng.random(100_000) * 2 - 0.95).astype(np.float32),
+                        (rng.integers(0, 1 << 24, 100_000) * 3.7).astype(np.float32)]).astype(np.float64)
+    got = api.device_log(x, 2).astype(np.float32)
+    libm = ctypes.CDLL("libm.so.6")
+    libm.log1pf.restype, libm.log1pf.argtypes = ctypes.c_float, [ctypes.c_float]
+    sel = np.arange(0, len(x), 5)
+    want = np.array([libm.log1pf(float(t)) for t in x[sel]], np.float32)
+    g = got[sel]
+    same = (g.view(np.uint32) == want.view(np.uint32)) | (np.isnan(g) & np.isnan(want))
+    assert same.all(), f"{int((~same).sum())} differ, e.g. x={x[sel][~same][:3]}"
+
+
 @pytest.mark.gpu
 def test_device_log_equals_host_libm():
     from sage_b200 import api

@@ -6,7 +6,7 @@ import sage_b200
 from sage_b200 import IndexedDatabase, Precursor, ProcessedSpectrum, Scorer, SpectraBatch, Tolerance, synth
 from oracle import oracle as O
 
-from helpers import assert_features_equal, oracle_cfg, oracle_db_from_peptides, peptides_from_oracle
+from helpers import assert_features_equal, f64_exact_default, oracle_cfg, oracle_db_from_peptides, peptides_from_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -30,7 +30,7 @@ def run_both(odb, gdb, spectra, pep_caps=(2048, 0), **kw):
             sc.set_option("pep_cap", cap)
         gf, gc = sc.score_batch(spectra)
         n = assert_features_equal(gf, gc, of, oc, kw.get("report_psms", 1), what=str({"pep_cap": cap, **{k: v for k, v in kw.items() if "tol" not in k}}),
-                                  f64_exact=None if kw.get("score_type", 0) == 0 else False)   # OpenMS: f32 log1p, not reproduced bit for bit
+                                  f64_exact=f64_exact_default(kw.get("score_type", 0)))
     return sc, n, octr
 
 

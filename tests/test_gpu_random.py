@@ -5,7 +5,7 @@ import pytest
 
 from sage_b200 import IndexedDatabase, Scorer, SpectraBatch, Tolerance, synth
 
-from helpers import assert_features_equal, oracle_cfg, oracle_db_from_peptides
+from helpers import assert_features_equal, f64_exact_default, oracle_cfg, oracle_db_from_peptides
 
 pytestmark = pytest.mark.gpu
 
@@ -77,11 +77,11 @@ def test_random_configuration(seed):
     sc.set_option("pep_cap", int(rng.choice([0, 64, 8192])))
     sc.set_option("wide_tile", int(rng.choice([512, 4096, 81920])))
     sc.set_option("pipeline_chunks", int(rng.choice([1, 2, 7])))
-    sc.set_option("score_tile", int(rng.choice([128, 384, 2048])))   # small tiles: candidates straddle tile borders in k_score
+    sc.set_option("score_fast", int(rng.integers(2)))   # straight-line vs generic task body of k_score
     gf, gc = sc.score_batch(spectra)
     of, oc, _, _ = odb.score_batch(oracle_cfg(**kw), spectra.as_dict())
     assert_features_equal(gf, gc, of, oc, kw["report_psms"], what=f"seed {seed}: kinds={kinds} bucket={bucket} min_ion={min_ion} {kw}",
-                          f64_exact=None if kw["score_type"] == 0 else False)
+                          f64_exact=f64_exact_default(kw["score_type"]))
     # idempotence: a second pass over the same resident batch returns the same bytes
     gf2, gc2 = sc.score_batch(spectra)
     sel = (np.arange(len(gf)) % kw["report_psms"]) < np.repeat(gc, kw["report_psms"])
