@@ -209,6 +209,18 @@ struct DbView {
     uint8_t kinds[MAX_KINDS];
 };
 
+// Secondary index for open search (k_prelim_wide): the same fragments grouped by PEPTIDE BLOCK (`block` consecutive PeptideIx == one
+// shared-memory count tile) and sorted by m/z inside a block, so the entries matching one (peak, charge) probe inside one tile are a single
+// contiguous run found through a per-block m/z LUT — instead of filtering every entry of the page slices (database.rs:514-534 visits ~9x more
+// entries than match). Built lazily per db the first time a scorer meets a window wider than NARROW_CAP (sage_b200.cu: db_wide_index).
+struct WideIndexView {
+    const uint2* frag;        // {PeptideIx, m/z bits}, block-major, ascending m/z inside a block; nullptr = not built (page-slice streaming is used)
+    const uint64_t* blk_off;  // [n_block + 1]
+    const uint32_t* lut;      // [n_block][cells + 1]: #{entries of the block with m/z < base + c / inv_w}
+    uint32_t block, n_block, cells;
+    float base, inv_w;
+};
+
 struct ScorerView {
     Tol precursor_tol, fragment_tol;
     uint32_t min_matched_peaks;

@@ -620,19 +620,22 @@ struct WideFast {                            // fast path: all tile boundaries o
     uint32_t vpage[WIDE_VCAP];
     float vflo[WIDE_VCAP], vfhi[WIDE_VCAP];
 };
+constexpr uint32_t WIDE_TMAX = 2048;         // (peak, charge) probes per query handled by the block-index path
+constexpr int WIDE_WALK_UNROLL = 4;          // probes a warp walks concurrently (independent loads in flight)
+struct WideBlk { float flo[WIDE_TMAX], fhi[WIDE_TMAX]; };   // Tolerance::bounds of every probe of the query
 struct WideSmem {
     uint32_t cnt32[WIDE_TILE / 2];
-    union { WideSlow slow; WideFast fast; } u;
+    union { WideSlow slow; WideFast fast; WideBlk blk; } u;
     uint64_t heap[K_MAX];
     uint64_t queue[2 * WIDE_THREADS];
     uint32_t s_warp[40];
     uint32_t hist[WIDE_HLEV];   // entries seen in earlier tiles with matched == level (level 63 = >= 63)
-    uint32_t s_item, s_slot, s_level, s_listn, s_serial, s_nranges, s_nvis, s_fast;
+    uint32_t s_item, s_slot, s_level, s_listn, s_serial, s_nranges, s_nvis, s_fast, s_lit /* literal first-k slots already listed */;
 };
 
 
 __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, ScorerView sc, BatchView b, uint32_t n_items, uint64_t* wlist,
-                                                                   WideSlot* wslots) {
+                                                                   WideSlot* wslots, WideIndexView wv) {
     extern __shared__ __align__(16) unsigned char wide_raw[];
     WideSmem& S = *reinterpret_cast<WideSmem*>(wide_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = WIDE_THREADS / 32;
@@ -645,7 +648,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
             S.s_item = w < nw ? b.wide_items[w] : n_items;
             if (w < nw) {
                 S.s_slot = (uint32_t)w;
-                S.s_level = 1; S.s_listn = 0; S.s_serial = 0;
+                S.s_level = 1; S.s_listn = 0; S.s_serial = 0; S.s_lit = 0;
             }
         }
         if (tid < WIDE_HLEV) S.hist[tid] = 0;
@@ -661,9 +664,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         const uint32_t n = q.potential;                       // dense slots of this window
         const uint32_t k = min(n, sc.kparam);                 // n > NARROW_CAP > k here
         const uint32_t TILE = sc.wide_tile;                   // <= WIDE_TILE (smaller only in tests, to exercise the multi-tile logic)
-        // two short leading tiles tighten the matched-count bound early (keeps the survivor lists short), then full tiles
+        // Block mode (secondary index present): tile t == peptide block b0 + t of the block-major, m/z-sorted index copy; a probe's matches inside
+        // a tile are one contiguous run of that block. Otherwise (index not built / too many probes): page-slice streaming with two short leading
+        // tiles that tighten the matched-count bound early (keeps the survivor lists short), then full tiles.
+        const bool blockmode = wv.frag != nullptr && wv.block == TILE && ntask <= WIDE_TMAX;
+        const uint32_t blk0 = blockmode ? q.pre_lo / TILE : 0;
         const uint32_t T0 = max(TILE / 8, 256u) & ~7u, T1 = max(TILE / 4, 256u) & ~7u;
-        const uint32_t ntiles = n <= T0 ? 1 : (n <= T0 + T1 ? 2 : 2 + (n - T0 - T1 + TILE - 1) / TILE);
+        const uint32_t ntiles = blockmode ? q.pre_hi / TILE - blk0 + 1 : (n <= T0 ? 1 : (n <= T0 + T1 ? 2 : 2 + (n - T0 - T1 + TILE - 1) / TILE));
         uint32_t my_matched = 0, my_pages = 0, nz = 0;
         uint32_t msum = 0;   // sum of all slot counts == matched_peaks of this query (replaces per-match counting in the streaming loop)
         long long my_entries = 0;
@@ -671,7 +678,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
 
         // ---- fast path setup: enumerate the page visits of every (peak, charge) probe and resolve all tile boundaries at once
         const uint32_t nb1 = ntiles + 1;
-        if (tid == 0) { S.s_nvis = 0; S.s_fast = (nb1 <= WIDE_BT && db.bucket_size <= 65535u) ? 1u : 0u; }
+        if (tid == 0) { S.s_nvis = 0; S.s_fast = (!blockmode && nb1 <= WIDE_BT && db.bucket_size <= 65535u) ? 1u : 0u; }
+        if (blockmode) {   // Tolerance::bounds of every (peak, fragment charge) probe, once per query
+            for (uint32_t t = tid; t < ntask; t += WIDE_THREADS) {
+                const uint32_t p = t / nfc, fc = t - p * nfc + 1;
+                const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
+                tol_bounds(sc.fragment_tol, mass, S.u.blk.flo[t], S.u.blk.fhi[t]);
+            }
+        }
         __syncthreads();
         if (S.s_fast) {
             WideFast& F = S.u.fast;
@@ -712,8 +726,9 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         const bool fast = S.s_fast != 0;
 
         for (uint32_t tile = 0; tile < ntiles; tile++) {
-            const uint32_t d0 = tile == 0 ? 0 : (tile == 1 ? T0 : T0 + T1 + (tile - 2) * TILE);   // first dense slot of the tile
-            const uint32_t dn = min(tile == 0 ? T0 : (tile == 1 ? T1 : TILE), n - d0);            // slots in the tile
+            // first dense slot of the tile / slots in the tile
+            const uint32_t d0 = blockmode ? max(q.pre_lo, (blk0 + tile) * TILE) - q.pre_lo : (tile == 0 ? 0 : (tile == 1 ? T0 : T0 + T1 + (tile - 2) * TILE));
+            const uint32_t dn = blockmode ? min(q.pre_hi + 1, (blk0 + tile + 1) * TILE) - (q.pre_lo + d0) : min(tile == 0 ? T0 : (tile == 1 ? T1 : TILE), n - d0);
             const uint32_t pep_lo = q.pre_lo + d0;                         // PeptideIx of slot d0
             const bool last_tile = tile + 1 == ntiles;
             const bool tile_entered_serial = S.s_serial != 0;  // uniform: s_serial only changes between barriers at the end of a tile
@@ -721,7 +736,57 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
             const uint32_t pep_hi_excl = last_tile ? q.pre_hi + 1 : pep_lo + dn;
             for (uint32_t i = tid; i < (dn + 1) / 2; i += WIDE_THREADS) S.cnt32[i] = 0;
             __syncthreads();
-            if (fast) {
+            if (blockmode) {
+                // every probe's matches inside this tile are ONE run of the block's m/z-sorted entries: start from the per-block m/z LUT (one
+                // cell early: conservative), walk 32 coalesced entries at a time while the run can continue, exact filter on the values
+                // (database.rs:526-533: PeptideIx inside the edge-filtered window, m/z inside [flo, fhi]). A warp walks WIDE_WALK_UNROLL
+                // probes concurrently.
+                const uint32_t blk = blk0 + tile;
+                const uint2* const ent = wv.frag + wv.blk_off[blk];
+                const uint32_t blen = (uint32_t)(wv.blk_off[blk + 1] - wv.blk_off[blk]);
+                const uint32_t* const lutb = wv.lut + (size_t)blk * (wv.cells + 1);
+                const uint32_t t_lo = max(q.eff_lo, pep_lo);
+                const uint32_t t_hi = min(q.eff_hi, pep_hi_excl - 1);
+                const bool t_any = q.eff_lo <= q.eff_hi && t_lo <= t_hi;
+                const uint32_t t_span = t_any ? t_hi - t_lo : 0u;
+                for (uint32_t j0 = warp * WIDE_WALK_UNROLL; t_any && j0 < ntask; j0 += nwarps * WIDE_WALK_UNROLL) {
+                    float flo[WIDE_WALK_UNROLL], fhi[WIDE_WALK_UNROLL];
+                    uint32_t pos[WIDE_WALK_UNROLL];
+                    bool live[WIDE_WALK_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < WIDE_WALK_UNROLL; u++) {
+                        const uint32_t j = j0 + u;
+                        live[u] = j < ntask;
+                        flo[u] = live[u] ? S.u.blk.flo[j] : 0.0f;
+                        fhi[u] = live[u] ? S.u.blk.fhi[j] : 0.0f;
+                        const float tt = (flo[u] - wv.base) * wv.inv_w;
+                        const int c = tt > 1.0f ? (int)fminf(tt, (float)(wv.cells - 1)) - 1 : 0;   // NaN -> cell 0
+                        pos[u] = live[u] ? __ldg(lutb + c) : blen;
+                    }
+                    for (;;) {
+                        uint2 f[WIDE_WALK_UNROLL];
+#pragma unroll
+                        for (int u = 0; u < WIDE_WALK_UNROLL; u++) {
+                            const uint32_t e = pos[u] + lane;
+                            f[u] = (live[u] && e < blen) ? __ldg(ent + e) : make_uint2(0xFFFFFFFFu, 0x7F800000u);   // past the block: +inf ends the run
+                        }
+                        bool any_live = false;
+#pragma unroll
+                        for (int u = 0; u < WIDE_WALK_UNROLL; u++) {
+                            const float m = __uint_as_float(f[u].y);
+                            if (m >= flo[u] && m <= fhi[u] && f[u].x - t_lo <= t_span) {
+                                const uint32_t idx = f[u].x - pep_lo;
+                                atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                            }
+                            // entries ascend in m/z: the run can only continue while the last entry fetched is still <= fhi
+                            live[u] = live[u] && __shfl_sync(0xffffffffu, m <= fhi[u], 31);
+                            pos[u] += 32;
+                            any_live |= live[u];
+                        }
+                        if (!any_live) break;
+                    }
+                }
+            } else if (fast) {
                 // stream every visit's sub-slice of this tile: one warp walks two visits at a time, 4 coalesced 8-byte entries per lane
                 // from each (8 loads = 2 KB in flight per warp, 32 KB per CTA)
                 const WideFast& F = S.u.fast;
@@ -862,17 +927,21 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
             // thread per query. If a list overflows, this CTA replays it itself and continues serially (s_serial).
             auto cnt = [&](uint32_t i) -> uint32_t { return (S.cnt32[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu; };
             uint32_t scan_from = 0;
-            if (tile == 0) {
-                for (uint32_t i = tid; i < k; i += WIDE_THREADS) {
-                    const uint32_t c = cnt(i);
-                    nz += c != 0;
-                    msum += c;
-                    if (c) atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
-                    list[i] = c ? prescore_key(c, q.pre_lo + i, q.charge, q.iso) : PRESCORE_DEFAULT;
+            {   // the literal first k dense slots open the list (they may spread over several tiles when the leading block-mode tiles are short)
+                const uint32_t lit0 = S.s_lit, nlit = min(k - lit0, dn);   // uniform: s_lit only changes behind the barrier below
+                if (nlit) {
+                    for (uint32_t i = tid; i < nlit; i += WIDE_THREADS) {
+                        const uint32_t c = cnt(i);
+                        nz += c != 0;
+                        msum += c;
+                        if (c) atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
+                        list[lit0 + i] = c ? prescore_key(c, pep_lo + i, q.charge, q.iso) : PRESCORE_DEFAULT;
+                    }
+                    __syncthreads();
+                    if (tid == 0) { S.s_lit = lit0 + nlit; S.s_listn = lit0 + nlit; }
+                    scan_from = nlit;
+                    __syncthreads();
                 }
-                if (tid == 0) S.s_listn = k;
-                scan_from = k;
-                __syncthreads();
             }
             if (!S.s_serial) {
                 const uint32_t level = S.s_level;
@@ -1054,6 +1123,46 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
             h->n = k; h->default_run = 0; h->matched_peaks = matched_total; h->scored_candidates = nonzero_total;
             slot->off = list_off; slot->item = item; slot->n_list = S.s_listn; slot->state = S.s_serial ? 1 : 0; slot->k = k;
         }
+    }
+}
+
+// SURVEY.md §8d work counters of the open-search queries in the REFERENCE's terms (pages visited, entries of [inner_left, inner_right) the
+// filter database.rs:514 walks): the block-index path of k_prelim_wide never touches the page layout, so the counters that feed the
+// algorithmic-bytes figure are produced here, one warp per query, from the bucket minima and the page-grid directory alone (no entry is read).
+__global__ void __launch_bounds__(256) k_wide_account(DbView db, ScorerView sc, BatchView b) {
+    const uint32_t lane = threadIdx.x & 31, w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned long long nw = min(b.counters[C_WIDE], (unsigned long long)b.wide_cap);
+    if (w >= nw) return;
+    const uint32_t item = b.wide_items[w];
+    const QueryDesc q = b.queries[item];
+    const uint32_t s = item / sc.qmax;
+    const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
+    const uint32_t nfc = q.nfc, ntask = np * nfc;
+    if (ntask > WIDE_TMAX) return;   // such a query took the page-slice path of k_prelim_wide, which counts for itself
+    unsigned long long pages = 0, entries = 0;
+    for (uint32_t t = lane; t < ntask; t += 32) {
+        const uint32_t p = t / nfc, fc = t - p * nfc + 1;
+        const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
+        float flo, fhi;
+        tol_bounds(sc.fragment_tol, mass, flo, fhi);
+        uint32_t bl, br;
+        bucket_range(db, flo, fhi, bl, br);
+        for (uint32_t page = bl; page < br; page++) {
+            const uint64_t pbase = (uint64_t)page * db.bucket_size;
+            const uint32_t pn = (uint32_t)(min(pbase + db.bucket_size, db.n_frag) - pbase);
+            const uint32_t st = page_lower_bound_dir(db, page, db.frag + pbase, pn, q.pre_lo);        // partition_point(pep < pre_idx_lo)
+            const uint32_t en = page_lower_bound_dir(db, page, db.frag + pbase, pn, q.pre_hi + 1);    // inner_right
+            entries += en - (st == 0 ? 0 : st - 1);                                                     // inner_left = saturating_sub(.., 1)
+            pages++;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        pages += __shfl_down_sync(0xffffffffu, pages, o);
+        entries += __shfl_down_sync(0xffffffffu, entries, o);
+    }
+    if (lane == 0) {
+        if (pages) atomicAdd(b.counters + C_PAGES, pages);
+        if (entries) atomicAdd(b.counters + C_ENTRIES, entries);
     }
 }
 
@@ -2176,6 +2285,46 @@ __global__ void k_build_pep_lut(DbView db, float base, float inv_w, uint32_t* lu
     }
     lut[c] = lo;
 }
+// ---- secondary (open-search) index: keys (block, m/z) of every fragment, block offsets, per-block m/z LUT
+__global__ void k_wide_keys(uint64_t n_frag, const uint2* frag, uint32_t block, uint64_t* key64, uint32_t* pep) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frag) return;
+    const uint2 f = frag[i];
+    key64[i] = ((uint64_t)(f.x / block) << 32) | (uint32_t)((uint32_t)f32_key(__uint_as_float(f.y)) ^ 0x80000000u);   // unsigned order == total_cmp order
+    pep[i] = f.x;
+}
+__global__ void k_wide_pack(uint64_t n_frag, const uint64_t* key64, const uint32_t* pep, uint2* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frag) return;
+    const uint32_t u = (uint32_t)key64[i] ^ 0x80000000u;               // back to the signed total_cmp key ...
+    const uint32_t bits = u ^ (((uint32_t)((int)u >> 31)) >> 1);        // ... and to the float's bit pattern (f32_key is an involution)
+    out[i] = make_uint2(pep[i], bits);
+}
+__global__ void k_wide_block_offsets(uint64_t n_frag, const uint64_t* key64, uint32_t n_block, uint64_t* blk_off) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_block) return;
+    uint64_t lo = 0, hi = n_frag;
+    const uint64_t want = (uint64_t)b << 32;
+    while (lo < hi) { const uint64_t m = (lo + hi) >> 1; if (key64[m] < want) lo = m + 1; else hi = m; }
+    blk_off[b] = lo;
+}
+__global__ void k_wide_lut(WideIndexView w, uint32_t* lut) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t per = (uint64_t)w.cells + 1;
+    if (j >= (uint64_t)w.n_block * per) return;
+    const uint32_t b = (uint32_t)(j / per), c = (uint32_t)(j - (uint64_t)b * per);
+    const uint2* e = w.frag + w.blk_off[b];
+    const uint32_t n = (uint32_t)(w.blk_off[b + 1] - w.blk_off[b]);
+    uint32_t lo = 0;
+    if (c == w.cells) lo = n;
+    else if (c > 0) {
+        const float edge = w.base + (float)c * (1.0f / w.inv_w);
+        uint32_t hi = n;
+        while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__uint_as_float(e[m].y) < edge) lo = m + 1; else hi = m; }
+    }
+    lut[j] = lo;
+}
+
 __global__ void k_build_bucket_lut(DbView db, float base, float inv_w, uint32_t* lut) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= BUCKET_LUT_CELLS) return;

@@ -113,6 +113,12 @@ struct sage_b200_db {
          *d_pep_flags = nullptr, *d_pep_missed = nullptr;
     uint64_t total_residues = 0, device_bytes = 0;
     int sm_count = 148;
+    // secondary index for open search (WideIndexView), built lazily by the first scorer that meets a wide window; guarded by wmu
+    mutable std::mutex wmu;
+    mutable WideIndexView wv{};
+    mutable void *d_wfrag = nullptr, *d_wblk = nullptr, *d_wlut = nullptr;
+    mutable int wide_failed = 0;
+    mutable uint64_t wide_bytes = 0;
 };
 
 static int dmalloc(sage_b200_db* db, void** p, size_t bytes) {
@@ -227,7 +233,7 @@ extern "C" int sage_b200_device_count(void) {
 extern "C" void sage_b200_db_destroy(sage_b200_db* db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    void* ps[] = {db->d_page_grid, db->d_bucket_lut, db->d_pep_lut, db->d_frag, db->d_bucket_min, db->d_pep_mono, db->d_ion_off, db->d_ions, db->d_pep_len, db->d_pep_flags, db->d_pep_missed};
+    void* ps[] = {db->d_wfrag, db->d_wblk, db->d_wlut, db->d_page_grid, db->d_bucket_lut, db->d_pep_lut, db->d_frag, db->d_bucket_min, db->d_pep_mono, db->d_ion_off, db->d_ions, db->d_pep_len, db->d_pep_flags, db->d_pep_missed};
     for (void* p : ps)
         if (p) cudaFree(p);
     delete db;
@@ -462,6 +468,75 @@ extern "C" int sage_b200_db_export_index(const sage_b200_db* db, uint32_t* fragm
     }
     if (bucket_min && db->v.n_bucket) CUDA_TRY(cudaMemcpy(bucket_min, db->d_bucket_min, 4ull * db->v.n_bucket, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+// Secondary index for open search (device_common.cuh: WideIndexView): fragments keyed by (PeptideIx / block, m/z), one LSD radix sort, block
+// offsets and a per-block m/z LUT. `block` = the scorer's count-tile size. Returns a view with frag == nullptr when the index cannot be built
+// (out of memory, SAGE_B200_NO_WIDE_INDEX=1): k_prelim_wide then streams the page slices as the reference does.
+static WideIndexView db_wide_index(const sage_b200_db* db, uint32_t block) {
+    std::lock_guard<std::mutex> lock(db->wmu);
+    WideIndexView none{};
+    if (const char* e = getenv("SAGE_B200_NO_WIDE_INDEX")) if (e[0] == '1') return none;   // A/B + tests: stream the page slices instead
+    if (db->wv.frag != nullptr && db->wv.block == block) return db->wv;
+    if (db->wide_failed || block == 0 || db->v.n_frag == 0 || db->v.n_pep == 0) return none;
+    const uint64_t nf = db->v.n_frag;
+    cudaDeviceSynchronize();   // a rebuild with another block size (tests) must not free arrays a kernel still reads
+    for (void** p : {&db->d_wfrag, &db->d_wblk, &db->d_wlut}) { if (*p) cudaFree(*p); *p = nullptr; }
+    db->wv = WideIndexView{};
+    void *k_a = nullptr, *k_b = nullptr, *p_a = nullptr, *p_b = nullptr, *tmp = nullptr;
+    auto cleanup = [&]() { for (void* p : {k_a, k_b, p_a, p_b, tmp}) if (p) cudaFree(p); };
+    auto give_up = [&]() { cleanup(); for (void** p : {&db->d_wfrag, &db->d_wblk, &db->d_wlut}) { if (*p) cudaFree(*p); *p = nullptr; } cudaGetLastError(); db->wide_failed = 1; return WideIndexView{}; };
+    const uint32_t n_block = (db->v.n_pep + block - 1) / block;
+    uint32_t cells = 65536;
+    while (cells > 256 && (uint64_t)n_block * (cells + 1) * 4 > (512ull << 20)) cells >>= 1;
+    if (cudaMalloc(&db->d_wfrag, 8 * nf + 64) != cudaSuccess || cudaMalloc(&db->d_wblk, 8 * ((size_t)n_block + 1)) != cudaSuccess ||
+        cudaMalloc(&db->d_wlut, 4 * (size_t)n_block * (cells + 1)) != cudaSuccess)
+        return give_up();
+    if (cudaMalloc(&k_a, 8 * nf) != cudaSuccess || cudaMalloc(&k_b, 8 * nf) != cudaSuccess || cudaMalloc(&p_a, 4 * nf) != cudaSuccess ||
+        cudaMalloc(&p_b, 4 * nf) != cudaSuccess)
+        return give_up();
+    k_wide_keys<<<(unsigned)((nf + 255) / 256), 256>>>(nf, db->v.frag, block, (uint64_t*)k_a, (uint32_t*)p_a);
+    int nb_bits = 1;
+    while (nb_bits < 32 && (n_block >> nb_bits)) nb_bits++;
+    size_t tb = 0;
+    if (nf > 0x7FFFFFFFull) return give_up();
+    if (cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint64_t*)k_a, (uint64_t*)k_b, (const uint32_t*)p_a, (uint32_t*)p_b, (int)nf, 0, 32 + nb_bits) != cudaSuccess ||
+        cudaMalloc(&tmp, tb + 16) != cudaSuccess ||
+        cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint64_t*)k_a, (uint64_t*)k_b, (const uint32_t*)p_a, (uint32_t*)p_b, (int)nf, 0, 32 + nb_bits) != cudaSuccess)
+        return give_up();
+    k_wide_pack<<<(unsigned)((nf + 255) / 256), 256>>>(nf, (const uint64_t*)k_b, (const uint32_t*)p_b, (uint2*)db->d_wfrag);
+    k_wide_block_offsets<<<(n_block + 1 + 255) / 256, 256>>>(nf, (const uint64_t*)k_b, n_block, (uint64_t*)db->d_wblk);
+    if (cudaDeviceSynchronize() != cudaSuccess) return give_up();
+    cleanup();
+    k_a = k_b = p_a = p_b = tmp = nullptr;
+    // m/z range of the index: smallest = first bucket minimum, largest = the largest last entry of any block
+    std::vector<uint64_t> off(n_block + 1);
+    if (cudaMemcpy(off.data(), db->d_wblk, 8 * ((size_t)n_block + 1), cudaMemcpyDeviceToHost) != cudaSuccess) return give_up();
+    float lo = INFINITY, hi = -INFINITY;
+    for (uint32_t bI = 0; bI < n_block; bI++) {
+        if (off[bI + 1] == off[bI]) continue;
+        uint2 first, last;
+        if (cudaMemcpy(&first, (const uint2*)db->d_wfrag + off[bI], 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(&last, (const uint2*)db->d_wfrag + off[bI + 1] - 1, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return give_up();
+        float a, z;
+        memcpy(&a, &first.y, 4); memcpy(&z, &last.y, 4);
+        lo = std::min(lo, a); hi = std::max(hi, z);
+    }
+    WideIndexView w{};
+    w.frag = (const uint2*)db->d_wfrag; w.blk_off = (const uint64_t*)db->d_wblk; w.lut = (const uint32_t*)db->d_wlut;
+    w.block = block; w.n_block = n_block; w.cells = cells;
+    const float width = (hi - lo) / (float)cells;
+    w.base = std::isfinite(lo) ? lo : 0.0f;
+    w.inv_w = (std::isfinite(width) && width > 0.0f) ? 1.0f / width : 0.0f;
+    if (w.inv_w > 0.0f) {
+        const uint64_t total = (uint64_t)n_block * (cells + 1);
+        k_wide_lut<<<(unsigned)((total + 255) / 256), 256>>>(w, (uint32_t*)db->d_wlut);
+    } else if (cudaMemset(db->d_wlut, 0, 4 * (size_t)n_block * (cells + 1)) != cudaSuccess) return give_up();   // degenerate range: every walk starts at the block start
+    if (cudaDeviceSynchronize() != cudaSuccess) return give_up();
+    db->wv = w;
+    db->wide_bytes = 8 * nf + 8 * ((uint64_t)n_block + 1) + 4ull * n_block * (cells + 1);
+    return w;
 }
 
 // Dynamic shared-memory opt-in of the kernels that need more than 48 KB: set ONCE per device to the device maximum (the attribute is per-function,
@@ -934,8 +1009,14 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     launches += 3;
     if (C.wide_cap) {
         const int ctas = (int)std::min<uint64_t>((uint64_t)db->sm_count, C.wide_cap);
-        k_prelim_wide<<<ctas, WIDE_THREADS, sizeof(WideSmem), st>>>(db->v, sv, bv, (uint32_t)C.nitems, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>());
+        const WideIndexView wv = db_wide_index(db, sv.wide_tile);   // built on first use (the first open-search chunk of a scorer is a re-run anyway)
+        k_prelim_wide<<<ctas, WIDE_THREADS, sizeof(WideSmem), st>>>(db->v, sv, bv, (uint32_t)C.nitems, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>(), wv);
         CUDA_TRY(cudaGetLastError());
+        if (wv.frag != nullptr) {   // reference-terms work counters of the queries the block-index path counted (no index entry is read)
+            k_wide_account<<<(C.wide_cap + 7) / 8, 256, 0, st>>>(db->v, sv, bv);
+            CUDA_TRY(cudaGetLastError());
+            launches++;
+        }
         k_replay<<<(unsigned)((C.wide_cap + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(
             sv, bv, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>(), C.wide_cap, L.d_counters.as<unsigned long long>() + C_WIDE, 0u);
         CUDA_TRY(cudaGetLastError());
@@ -1071,6 +1152,21 @@ static int check_spectra(const sage_b200_spectra* sp) {
     return 0;
 }
 
+// Error exit of a batch call: the other lane may still have an H2D reading the caller's arrays or a D2H writing into them. Drain both lanes
+// before the error is returned, so the caller may free or reuse its buffers at once; the error message of the failure is preserved.
+static int drain_lanes(sage_b200_scorer* S, int rc) {
+    const std::string msg = g_last_error;
+    for (Lane& L : S->lanes) {
+        if (L.copy) cudaStreamSynchronize(L.copy);
+        if (L.stream) cudaStreamSynchronize(L.stream);
+        L.chunk.loaded = false; L.ran = false; L.downloading = false;
+    }
+    cudaGetLastError();
+    S->frag_dst = nullptr;
+    g_last_error = msg;
+    return rc;
+}
+
 extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectra* sp, sage_b200_feature* features, uint32_t* counts,
                                      sage_b200_fragment* fragments, uint64_t fragment_capacity, uint64_t* fragments_used) {
     if (!S) return fail(SAGE_B200_EINVAL, "score_batch: null scorer");
@@ -1109,18 +1205,18 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
         uint64_t c1 = std::min<uint64_t>(sp->n, c0 + (c0 == 0 && first ? first : target));
         while (c1 > c0 + 1 && sp->peak_offsets[c1] - sp->peak_offsets[c0] > max_peaks) c1 = c0 + (c1 - c0) / 2;
         Lane& L = S->lanes[li];
-        if ((rc = lane_finish(S, L))) return rc;   // the chunk that used this lane two iterations ago
+        if ((rc = lane_finish(S, L))) return drain_lanes(S, rc);   // the chunk that used this lane two iterations ago
         const double ti0 = S->trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S->t_base).count() : 0.0;
-        if ((rc = chunk_upload(S, L, sp, c0, c1))) return rc;
-        if ((rc = chunk_run(S, L, false))) return rc;
-        if ((rc = chunk_download(S, L, features + c0 * S->sv.report_psms, counts + c0))) return rc;
+        if ((rc = chunk_upload(S, L, sp, c0, c1))) return drain_lanes(S, rc);
+        if ((rc = chunk_run(S, L, false))) return drain_lanes(S, rc);
+        if ((rc = chunk_download(S, L, features + c0 * S->sv.report_psms, counts + c0))) return drain_lanes(S, rc);
         if (S->trace) { L.chunk.t_issue0 = ti0; L.chunk.t_issue1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S->t_base).count(); }
-        if (annotate && (rc = lane_finish(S, L))) return rc;   // fragment offsets are global: chunks run one after another
+        if (annotate && (rc = lane_finish(S, L))) return drain_lanes(S, rc);   // fragment offsets are global: chunks run one after another
         c0 = c1;
         if (!annotate) li ^= 1;
     }
     for (Lane& L : S->lanes) {
-        if ((rc = lane_finish(S, L))) return rc;
+        if ((rc = lane_finish(S, L))) return drain_lanes(S, rc);
         L.chunk.loaded = false;
     }
     finish_counters(S);
@@ -1246,7 +1342,7 @@ extern "C" int sage_b200_quick_score(sage_b200_scorer* S, const sage_b200_spectr
     }
     S->quick_mode = 0;
     L.chunk.loaded = false;
-    if (rc) return rc;
+    if (rc) return drain_lanes(S, rc);
     std::vector<uint8_t> h(npep);
     CUDA_TRY(cudaMemcpy(h.data(), S->d_keep.p, npep, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < npep; i++) keep[i] |= h[i];

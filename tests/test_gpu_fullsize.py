@@ -1,4 +1,4 @@
-"""BASELINE.json-size checks (cfg2 / cfg4 shapes: ~1.9 M peptides, 49 M fragments): oracle parity on samples the CPU finishes in seconds,
+"""BASELINE.json-size checks (cfg2 / cfg4 / cfg5: ~1.9 M peptides, 49 M fragments; cfg3: ~16 M peptides, ~680 M fragments): oracle parity on samples the CPU finishes in seconds,
 and size-independent properties over the full 50 k-spectrum batch."""
 import numpy as np
 import pytest
@@ -75,3 +75,71 @@ def test_cfg4_sample_parity(full):
     assert_features_equal(gf, gc, of, oc, 1, what="cfg4 sample")
     c = sc.counters()
     assert c["wide_queries"] == 96 and c["entries_scanned"] == octr["entries_scanned"] and c["pages"] == octr["pages"]
+
+
+def test_cfg5_at_size_chimeric_sample_parity(full):
+    """BASELINE.json configs[4] at its stated size: 100k co-fragmenting spectra, chimera = true, report_psms = 5, against the ~2M-peptide index.
+    Oracle parity on 3 x 1000-spectrum samples; properties over all 100k (rank == round, at most 5 PSMs, peaks are consumed)."""
+    pep, _, gdb, odb = full
+    chim = synth.make_spectra(pep, 100_000, seed=0xB205, chimeric=True)
+    kw = dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), chimera=True, report_psms=5)
+    sc = Scorer(gdb, **kw)
+    gf, gc = sc.score_batch(chim)
+    total = 0
+    for a in (0, 48_000, 99_000):
+        sub = chim.slice(a, a + 1000)
+        of, oc, _, _ = odb.score_batch(oracle_cfg(**kw), sub.as_dict())
+        of = of.copy()
+        of["spectrum"] += np.uint32(a)
+        total += assert_features_equal(gf[5 * a:5 * (a + 1000)], gc[a:a + 1000], of, oc, 5, what=f"cfg5 sample @{a}")
+    assert total > 4000
+    sel = (np.arange(len(gf)) % 5) < np.repeat(gc, 5)
+    g = gf[sel]
+    assert gc.max() <= 5 and gc.sum() > 150_000
+    assert np.array_equal(g["rank"], (np.arange(len(gf)) % 5)[sel] + 1)          # chimera: rank == round (scoring.rs:662)
+    assert np.all(g["matched_peaks"] >= 4)
+
+
+@pytest.fixture(scope="module")
+def cfg3():
+    """BASELINE.json configs[2]: human-tryptic-scale digest + 2 variable modifications (M+15.9949, STY+79.9663, up to 2 per peptide) + static C:
+    ~16 M peptides, ~680 M fragments (the same table bench.py's cfg3 uses)."""
+    pep = synth.make_peptides(2_000_000, var_mods=(("M", 15.9949), ("STY", 79.9663)), max_variable_mods=2, static_c=True)
+    gdb = IndexedDatabase.build_from_peptides(pep)
+    odb = oracle_db_from_peptides(pep)
+    return pep, gdb, odb
+
+
+def test_cfg3_index_matches_oracle_at_size(cfg3):
+    pep, gdb, odb = cfg3
+    assert len(pep) > 14_000_000 and gdb.info["n_fragments"] > 400_000_000
+    fp, fm, bm = gdb.export_index()
+    e = odb.export()
+    assert np.array_equal(bm.view(np.uint32), e["bucket_min"].view(np.uint32))
+    step = 1 << 26   # compare in slices: the arrays are 2.7 GB each
+    for a in range(0, len(fp), step):
+        assert np.array_equal(fp[a:a + step], e["frag_pep"][a:a + step]), a
+        assert np.array_equal(fm[a:a + step].view(np.uint32), e["frag_mz"][a:a + step].view(np.uint32)), a
+
+
+def test_cfg3_at_size_sample_parity(cfg3):
+    """200k spectra sharded over 8 GPUs = 25k per GPU: one shard here, oracle parity on 3 x 1000 spectra of it, plus an isotope-error /
+    report_psms variant on a smaller sample (the variable-mod index puts many isobaric positional isomers into every precursor window)."""
+    pep, gdb, odb = cfg3
+    spectra = synth.make_spectra(pep, 25_000, seed=0xB203)
+    kw = dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20))
+    sc = Scorer(gdb, **kw)
+    gf, gc = sc.score_batch(spectra)
+    total = 0
+    for a in (0, 12_000, 24_000):
+        sub = spectra.slice(a, a + 1000)
+        of, oc, _, _ = odb.score_batch(oracle_cfg(**kw), sub.as_dict())
+        of = of.copy()
+        of["spectrum"] += np.uint32(a)
+        total += assert_features_equal(gf[a:a + 1000], gc[a:a + 1000], of, oc, 1, what=f"cfg3 sample @{a}")
+    assert total > 2500
+    kw2 = dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=5, min_isotope_err=-1, max_isotope_err=2)
+    sub = spectra.slice(5000, 5400)
+    g2, c2 = Scorer(gdb, **kw2).score_batch(sub)
+    o2, oc2, _, _ = odb.score_batch(oracle_cfg(**kw2), sub.as_dict())
+    assert assert_features_equal(g2, c2, o2, oc2, 5, what="cfg3 isotope errors, report_psms 5") > 800

@@ -1,4 +1,6 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -138,16 +140,19 @@ def test_open_search_multi_tile(small):
     kw = dict(precursor_tol=Tolerance.da(-800, 800), fragment_tol=Tolerance.ppm(-20, 20), report_psms=3)
     sub = spectra.slice(0, 200)
     of, oc, _, octr = odb.score_batch(oracle_cfg(**kw), sub.as_dict(), counters=True)
-    for tile in (1024, 4096, 81920):
-        sc = Scorer(gdb, **kw)
-        sc.set_option("wide_tile", tile)
-        gf, gc = sc.score_batch(sub)
-        assert_features_equal(gf, gc, of, oc, 3, what=f"wide_tile={tile}")
+    # both counting strategies of k_prelim_wide: the block-major m/z-sorted index copy (default) and page-slice streaming (the reference's loop)
+    for tile, pages_mode in ((1024, False), (4096, False), (81920, False), (512, False), (1024, True), (81920, True)):
+        os.environ["SAGE_B200_NO_WIDE_INDEX"] = "1" if pages_mode else "0"
+        try:
+            sc = Scorer(gdb, **kw)
+            sc.set_option("wide_tile", tile)
+            gf, gc = sc.score_batch(sub)
+        finally:
+            os.environ.pop("SAGE_B200_NO_WIDE_INDEX", None)
+        assert_features_equal(gf, gc, of, oc, 3, what=f"wide_tile={tile} pages_mode={pages_mode}")
         c = sc.counters()
-        if c["wide_queries"] == c["queries"]:
-            for k in ("pages", "entries_scanned", "matched_fragments" if False else "pages"):
-                assert c[k] == octr[k], (tile, k, c[k], octr[k])
-            assert c["entries_scanned"] == octr["entries_scanned"]
+        if c["wide_queries"] == c["queries"]:   # the reference-terms work counters are the oracle's in both modes
+            assert c["pages"] == octr["pages"] and c["entries_scanned"] == octr["entries_scanned"], (tile, pages_mode, c["pages"], octr["pages"])
     # survivor-list overflow at various points -> the counting CTA replays and continues serially
     for lmax, tile in ((128, 1024), (200, 4096), (600, 2048), (3000, 1024)):
         sc = Scorer(gdb, **kw)
