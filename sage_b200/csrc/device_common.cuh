@@ -14,7 +14,7 @@ constexpr uint32_t NARROW_CAP = 8192; // precursor windows up to this many pepti
 constexpr int PRELIM_THREADS = 256;
 constexpr int SCORE_THREADS = 128;  // measured on cfg2: 128 (1.66 ms) beats 256 (1.95 ms) and 64 (1.75 ms); must stay >= K_MAX for the rank sort
 #ifndef SAGE_B200_SCORE_MIN_CTAS
-#define SAGE_B200_SCORE_MIN_CTAS 8
+#define SAGE_B200_SCORE_MIN_CTAS 10
 #endif
 constexpr int SCORE_MIN_CTAS = SAGE_B200_SCORE_MIN_CTAS;   // k_score CTAs per SM the register budget is held to (A/B: profiles/r02_*)
 #ifndef SAGE_B200_SCORE_TILE

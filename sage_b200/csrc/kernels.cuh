@@ -622,15 +622,20 @@ struct WideFast {                            // fast path: all tile boundaries o
 };
 constexpr uint32_t WIDE_TMAX = 2048;         // (peak, charge) probes per query handled by the block-index path
 constexpr int WIDE_WALK_UNROLL = 4;          // probes a warp walks concurrently (independent loads in flight)
-struct WideBlk { float flo[WIDE_TMAX], fhi[WIDE_TMAX]; };   // Tolerance::bounds of every probe of the query
+constexpr uint32_t WIDE_QCAP = WIDE_THREADS;  // slots a tile may queue as survivors (one per thread in the ordering step); more -> the tile is scanned instead
+struct WideBlk {
+    float flo[WIDE_TMAX], fhi[WIDE_TMAX];    // Tolerance::bounds of every probe of the query
+    uint32_t qslot[WIDE_QCAP];               // tile-relative slots whose count reached the survivor level during the walk (unordered)
+};
 struct WideSmem {
-    uint32_t cnt32[WIDE_TILE / 2];
+    uint32_t cnt32[WIDE_TILE / 2 + 4];   // + slack: a block-mode tile can hold TILE + 1 slots (the phantom slot pre_idx_hi == n_pep)
     union { WideSlow slow; WideFast fast; WideBlk blk; } u;
     uint64_t heap[K_MAX];
     uint64_t queue[2 * WIDE_THREADS];
     uint32_t s_warp[40];
     uint32_t hist[WIDE_HLEV];   // entries seen in earlier tiles with matched == level (level 63 = >= 63)
     uint32_t s_item, s_slot, s_level, s_listn, s_serial, s_nranges, s_nvis, s_fast, s_lit /* literal first-k slots already listed */;
+    uint32_t s_qn /* survivor candidates queued in this tile */, s_tnext /* next probe group of this tile (dynamic distribution over the warps) */;
 };
 
 
@@ -670,7 +675,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         const bool blockmode = wv.frag != nullptr && wv.block == TILE && ntask <= WIDE_TMAX;
         const uint32_t blk0 = blockmode ? q.pre_lo / TILE : 0;
         const uint32_t T0 = max(TILE / 8, 256u) & ~7u, T1 = max(TILE / 4, 256u) & ~7u;
-        const uint32_t ntiles = blockmode ? q.pre_hi / TILE - blk0 + 1 : (n <= T0 ? 1 : (n <= T0 + T1 ? 2 : 2 + (n - T0 - T1 + TILE - 1) / TILE));
+        // (pre_idx_hi may be n_pep, one past the last peptide: that phantom slot never matches and belongs to the last real block's tile)
+        const uint32_t ntiles = blockmode ? min(q.pre_hi, db.n_pep - 1) / TILE - blk0 + 1 : (n <= T0 ? 1 : (n <= T0 + T1 ? 2 : 2 + (n - T0 - T1 + TILE - 1) / TILE));
         uint32_t my_matched = 0, my_pages = 0, nz = 0;
         uint32_t msum = 0;   // sum of all slot counts == matched_peaks of this query (replaces per-match counting in the streaming loop)
         long long my_entries = 0;
@@ -728,13 +734,23 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         for (uint32_t tile = 0; tile < ntiles; tile++) {
             // first dense slot of the tile / slots in the tile
             const uint32_t d0 = blockmode ? max(q.pre_lo, (blk0 + tile) * TILE) - q.pre_lo : (tile == 0 ? 0 : (tile == 1 ? T0 : T0 + T1 + (tile - 2) * TILE));
-            const uint32_t dn = blockmode ? min(q.pre_hi + 1, (blk0 + tile + 1) * TILE) - (q.pre_lo + d0) : min(tile == 0 ? T0 : (tile == 1 ? T1 : TILE), n - d0);
+            const uint32_t dn = blockmode ? (tile + 1 == ntiles ? q.pre_hi + 1 : (blk0 + tile + 1) * TILE) - (q.pre_lo + d0)   // <= TILE + 1 (phantom slot)
+                                          : min(tile == 0 ? T0 : (tile == 1 ? T1 : TILE), n - d0);
             const uint32_t pep_lo = q.pre_lo + d0;                         // PeptideIx of slot d0
             const bool last_tile = tile + 1 == ntiles;
             const bool tile_entered_serial = S.s_serial != 0;  // uniform: s_serial only changes between barriers at the end of a tile
             // exclusive PeptideIx bound of the tile; the last tile ends at pre_hi + 1 so that its end == inner_right (database.rs:506-511)
             const uint32_t pep_hi_excl = last_tile ? q.pre_hi + 1 : pep_lo + dn;
-            for (uint32_t i = tid; i < (dn + 1) / 2; i += WIDE_THREADS) S.cnt32[i] = 0;
+            {   // zero the tile's counts, 16 bytes per store
+                uint4* const z = reinterpret_cast<uint4*>(S.cnt32);
+                for (uint32_t i = tid; i < ((dn + 1) / 2 + 3) / 4; i += WIDE_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+            }
+            if (tid == 0) { S.s_qn = 0; S.s_tnext = 0; }
+            // Block mode counts matched_peaks / scored_candidates while it walks (the atomic returns the slot's previous count), and — once the
+            // survivor level is >= 2, i.e. from the second tile on — queues the few slots whose count reaches the level instead of scanning all
+            // `dn` counts of the tile afterwards.
+            const uint32_t tile_level = S.s_level;
+            const bool use_q = blockmode && tile_level >= 2 && !tile_entered_serial;
             __syncthreads();
             if (blockmode) {
                 // every probe's matches inside this tile are ONE run of the block's m/z-sorted entries: start from the per-block m/z LUT (one
@@ -749,7 +765,11 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                 const uint32_t t_hi = min(q.eff_hi, pep_hi_excl - 1);
                 const bool t_any = q.eff_lo <= q.eff_hi && t_lo <= t_hi;
                 const uint32_t t_span = t_any ? t_hi - t_lo : 0u;
-                for (uint32_t j0 = warp * WIDE_WALK_UNROLL; t_any && j0 < ntask; j0 += nwarps * WIDE_WALK_UNROLL) {
+                for (;;) {
+                    uint32_t j0 = 0;   // next group of WIDE_WALK_UNROLL probes (walk lengths vary: dynamic distribution keeps the 32 warps level)
+                    if (lane == 0) j0 = atomicAdd(&S.s_tnext, (uint32_t)WIDE_WALK_UNROLL);
+                    j0 = __shfl_sync(0xffffffffu, j0, 0);
+                    if (!t_any || j0 >= ntask) break;
                     float flo[WIDE_WALK_UNROLL], fhi[WIDE_WALK_UNROLL];
                     uint32_t pos[WIDE_WALK_UNROLL];
                     bool live[WIDE_WALK_UNROLL];
@@ -775,8 +795,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                         for (int u = 0; u < WIDE_WALK_UNROLL; u++) {
                             const float m = __uint_as_float(f[u].y);
                             if (m >= flo[u] && m <= fhi[u] && f[u].x - t_lo <= t_span) {
-                                const uint32_t idx = f[u].x - pep_lo;
-                                atomicAdd(&S.cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                                const uint32_t idx = f[u].x - pep_lo, sh = (idx & 1) * 16;
+                                const uint32_t prev = (atomicAdd(&S.cnt32[idx >> 1], 1u << sh) >> sh) & 0xFFFFu;   // this slot's count before this match
+                                msum++;
+                                nz += prev == 0;
+                                if (use_q && prev + 1 == tile_level) {   // exactly one match sees the slot cross the level
+                                    const uint32_t qi = atomicAdd(&S.s_qn, 1u);
+                                    if (qi < WIDE_QCAP) S.u.blk.qslot[qi] = idx;
+                                }
                             }
                             // entries ascend in m/z: the run can only continue while the last entry fetched is still <= fhi
                             live[u] = live[u] && __shfl_sync(0xffffffffu, m <= fhi[u], 31);
@@ -932,8 +958,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                 if (nlit) {
                     for (uint32_t i = tid; i < nlit; i += WIDE_THREADS) {
                         const uint32_t c = cnt(i);
-                        nz += c != 0;
-                        msum += c;
+                        if (!blockmode) { nz += c != 0; msum += c; }   // block mode counted both while walking
                         if (c) atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
                         list[lit0 + i] = c ? prescore_key(c, pep_lo + i, q.charge, q.iso) : PRESCORE_DEFAULT;
                     }
@@ -945,6 +970,28 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
             }
             if (!S.s_serial) {
                 const uint32_t level = S.s_level;
+                const bool qmode = use_q && S.s_qn <= WIDE_QCAP;   // uniform
+                uint32_t total = 0;
+                bool overflow = false;
+                if (qmode) {
+                    // the tile's survivors are the queued slots (count >= level at the end of the walk, each queued exactly once); order them by
+                    // slot with a rank count (a few dozen entries per tile), skip the literal slots, emit in dense order
+                    const uint32_t nq = S.s_qn;
+                    const uint32_t myslot = tid < nq ? S.u.blk.qslot[tid] : 0xFFFFFFFFu;
+                    const bool valid = tid < nq && myslot >= scan_from;
+                    total = (uint32_t)__syncthreads_count(valid);
+                    overflow = S.s_listn + total > sc.wide_lmax;
+                    if (valid && !overflow) {
+                        uint32_t rank = 0;
+                        for (uint32_t j = 0; j < nq; j++) {
+                            const uint32_t sj = S.u.blk.qslot[j];
+                            rank += sj < myslot && sj >= scan_from;
+                        }
+                        const uint32_t c = cnt(myslot);
+                        list[S.s_listn + rank] = prescore_key(c, pep_lo + myslot, q.charge, q.iso);
+                        atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
+                    }
+                } else {
                 // each warp owns a contiguous segment (multiple of 256 slots, 8-aligned); a lane reads 8 slots with one 16-byte load.
                 // pass 1 counts survivors and feeds the histogram, pass 2 writes them in dense order
                 const uint32_t base0 = scan_from & ~7u;
@@ -969,9 +1016,9 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                         for (int u = 0; u < 4; u++) {
                             nzm += __popc(__vcmpne2(ww[u], 0u));
                             svm += __popc(__vcmpgeu2(ww[u], lvl2) & __vcmpne2(ww[u], 0u));
-                            msum += (ww[u] & 0xFFFFu) + (ww[u] >> 16);
+                            if (!blockmode) msum += (ww[u] & 0xFFFFu) + (ww[u] >> 16);
                         }
-                        nz += nzm >> 4;
+                        if (!blockmode) nz += nzm >> 4;
                         wcount += svm >> 4;
                         if (svm == 0) continue;
                     }
@@ -979,7 +1026,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                     for (int u = 0; u < 8; u++) {
                         const uint32_t c = (ww[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu;
                         if (c && i + u >= scan_from && i + u < dn) {
-                            if (edge) { nz++; wcount += c >= level; msum += c; }
+                            if (edge) { wcount += c >= level; if (!blockmode) { nz++; msum += c; } }
                             if (c >= level) atomicAdd(&S.hist[min(c, WIDE_HLEV - 1)], 1u);
                         }
                     }
@@ -987,13 +1034,13 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                 for (int o = 16; o > 0; o >>= 1) wcount += __shfl_down_sync(0xffffffffu, wcount, o);
                 if (lane == 0) S.s_warp[warp] = wcount;
                 __syncthreads();
-                uint32_t woff = S.s_listn, total = 0;
+                uint32_t woff = S.s_listn;
                 for (uint32_t w = 0; w < nwarps; w++) {
                     const uint32_t x = S.s_warp[w];
                     if (w < warp) woff += x;
                     total += x;
                 }
-                const bool overflow = S.s_listn + total > sc.wide_lmax;
+                overflow = S.s_listn + total > sc.wide_lmax;
                 if (!overflow && S.s_warp[warp] != 0) {
                     for (uint32_t i0 = w_lo; i0 < w_hi; i0 += 256) {
                         const uint32_t i = i0 + 8 * lane;
@@ -1025,6 +1072,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                         woff += __shfl_sync(0xffffffffu, incl, 31);
                     }
                 }
+                }   // scan / queue
                 __syncthreads();
                 if (tid == 0) {
                     if (!overflow) {
@@ -1051,7 +1099,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                 __syncthreads();
             }
             if (S.s_serial) {
-                const bool count_nz = tile_entered_serial;  // pass 1 above already counted this tile's non-zero slots otherwise
+                const bool count_nz = tile_entered_serial && !blockmode;  // pass 1 above (or the block-mode walk) already counted this tile's non-zero slots otherwise
                 for (uint32_t base = scan_from; base < dn; base += 2 * WIDE_THREADS) {
                     uint64_t key[2];
                     uint32_t ncand = 0;

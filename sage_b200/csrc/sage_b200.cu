@@ -12,6 +12,7 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cmath>
 #include <cstdarg>
@@ -94,6 +95,47 @@ struct PinBuf {
         cap = 0;
     }
 };
+
+// Host -> device copy of a PAGEABLE array (a Rust Vec<f32>, a numpy array) through a pinned staging buffer: a few helper threads copy 2 MB pieces
+// into the staging buffer while the calling thread submits each piece's DMA as soon as it is staged, so the memcpy (one core moves ~10 GB/s,
+// PCIe 5 x16 ~55 GB/s) overlaps the transfer instead of preceding it.
+static int staged_h2d(void* dst, const void* src, size_t bytes, PinBuf& stage, cudaStream_t st) {
+    if (bytes == 0) return 0;
+    int rc = stage.reserve(bytes);
+    if (rc) return rc;
+    const size_t piece = 2u << 20;
+    const size_t np = (bytes + piece - 1) / piece;
+    if (np <= 2) {   // small: a plain copy is cheaper than starting threads
+        memcpy(stage.p, src, bytes);
+        CUDA_TRY(cudaMemcpyAsync(dst, stage.p, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    std::vector<std::atomic<unsigned char>> done(np);
+    for (auto& d : done) d.store(0, std::memory_order_relaxed);
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= np) return;
+            const size_t off = i * piece, len = std::min(piece, bytes - off);
+            memcpy((char*)stage.p + off, (const char*)src + off, len);
+            done[i].store(1, std::memory_order_release);
+        }
+    };
+    const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+    const size_t nthreads = std::min<size_t>({(size_t)6, (size_t)hw - 1, np});
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nthreads; t++) th.emplace_back(worker);
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < np && e == cudaSuccess; i++) {
+        while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+        const size_t off = i * piece, len = std::min(piece, bytes - off);
+        e = cudaMemcpyAsync((char*)dst + off, (char*)stage.p + off, len, cudaMemcpyHostToDevice, st);
+    }
+    for (auto& t : th) t.join();
+    if (e != cudaSuccess) return fail(SAGE_B200_ECUDA, "staged host-to-device copy failed: %s", cudaGetErrorString(e));
+    return 0;
+}
 
 static bool is_pinned(const void* p) {
     cudaPointerAttributes a;
@@ -487,8 +529,10 @@ static WideIndexView db_wide_index(const sage_b200_db* db, uint32_t block) {
     auto cleanup = [&]() { for (void* p : {k_a, k_b, p_a, p_b, tmp}) if (p) cudaFree(p); };
     auto give_up = [&]() { cleanup(); for (void** p : {&db->d_wfrag, &db->d_wblk, &db->d_wlut}) { if (*p) cudaFree(*p); *p = nullptr; } cudaGetLastError(); db->wide_failed = 1; return WideIndexView{}; };
     const uint32_t n_block = (db->v.n_pep + block - 1) / block;
-    uint32_t cells = 65536;
-    while (cells > 256 && (uint64_t)n_block * (cells + 1) * 4 > (512ull << 20)) cells >>= 1;
+    // ~2 M entries per 80 k-peptide block, most of them inside a third of the m/z range: 2^18 cells leave a few dozen entries per cell there,
+    // so the conservative (one cell early) start of a walk costs about one extra 32-entry fetch (measured: 2^16 cells -> ~8 extra fetches)
+    uint32_t cells = 1u << 18;
+    while (cells > 256 && (uint64_t)n_block * (cells + 1) * 4 > (1024ull << 20)) cells >>= 1;
     if (cudaMalloc(&db->d_wfrag, 8 * nf + 64) != cudaSuccess || cudaMalloc(&db->d_wblk, 8 * ((size_t)n_block + 1)) != cudaSuccess ||
         cudaMalloc(&db->d_wlut, 4 * (size_t)n_block * (cells + 1)) != cudaSuccess)
         return give_up();
@@ -833,13 +877,10 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
     CUDA_TRY(cudaEventRecord(L.ev[0], cp));
     const float* src_m = sp->masses + pk0;
     const float* src_i = sp->intensities + pk0;
+    const bool pin_m = npk == 0 || is_pinned(src_m), pin_i = npk == 0 || is_pinned(src_i);
     if (npk) {
-        if (!is_pinned(src_m)) {
-            if ((rc = L.h_masses.reserve(4 * npk))) return rc;
-            memcpy(L.h_masses.p, src_m, 4 * npk);
-            src_m = (const float*)L.h_masses.p;
-        }
-        CUDA_TRY(cudaMemcpyAsync(L.d_masses.p, src_m, 4 * npk, cudaMemcpyHostToDevice, cp));
+        if (pin_m) CUDA_TRY(cudaMemcpyAsync(L.d_masses.p, src_m, 4 * npk, cudaMemcpyHostToDevice, cp));
+        else if ((rc = staged_h2d(L.d_masses.p, src_m, 4 * npk, L.h_masses, cp))) return rc;   // pageable caller memory: staged + overlapped
     }
     unsigned char* hs = (unsigned char*)L.h_small.p;
     auto pack = [&]() -> int {   // small per-spectrum arrays -> one pinned blob -> one H2D
@@ -881,11 +922,6 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
         if ((r = L.d_counts.reserve(4 * (size_t)n))) return r;
         if ((r = L.d_counters.reserve(8 * (C_COUNT + (size_t)sv.qmax)))) return r;   // + one in-use flag per query slot
         if ((r = L.h_counters.reserve(8 * C_COUNT + 32))) return r;
-        if (npk && !is_pinned(src_i)) {
-            if ((r = L.h_intens.reserve(4 * npk))) return r;
-            memcpy(L.h_intens.p, src_i, 4 * npk);
-            src_i = (const float*)L.h_intens.p;
-        }
         return 0;
     };
     if ((rc = pack())) {
@@ -894,7 +930,10 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
     }
     CUDA_TRY(cudaMemcpyAsync(L.d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, cp));
     CUDA_TRY(cudaEventRecord(L.ev_masses, cp));   // setup + preliminary scoring can start: they never read intensities
-    if (npk) CUDA_TRY(cudaMemcpyAsync(L.d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, cp));
+    if (npk) {
+        if (pin_i) CUDA_TRY(cudaMemcpyAsync(L.d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, cp));
+        else if ((rc = staged_h2d(L.d_intens.p, src_i, 4 * npk, L.h_intens, cp))) { cudaStreamSynchronize(cp); return rc; }
+    }
     CUDA_TRY(cudaEventRecord(L.ev_intens, cp));
     CUDA_TRY(cudaEventRecord(L.ev[1], cp));
     S->last.h2d_bytes += C.small_bytes + 8 * npk;

@@ -92,7 +92,7 @@ def test_cfg5_at_size_chimeric_sample_parity(full):
         of = of.copy()
         of["spectrum"] += np.uint32(a)
         total += assert_features_equal(gf[5 * a:5 * (a + 1000)], gc[a:a + 1000], of, oc, 5, what=f"cfg5 sample @{a}")
-    assert total > 4000
+    assert total > 3500
     sel = (np.arange(len(gf)) % 5) < np.repeat(gc, 5)
     g = gf[sel]
     assert gc.max() <= 5 and gc.sum() > 150_000

@@ -242,6 +242,24 @@ def test_quick_score_prefilter(small):
         assert np.array_equal(sc.quick_score(sub, True, k0)[:10], np.ones(10, np.uint8))
 
 
+def test_quick_score_fresh_scorer_rerun_leaves_no_stale_marks(small):
+    # a chunk whose work lists overflow is re-run with exact sizes; keep[] is OR-accumulated, so the partial hit sets of the
+    # overflowed attempt must not leave marks behind. Fresh scorers start with an empty open-search work list (wide_cap = 0) and a tiny
+    # narrow arena, so the first chunk of each of these calls is re-run; with charge / isotope folds a partial set changes the final trim.
+    pep, odb, gdb, spectra = small
+    sub = SpectraBatch(**{**spectra.slice(0, 300).__dict__, "prec_charge": np.where(np.arange(300) % 3 == 0, 0, spectra.prec_charge[:300]).astype(np.uint8)})
+    for kw, reset in ((dict(precursor_tol=Tolerance.da(-500, 500), fragment_tol=Tolerance.ppm(-20, 20), min_isotope_err=-1, max_isotope_err=1, report_psms=2), None),
+                      (dict(precursor_tol=Tolerance.da(-30, 30), fragment_tol=Tolerance.ppm(-20, 20), min_isotope_err=-1, max_isotope_err=2, report_psms=1), 0)):
+        for low in (False, True):
+            sc = Scorer(gdb, **kw)   # fresh: nothing learned yet
+            if reset is not None:
+                sc.set_option("worklist_reset", reset)
+            g = sc.quick_score(sub, low)
+            assert sc.counters()["chunk_retries"] > 0
+            o = odb.quick_score(oracle_cfg(**kw), sub.as_dict(), low)
+            assert g.sum() > 100 and np.array_equal(g, o), (kw, low, int(g.sum()), int(o.sum()), int((g != o).sum()))
+
+
 def test_initial_hits_heap_order(small):
     # white box: the preliminary list must come back in the reference's bounded_min_heapify order
     pep, odb, gdb, spectra = small
