@@ -504,10 +504,13 @@ class Scorer:
         return {k: getattr(cc, k) for k, _ in CCounters._fields_}
 
 
-def score_batch_multi(scorers, batch: SpectraBatch):
+def score_batch_multi(scorers, batch: SpectraBatch, out: np.ndarray | None = None, counts: np.ndarray | None = None):
     """sage_b200_score_batch_multi: one process, one Scorer per GPU (same settings), spectra split into contiguous blocks."""
     n, r = len(batch), scorers[0].report_psms
-    out, counts = np.zeros(n * r, FEATURE_DTYPE), np.zeros(n, np.uint32)
+    if out is None:
+        out = np.zeros(n * r, FEATURE_DTYPE)
+    if counts is None:
+        counts = np.zeros(n, np.uint32)
     keep: list = []
     cs = batch._c(keep)
     arr = (C.c_void_p * len(scorers))(*[s._h for s in scorers])

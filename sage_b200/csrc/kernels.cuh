@@ -10,6 +10,8 @@
 //
 // All of this is integer/f32 gather-reduce work bound by memory latency/bandwidth; tensor cores are not used.
 #pragma once
+#include <type_traits>
+
 #include "device_common.cuh"
 #include "glibc_log.cuh"
 
@@ -621,7 +623,7 @@ struct WideFast {                            // fast path: all tile boundaries o
     float vflo[WIDE_VCAP], vfhi[WIDE_VCAP];
 };
 constexpr uint32_t WIDE_TMAX = 2048;         // (peak, charge) probes per query handled by the block-index path
-constexpr int WIDE_WALK_UNROLL = 4;          // probes a warp walks concurrently (independent loads in flight)
+constexpr int WIDE_WALK_UNROLL = 8;          // entries of a run a thread fetches per step (independent loads in flight)
 constexpr uint32_t WIDE_QCAP = WIDE_THREADS;  // slots a tile may queue as survivors (one per thread in the ordering step); more -> the tile is scanned instead
 struct WideBlk {
     float flo[WIDE_TMAX], fhi[WIDE_TMAX];    // Tolerance::bounds of every probe of the query
@@ -753,10 +755,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
             const bool use_q = blockmode && tile_level >= 2 && !tile_entered_serial;
             __syncthreads();
             if (blockmode) {
-                // every probe's matches inside this tile are ONE run of the block's m/z-sorted entries: start from the per-block m/z LUT (one
-                // cell early: conservative), walk 32 coalesced entries at a time while the run can continue, exact filter on the values
-                // (database.rs:526-533: PeptideIx inside the edge-filtered window, m/z inside [flo, fhi]). A warp walks WIDE_WALK_UNROLL
-                // probes concurrently.
+                // every probe's matches inside this tile are ONE run of the block's m/z-sorted entries, located through the per-block m/z LUT;
+                // exact filter on the values (database.rs:526-533: PeptideIx inside the edge-filtered window, m/z inside [flo, fhi])
                 const uint32_t blk = blk0 + tile;
                 const uint2* const ent = wv.frag + wv.blk_off[blk];
                 const uint32_t blen = (uint32_t)(wv.blk_off[blk + 1] - wv.blk_off[blk]);
@@ -765,36 +765,28 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                 const uint32_t t_hi = min(q.eff_hi, pep_hi_excl - 1);
                 const bool t_any = q.eff_lo <= q.eff_hi && t_lo <= t_hi;
                 const uint32_t t_span = t_any ? t_hi - t_lo : 0u;
-                for (;;) {
-                    uint32_t j0 = 0;   // next group of WIDE_WALK_UNROLL probes (walk lengths vary: dynamic distribution keeps the 32 warps level)
-                    if (lane == 0) j0 = atomicAdd(&S.s_tnext, (uint32_t)WIDE_WALK_UNROLL);
-                    j0 = __shfl_sync(0xffffffffu, j0, 0);
-                    if (!t_any || j0 >= ntask) break;
-                    float flo[WIDE_WALK_UNROLL], fhi[WIDE_WALK_UNROLL];
-                    uint32_t pos[WIDE_WALK_UNROLL];
-                    bool live[WIDE_WALK_UNROLL];
-#pragma unroll
-                    for (int u = 0; u < WIDE_WALK_UNROLL; u++) {
-                        const uint32_t j = j0 + u;
-                        live[u] = j < ntask;
-                        flo[u] = live[u] ? S.u.blk.flo[j] : 0.0f;
-                        fhi[u] = live[u] ? S.u.blk.fhi[j] : 0.0f;
-                        const float tt = (flo[u] - wv.base) * wv.inv_w;
-                        const int c = tt > 1.0f ? (int)fminf(tt, (float)(wv.cells - 1)) - 1 : 0;   // NaN -> cell 0
-                        pos[u] = live[u] ? __ldg(lutb + c) : blen;
+                // One thread per probe: exact lower bound of flo inside the LUT bracket (3 cells, a few dozen entries: ~6 probes), then the run of
+                // matches itself, WIDE_WALK_UNROLL entries per step with their loads issued together. (A warp-cooperative walk — 32 coalesced
+                // entries per step — was measured first: 1.1 M warp instructions per query, most of them spent on entries outside the run.)
+                for (uint32_t j = tid; t_any && j < ntask; j += WIDE_THREADS) {
+                    const float flo = S.u.blk.flo[j], fhi = S.u.blk.fhi[j];
+                    const float tt = (flo - wv.base) * wv.inv_w;
+                    const int c = tt > 1.0f ? (int)fminf(tt, (float)(wv.cells - 1)) - 1 : 0;   // one cell early (float rounding of the cell index); NaN -> 0
+                    uint32_t lo = __ldg(lutb + c), hi = __ldg(lutb + min((uint32_t)c + 3u, wv.cells));
+                    while (lo < hi) {   // first entry with m/z >= flo
+                        const uint32_t mid = lo + ((hi - lo) >> 1);
+                        if (__uint_as_float(__ldg(&ent[mid].y)) < flo) lo = mid + 1; else hi = mid;
                     }
-                    for (;;) {
+                    for (uint32_t e = lo; e < blen; e += WIDE_WALK_UNROLL) {
                         uint2 f[WIDE_WALK_UNROLL];
 #pragma unroll
-                        for (int u = 0; u < WIDE_WALK_UNROLL; u++) {
-                            const uint32_t e = pos[u] + lane;
-                            f[u] = (live[u] && e < blen) ? __ldg(ent + e) : make_uint2(0xFFFFFFFFu, 0x7F800000u);   // past the block: +inf ends the run
-                        }
-                        bool any_live = false;
+                        for (int u = 0; u < WIDE_WALK_UNROLL; u++) f[u] = e + u < blen ? __ldg(ent + e + u) : make_uint2(0xFFFFFFFFu, 0x7F800000u);   // past the block: +inf
+                        bool more = true;
 #pragma unroll
                         for (int u = 0; u < WIDE_WALK_UNROLL; u++) {
                             const float m = __uint_as_float(f[u].y);
-                            if (m >= flo[u] && m <= fhi[u] && f[u].x - t_lo <= t_span) {
+                            more = more && m <= fhi;   // entries ascend in m/z: the first one above fhi ends the run
+                            if (more && m >= flo && f[u].x - t_lo <= t_span) {
                                 const uint32_t idx = f[u].x - pep_lo, sh = (idx & 1) * 16;
                                 const uint32_t prev = (atomicAdd(&S.cnt32[idx >> 1], 1u << sh) >> sh) & 0xFFFFu;   // this slot's count before this match
                                 msum++;
@@ -804,12 +796,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                                     if (qi < WIDE_QCAP) S.u.blk.qslot[qi] = idx;
                                 }
                             }
-                            // entries ascend in m/z: the run can only continue while the last entry fetched is still <= fhi
-                            live[u] = live[u] && __shfl_sync(0xffffffffu, m <= fhi[u], 31);
-                            pos[u] += 32;
-                            any_live |= live[u];
                         }
-                        if (!any_live) break;
+                        if (!more) break;
                     }
                 }
             } else if (fast) {
@@ -1218,9 +1206,15 @@ __global__ void __launch_bounds__(256) k_wide_account(DbView db, ScorerView sc, 
 // serial replays (their result ORDER is observable) of all queries of the batch run concurrently instead of stalling a whole CTA each.
 // Heaps live in shared memory, interleaved by thread. Used by both preliminary-scoring kernels.
 constexpr int REPLAY_THREADS = 128;
+// COMPACT (narrow windows, <= NARROW_CAP peptides): inside one query precursor charge and isotope error are constants and PeptideIx - pre_idx_lo
+// fits 16 bits, so the heap holds 32-bit keys (matched << 16 | PeptideIx - pre_idx_lo; PreScore::default() -> 0x0000FFFF, below every real key,
+// which has matched >= 1): same order as the packed 64-bit PreScore, half the shared memory (twice the resident CTAs) and half the LDS traffic.
+template <bool COMPACT>
 __global__ void __launch_bounds__(REPLAY_THREADS) k_replay(ScorerView sc, BatchView b, const uint64_t* lists, const ReplaySlot* slots, uint32_t n_slots,
                                                            const unsigned long long* n_slots_dev, uint32_t n_spectra) {
-    extern __shared__ uint64_t rheap[];  // [kparam][REPLAY_THREADS]
+    typedef typename std::conditional<COMPACT, uint32_t, uint64_t>::type key_t;
+    extern __shared__ __align__(8) unsigned char rheap_raw[];
+    key_t* const rheap = reinterpret_cast<key_t*>(rheap_raw);  // [kparam][REPLAY_THREADS]
     uint32_t slot = blockIdx.x * REPLAY_THREADS + threadIdx.x;
     if (n_slots_dev != nullptr) n_slots = (uint32_t)min((unsigned long long)n_slots, *n_slots_dev);   // slots actually filled (device-side count)
     if (slot >= n_slots) return;
@@ -1232,33 +1226,45 @@ __global__ void __launch_bounds__(REPLAY_THREADS) k_replay(ScorerView sc, BatchV
     if (ws.state != 0) return;
     const uint64_t* list = lists + ws.off;
     const uint32_t k = ws.k, tid = threadIdx.x;
-    auto H = [&](uint32_t i) -> uint64_t& { return rheap[i * REPLAY_THREADS + tid]; };
+    uint32_t pre_lo = 0, q_charge = 0;
+    int q_iso = 0;
+    if (COMPACT) { const QueryDesc q = b.queries[ws.item]; pre_lo = q.pre_lo; q_charge = q.charge; q_iso = q.iso; }
+    auto pack = [&](uint64_t k64) -> key_t {
+        if (!COMPACT) return (key_t)k64;
+        return (key_t)(key_peptide(k64) == 0xFFFFFFFFu ? 0x0000FFFFu : ((key_matched(k64) << 16) | (key_peptide(k64) - pre_lo)));
+    };
+    auto unpack = [&](key_t kk) -> uint64_t {
+        if (!COMPACT) return (uint64_t)kk;
+        const uint32_t v = (uint32_t)kk;
+        return v == 0x0000FFFFu ? PRESCORE_DEFAULT : prescore_key(v >> 16, pre_lo + (v & 0xFFFFu), q_charge, q_iso);
+    };
+    auto H = [&](uint32_t i) -> key_t& { return rheap[i * REPLAY_THREADS + tid]; };
     // sift_down (heap.rs:31-60) of `val` from `index`, written with a hole: children smaller than val move up, val lands where the swaps
     // of the reference would have carried it (same path: the smaller child, the left one on ties, and only if it is < val)
-    auto sift = [&](uint32_t index, uint64_t val) {
+    auto sift = [&](uint32_t index, key_t val) {
         for (;;) {
             const uint32_t l = index * 2 + 1;
             if (l >= k) break;
             uint32_t c = l;
-            uint64_t cv = H(l);
-            if (l + 1 < k) { const uint64_t cr = H(l + 1); if (cr < cv) { cv = cr; c = l + 1; } }
+            key_t cv = H(l);
+            if (l + 1 < k) { const key_t cr = H(l + 1); if (cr < cv) { cv = cr; c = l + 1; } }
             if (!(cv < val)) break;
             H(index) = cv;
             index = c;
         }
         H(index) = val;
     };
-    for (uint32_t i = 0; i < k; i++) H(i) = __ldg(list + i);
+    for (uint32_t i = 0; i < k; i++) H(i) = pack(__ldg(list + i));
     for (uint32_t i = k / 2; i-- > 0;) sift(i, H(i));
-    uint64_t root = H(0);
+    key_t root = H(0);
     uint64_t nxt = k < ws.n_list ? __ldg(list + k) : 0;
     for (uint32_t j = k; j < ws.n_list; j++) {
-        const uint64_t kq = nxt;
+        const key_t kq = pack(nxt);
         if (j + 1 < ws.n_list) nxt = __ldg(list + j + 1);   // in flight while the heap is updated
         if (kq > root) { sift(0, kq); root = H(0); }
     }
     uint64_t* keys = b.hit_keys + (size_t)ws.item * sc.kparam;
-    for (uint32_t i = 0; i < k; i++) keys[i] = H(i);
+    for (uint32_t i = 0; i < k; i++) keys[i] = unpack(H(i));
 }
 
 // ------------------------------------------------------------------------------------------------ scoring

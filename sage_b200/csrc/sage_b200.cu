@@ -599,7 +599,8 @@ static int ensure_kernel_attributes(int device) {
         return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
     };
     CUDA_TRY(raise((const void*)k_prelim_narrow));
-    CUDA_TRY(raise((const void*)k_replay));
+    CUDA_TRY(raise((const void*)k_replay<true>));
+    CUDA_TRY(raise((const void*)k_replay<false>));
     CUDA_TRY(raise((const void*)k_prelim_wide));
     CUDA_TRY(raise((const void*)k_score));
     CUDA_TRY(raise((const void*)k_process_ms2));
@@ -718,7 +719,7 @@ struct sage_b200_scorer {
     // learned work-list sizes (per spectrum of a chunk): narrow key-list arena entries and open-search queries. A chunk that needs more than
     // its capacity is re-run once with the exact sizes it counted, and the estimates grow.
     double nlist_per_spectrum = 512.0, wide_per_spectrum = 0.0;
-    int first_chunk_pct = 20;
+    int first_chunk_pct = 0;   // measured on cfg2 (e2e ms per 50k-spectrum call): 0 -> 3.44, 10 -> 3.46, 20 -> 3.52, 35 -> 3.53 (profiles/r02_e_*)
     // SAGE_B200_TRACE=1: per-chunk device timeline (ms since the start of the call) on stderr
     bool trace = false;
     cudaEvent_t ev_base = nullptr;
@@ -1042,8 +1043,9 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     k_prelim_narrow<<<(unsigned)std::min<uint64_t>(C.nitems, (uint64_t)db->sm_count * 6), PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>());
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(L.ev[8], st));   // narrow counting kernels done (the open-search kernel, when present, is timed with the replays)
-    k_replay<<<(unsigned)((C.nitems + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(sv, bv, L.d_nlist.as<uint64_t>(), L.d_nslots.as<ReplaySlot>(),
-                                                                                                       (uint32_t)C.nitems, nullptr, n);
+    // narrow windows (<= NARROW_CAP peptides): 32-bit heap keys, half the shared memory
+    k_replay<true><<<(unsigned)((C.nitems + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm / 2, st>>>(sv, bv, L.d_nlist.as<uint64_t>(), L.d_nslots.as<ReplaySlot>(),
+                                                                                                                 (uint32_t)C.nitems, nullptr, n);
     CUDA_TRY(cudaGetLastError());
     launches += 3;
     if (C.wide_cap) {
@@ -1056,7 +1058,7 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
             CUDA_TRY(cudaGetLastError());
             launches++;
         }
-        k_replay<<<(unsigned)((C.wide_cap + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(
+        k_replay<false><<<(unsigned)((C.wide_cap + REPLAY_THREADS - 1) / REPLAY_THREADS), REPLAY_THREADS, rsm, st>>>(
             sv, bv, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>(), C.wide_cap, L.d_counters.as<unsigned long long>() + C_WIDE, 0u);
         CUDA_TRY(cudaGetLastError());
         launches += 2;
