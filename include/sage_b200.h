@@ -184,7 +184,7 @@ int sage_b200_bind_thread_to_device(int device);
  * OR-ed (the reference stores `true` into &[AtomicBool]). prefilter_low_memory selects the branch of scoring.rs:270. */
 int sage_b200_quick_score(sage_b200_scorer* scorer, const sage_b200_spectra* spectra, int prefilter_low_memory, uint8_t* keep);
 
-/* The same call split in phases for device-resident reuse (one batch of <= 131072 spectra / 2^25 peaks):
+/* The same call split in phases for device-resident reuse (one batch of <= 262144 spectra / 2^26 peaks):
  * upload makes the spectra resident in HBM, run launches the kernels (results stay on the device; may be repeated),
  * download copies the Feature rows back. score_batch == upload + run + download per chunk. */
 int sage_b200_batch_upload(sage_b200_scorer* scorer, const sage_b200_spectra* spectra);

@@ -600,16 +600,28 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32, WARPQ_MIN_CTAS) k_prelim_nar
 // tile to tile (one binary search per visit and tile), whole warps stream the sub-slices with coalesced 8-byte loads (4 in
 // flight per lane), matches become shared-memory atomics, and after each tile the exact trim (heap replay in index order)
 // consumes the tile's counts straight from shared memory. Every index entry of [inner_left, inner_right) is read exactly once.
-constexpr int WIDE_THREADS = 1024;
-constexpr uint32_t WIDE_TILE = 80 * 1024;    // peptides per tile (u16 counts: 160 KB)
-constexpr uint32_t WIDE_VMAX = 2048;         // page visits whose running position is cached in smem
-constexpr uint32_t WIDE_TCACHE = 2048;       // (peak, charge) probes whose bucket range is cached in smem
+// Shape of the open-search CTA (A/B: profiles/r02_*): threads, peptides per count tile, CTAs per SM the shared-memory budget allows.
+#ifndef SAGE_B200_WIDE_THREADS
+#define SAGE_B200_WIDE_THREADS 1024
+#endif
+#ifndef SAGE_B200_WIDE_TILE
+#define SAGE_B200_WIDE_TILE (80 * 1024)
+#endif
+#ifndef SAGE_B200_WIDE_CTAS
+#define SAGE_B200_WIDE_CTAS 1
+#endif
+constexpr int WIDE_THREADS = SAGE_B200_WIDE_THREADS;
+constexpr int WIDE_CTAS = SAGE_B200_WIDE_CTAS;
+constexpr bool WIDE_SMALL = WIDE_CTAS > 1;        // several CTAs per SM: every per-query table shrinks with the tile
+constexpr uint32_t WIDE_TILE = SAGE_B200_WIDE_TILE;    // peptides per tile (u16 counts: 160 KB at 80 k)
+constexpr uint32_t WIDE_VMAX = WIDE_SMALL ? 1024 : 2048;    // page visits whose running position is cached in smem
+constexpr uint32_t WIDE_TCACHE = WIDE_SMALL ? 1024 : 2048;  // (peak, charge) probes whose bucket range is cached in smem
 constexpr uint32_t WIDE_LMAX = 12288;        // survivor keys kept per query for the replay kernel (overflow -> in-kernel serial replay)
 constexpr uint32_t WIDE_HLEV = 64;           // matched-count histogram levels (last level = ">= 63")
 typedef ReplaySlot WideSlot;
 struct WideRange { uint64_t start; uint32_t len; float flo, fhi; };
 
-constexpr uint32_t WIDE_VCAP = 1024;         // page visits per query handled by the boundary-table fast path
+constexpr uint32_t WIDE_VCAP = WIDE_SMALL ? 512 : 1024;   // page visits per query handled by the boundary-table fast path
 constexpr uint32_t WIDE_BT = 16;             // boundary columns (tiles + 1) of the fast path
 struct WideSlow {                            // fallback: one search per (visit, tile), positions carried in `cur`
     uint32_t cur[WIDE_VMAX];
@@ -622,12 +634,14 @@ struct WideFast {                            // fast path: all tile boundaries o
     uint32_t vpage[WIDE_VCAP];
     float vflo[WIDE_VCAP], vfhi[WIDE_VCAP];
 };
-constexpr uint32_t WIDE_TMAX = 2048;         // (peak, charge) probes per query handled by the block-index path
-constexpr int WIDE_WALK_UNROLL = 8;          // entries of a run a thread fetches per step (independent loads in flight)
+constexpr uint32_t WIDE_TMAX = WIDE_SMALL ? 1024 : 2048;    // (peak, charge) probes per query handled by the block-index path
+constexpr int WIDE_WALK_UNROLL = 4;          // probes a warp walks concurrently (independent loads in flight)
+constexpr uint32_t WIDE_SMAX = WIDE_SMALL ? 3072 : 6144;    // (block, probe) run starts resolved per block group (one batch of independent searches)
 constexpr uint32_t WIDE_QCAP = WIDE_THREADS;  // slots a tile may queue as survivors (one per thread in the ordering step); more -> the tile is scanned instead
 struct WideBlk {
     float flo[WIDE_TMAX], fhi[WIDE_TMAX];    // Tolerance::bounds of every probe of the query
     uint32_t qslot[WIDE_QCAP];               // tile-relative slots whose count reached the survivor level during the walk (unordered)
+    uint32_t start[WIDE_SMAX];               // [tile of the current tile group][probe]: first entry of the block with m/z >= flo
 };
 struct WideSmem {
     uint32_t cnt32[WIDE_TILE / 2 + 4];   // + slack: a block-mode tile can hold TILE + 1 slots (the phantom slot pre_idx_hi == n_pep)
@@ -641,7 +655,7 @@ struct WideSmem {
 };
 
 
-__global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, ScorerView sc, BatchView b, uint32_t n_items, uint64_t* wlist,
+__global__ void __launch_bounds__(WIDE_THREADS, WIDE_CTAS) k_prelim_wide(DbView db, ScorerView sc, BatchView b, uint32_t n_items, uint64_t* wlist,
                                                                    WideSlot* wslots, WideIndexView wv) {
     extern __shared__ __align__(16) unsigned char wide_raw[];
     WideSmem& S = *reinterpret_cast<WideSmem*>(wide_raw);
@@ -677,8 +691,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         const bool blockmode = wv.frag != nullptr && wv.block == TILE && ntask <= WIDE_TMAX;
         const uint32_t blk0 = blockmode ? q.pre_lo / TILE : 0;
         const uint32_t T0 = max(TILE / 8, 256u) & ~7u, T1 = max(TILE / 4, 256u) & ~7u;
-        // (pre_idx_hi may be n_pep, one past the last peptide: that phantom slot never matches and belongs to the last real block's tile)
-        const uint32_t ntiles = blockmode ? min(q.pre_hi, db.n_pep - 1) / TILE - blk0 + 1 : (n <= T0 ? 1 : (n <= T0 + T1 ? 2 : 2 + (n - T0 - T1 + TILE - 1) / TILE));
+        // Block mode: the part of the window inside its FIRST block is cut into up to three tiles (T0, T1, rest) like the leading tiles of the
+        // page-slice path — without them the first tile runs at survivor level 1 over up to TILE slots and one query in eight overflowed its
+        // survivor list (measured); a sub-block tile re-reads the probes' (short) runs of that block and keeps the PeptideIx of its own range.
+        // (pre_idx_hi may be n_pep, one past the last peptide: that phantom slot never matches and belongs to the last real block's tile.)
+        const uint32_t nblk = blockmode ? min(q.pre_hi, db.n_pep - 1) / TILE - blk0 + 1 : 0;
+        const uint32_t n0 = blockmode ? (nblk == 1 ? n : (blk0 + 1) * TILE - q.pre_lo) : 0;    // dense slots inside the first block
+        const uint32_t nfirst = n0 <= T0 ? 1 : (n0 <= T0 + T1 ? 2 : 3);
+        const uint32_t ntiles = blockmode ? nfirst + nblk - 1 : (n <= T0 ? 1 : (n <= T0 + T1 ? 2 : 2 + (n - T0 - T1 + TILE - 1) / TILE));
         uint32_t my_matched = 0, my_pages = 0, nz = 0;
         uint32_t msum = 0;   // sum of all slot counts == matched_peaks of this query (replaces per-match counting in the streaming loop)
         long long my_entries = 0;
@@ -733,10 +753,41 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
         }
         const bool fast = S.s_fast != 0;
 
+        uint32_t grp0 = 0, grp_n = 0;   // current block group of the block-index path: blocks [grp0, grp0 + grp_n)
         for (uint32_t tile = 0; tile < ntiles; tile++) {
+            const uint32_t tblk = blockmode ? (tile < nfirst ? blk0 : blk0 + tile - nfirst + 1) : 0;   // block this tile lies in
+            if (blockmode && tblk >= grp0 + grp_n) {
+                // ---- run starts of every (block, probe) pair of the next block group, all searches independent: LUT bracket (the cell of flo, one
+                // early / two late to absorb the float rounding of the cell index), then the exact lower bound on the entries' m/z
+                grp0 = tblk;
+                grp_n = min(blk0 + nblk - tblk, max(1u, WIDE_SMAX / max(ntask, 1u)));
+                __syncthreads();   // the previous group's starts are no longer read
+                for (uint32_t w = tid; w < grp_n * ntask; w += WIDE_THREADS) {
+                    const uint32_t g = w / ntask, j = w - g * ntask, blk = grp0 + g;
+                    const uint2* const ent = wv.frag + wv.blk_off[blk];
+                    const uint32_t blen = (uint32_t)(wv.blk_off[blk + 1] - wv.blk_off[blk]);
+                    const uint32_t* const lutb = wv.lut + (size_t)blk * (wv.cells + 1);
+                    const float flo = S.u.blk.flo[j];
+                    uint32_t lo = blen, hi = blen;   // NaN bounds: empty run
+                    if (flo == flo && S.u.blk.fhi[j] == S.u.blk.fhi[j]) {
+                        const float tt = (flo - wv.base) * wv.inv_w;
+                        const int c = tt > 1.0f ? (int)fminf(tt, (float)(wv.cells - 1)) - 1 : 0;
+                        lo = __ldg(lutb + c);
+                        hi = __ldg(lutb + min((uint32_t)c + 3u, wv.cells));
+                        while (lo < hi) {
+                            const uint32_t mid = lo + ((hi - lo) >> 1);
+                            if (__uint_as_float(__ldg(&ent[mid].y)) < flo) lo = mid + 1; else hi = mid;
+                        }
+                    }
+                    S.u.blk.start[w] = lo;
+                }
+                __syncthreads();
+            }
             // first dense slot of the tile / slots in the tile
-            const uint32_t d0 = blockmode ? max(q.pre_lo, (blk0 + tile) * TILE) - q.pre_lo : (tile == 0 ? 0 : (tile == 1 ? T0 : T0 + T1 + (tile - 2) * TILE));
-            const uint32_t dn = blockmode ? (tile + 1 == ntiles ? q.pre_hi + 1 : (blk0 + tile + 1) * TILE) - (q.pre_lo + d0)   // <= TILE + 1 (phantom slot)
+            const uint32_t d0 = blockmode ? (tile < nfirst ? (tile == 0 ? 0 : (tile == 1 ? T0 : T0 + T1)) : tblk * TILE - q.pre_lo)
+                                          : (tile == 0 ? 0 : (tile == 1 ? T0 : T0 + T1 + (tile - 2) * TILE));
+            const uint32_t dn = blockmode ? (tile < nfirst ? (tile == 0 ? min(T0, n0) : (tile == 1 ? min(T1, n0 - T0) : n0 - T0 - T1))
+                                                           : (tile + 1 == ntiles ? q.pre_hi + 1 - (q.pre_lo + d0) : TILE))   // <= TILE + 1 (phantom slot)
                                           : min(tile == 0 ? T0 : (tile == 1 ? T1 : TILE), n - d0);
             const uint32_t pep_lo = q.pre_lo + d0;                         // PeptideIx of slot d0
             const bool last_tile = tile + 1 == ntiles;
@@ -757,36 +808,47 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
             if (blockmode) {
                 // every probe's matches inside this tile are ONE run of the block's m/z-sorted entries, located through the per-block m/z LUT;
                 // exact filter on the values (database.rs:526-533: PeptideIx inside the edge-filtered window, m/z inside [flo, fhi])
-                const uint32_t blk = blk0 + tile;
+                const uint32_t blk = tblk;
                 const uint2* const ent = wv.frag + wv.blk_off[blk];
                 const uint32_t blen = (uint32_t)(wv.blk_off[blk + 1] - wv.blk_off[blk]);
-                const uint32_t* const lutb = wv.lut + (size_t)blk * (wv.cells + 1);
                 const uint32_t t_lo = max(q.eff_lo, pep_lo);
                 const uint32_t t_hi = min(q.eff_hi, pep_hi_excl - 1);
                 const bool t_any = q.eff_lo <= q.eff_hi && t_lo <= t_hi;
                 const uint32_t t_span = t_any ? t_hi - t_lo : 0u;
-                // One thread per probe: exact lower bound of flo inside the LUT bracket (3 cells, a few dozen entries: ~6 probes), then the run of
-                // matches itself, WIDE_WALK_UNROLL entries per step with their loads issued together. (A warp-cooperative walk — 32 coalesced
-                // entries per step — was measured first: 1.1 M warp instructions per query, most of them spent on entries outside the run.)
-                for (uint32_t j = tid; t_any && j < ntask; j += WIDE_THREADS) {
-                    const float flo = S.u.blk.flo[j], fhi = S.u.blk.fhi[j];
-                    const float tt = (flo - wv.base) * wv.inv_w;
-                    const int c = tt > 1.0f ? (int)fminf(tt, (float)(wv.cells - 1)) - 1 : 0;   // one cell early (float rounding of the cell index); NaN -> 0
-                    uint32_t lo = __ldg(lutb + c), hi = __ldg(lutb + min((uint32_t)c + 3u, wv.cells));
-                    while (lo < hi) {   // first entry with m/z >= flo
-                        const uint32_t mid = lo + ((hi - lo) >> 1);
-                        if (__uint_as_float(__ldg(&ent[mid].y)) < flo) lo = mid + 1; else hi = mid;
+                // The run starts of all probes were resolved for this tile group in one batch of independent searches (below the tile loop
+                // header); a warp walks WIDE_WALK_UNROLL runs at a time, 32 coalesced entries per run and step. Groups of probes are handed
+                // out dynamically (run lengths vary). Measured alternatives (profiles/r02_*): starting the walk at the LUT cell instead of the
+                // exact lower bound (166 ms per 50k queries: most fetched entries lie before the run), one thread per probe (348 ms: ~280 threads
+                // in flight per SM cannot hide the dependent-load latency).
+                const uint32_t* const starts = S.u.blk.start + (tblk - grp0) * ntask;
+                for (;;) {
+                    uint32_t j0 = 0;
+                    if (lane == 0) j0 = atomicAdd(&S.s_tnext, (uint32_t)WIDE_WALK_UNROLL);
+                    j0 = __shfl_sync(0xffffffffu, j0, 0);
+                    if (!t_any || j0 >= ntask) break;
+                    float fhi[WIDE_WALK_UNROLL];
+                    uint32_t pos[WIDE_WALK_UNROLL];
+                    bool live[WIDE_WALK_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < WIDE_WALK_UNROLL; u++) {
+                        const uint32_t j = j0 + u;
+                        live[u] = j < ntask;
+                        fhi[u] = live[u] ? S.u.blk.fhi[j] : 0.0f;
+                        pos[u] = live[u] ? starts[j] : blen;
                     }
-                    for (uint32_t e = lo; e < blen; e += WIDE_WALK_UNROLL) {
+                    for (;;) {
                         uint2 f[WIDE_WALK_UNROLL];
 #pragma unroll
-                        for (int u = 0; u < WIDE_WALK_UNROLL; u++) f[u] = e + u < blen ? __ldg(ent + e + u) : make_uint2(0xFFFFFFFFu, 0x7F800000u);   // past the block: +inf
-                        bool more = true;
+                        for (int u = 0; u < WIDE_WALK_UNROLL; u++) {
+                            const uint32_t e = pos[u] + lane;
+                            f[u] = (live[u] && e < blen) ? __ldg(ent + e) : make_uint2(0xFFFFFFFFu, 0x7F800000u);   // past the block: +inf ends the run
+                        }
+                        bool any_live = false;
 #pragma unroll
                         for (int u = 0; u < WIDE_WALK_UNROLL; u++) {
                             const float m = __uint_as_float(f[u].y);
-                            more = more && m <= fhi;   // entries ascend in m/z: the first one above fhi ends the run
-                            if (more && m >= flo && f[u].x - t_lo <= t_span) {
+                            const bool in = m <= fhi[u];   // (m >= flo holds from the run start on; NaN bounds match nothing: starts == block end)
+                            if (in && f[u].x - t_lo <= t_span) {
                                 const uint32_t idx = f[u].x - pep_lo, sh = (idx & 1) * 16;
                                 const uint32_t prev = (atomicAdd(&S.cnt32[idx >> 1], 1u << sh) >> sh) & 0xFFFFu;   // this slot's count before this match
                                 msum++;
@@ -796,8 +858,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_prelim_wide(DbView db, Scor
                                     if (qi < WIDE_QCAP) S.u.blk.qslot[qi] = idx;
                                 }
                             }
+                            // entries ascend in m/z: the run continues only while the last entry fetched is still <= fhi
+                            live[u] = live[u] && __shfl_sync(0xffffffffu, in, 31);
+                            pos[u] += 32;
+                            any_live |= live[u];
                         }
-                        if (!more) break;
+                        if (!any_live) break;
                     }
                 }
             } else if (fast) {

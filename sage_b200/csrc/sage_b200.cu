@@ -1049,7 +1049,7 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     CUDA_TRY(cudaGetLastError());
     launches += 3;
     if (C.wide_cap) {
-        const int ctas = (int)std::min<uint64_t>((uint64_t)db->sm_count, C.wide_cap);
+        const int ctas = (int)std::min<uint64_t>((uint64_t)db->sm_count * WIDE_CTAS, C.wide_cap);
         const WideIndexView wv = db_wide_index(db, sv.wide_tile);   // built on first use (the first open-search chunk of a scorer is a re-run anyway)
         k_prelim_wide<<<ctas, WIDE_THREADS, sizeof(WideSmem), st>>>(db->v, sv, bv, (uint32_t)C.nitems, L.d_wlist.as<uint64_t>(), L.d_wslots.as<WideSlot>(), wv);
         CUDA_TRY(cudaGetLastError());
@@ -1397,8 +1397,8 @@ extern "C" int sage_b200_batch_upload(sage_b200_scorer* S, const sage_b200_spect
     if (!S) return fail(SAGE_B200_EINVAL, "batch_upload: null scorer");
     int rc = check_spectra(sp);
     if (rc) return rc;
-    if (sp->n == 0 || sp->n > (1u << 17) || sp->peak_offsets[sp->n] - sp->peak_offsets[0] > (1ull << 25))
-        return fail(SAGE_B200_ELIMIT, "batch_upload takes 1..131072 spectra and at most 2^25 peaks (use score_batch for larger batches)");
+    if (sp->n == 0 || sp->n > (1u << 18) || sp->peak_offsets[sp->n] - sp->peak_offsets[0] > (1ull << 26))
+        return fail(SAGE_B200_ELIMIT, "batch_upload takes 1..262144 spectra and at most 2^26 peaks (use score_batch for larger batches)");
     std::lock_guard<std::mutex> lock(S->mu);
     CUDA_TRY(cudaSetDevice(S->db->device));
     S->last = sage_b200_counters{};
