@@ -600,20 +600,24 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32, WARPQ_MIN_CTAS) k_prelim_nar
 // tile to tile (one binary search per visit and tile), whole warps stream the sub-slices with coalesced 8-byte loads (4 in
 // flight per lane), matches become shared-memory atomics, and after each tile the exact trim (heap replay in index order)
 // consumes the tile's counts straight from shared memory. Every index entry of [inner_left, inner_right) is read exactly once.
-// Shape of the open-search CTA (A/B: profiles/r02_*): threads, peptides per count tile, CTAs per SM the shared-memory budget allows.
+// Shape of the open-search CTA: threads, peptides per count tile, CTAs per SM the shared-memory budget allows. Measured on cfg4 (ms per 50k
+// queries, block-index path; profiles/r02_*): 1024 thr x 80k tile x 1 CTA/SM 119.7 | 768 x 48k x 1 112.5 | 256 x 16k x 3 102.3 | 512 x 24k x 2 87.6 |
+// 384 x 20k x 3 84.2 | 512 x 36k x 2 83.3 | 512 x 32k x 2 82.9 | 512 x 40k x 2 82.6; walk unroll at 512 x 32k x 2: 2 -> 82.3, 4 -> 82.9, 8 -> 92.8.
+// Two resident CTAs matter more than the tile size: the kernel is a chain of short phases separated by CTA-wide barriers (12 barrier-stalled
+// warps per issued instruction with one CTA per SM), and a second CTA fills the gaps.
 #ifndef SAGE_B200_WIDE_THREADS
-#define SAGE_B200_WIDE_THREADS 1024
+#define SAGE_B200_WIDE_THREADS 512
 #endif
 #ifndef SAGE_B200_WIDE_TILE
-#define SAGE_B200_WIDE_TILE (80 * 1024)
+#define SAGE_B200_WIDE_TILE (32 * 1024)
 #endif
 #ifndef SAGE_B200_WIDE_CTAS
-#define SAGE_B200_WIDE_CTAS 1
+#define SAGE_B200_WIDE_CTAS 2
 #endif
 constexpr int WIDE_THREADS = SAGE_B200_WIDE_THREADS;
 constexpr int WIDE_CTAS = SAGE_B200_WIDE_CTAS;
 constexpr bool WIDE_SMALL = WIDE_CTAS > 1;        // several CTAs per SM: every per-query table shrinks with the tile
-constexpr uint32_t WIDE_TILE = SAGE_B200_WIDE_TILE;    // peptides per tile (u16 counts: 160 KB at 80 k)
+constexpr uint32_t WIDE_TILE = SAGE_B200_WIDE_TILE;    // peptides per tile (u16 counts: 64 KB at 32 k)
 constexpr uint32_t WIDE_VMAX = WIDE_SMALL ? 1024 : 2048;    // page visits whose running position is cached in smem
 constexpr uint32_t WIDE_TCACHE = WIDE_SMALL ? 1024 : 2048;  // (peak, charge) probes whose bucket range is cached in smem
 constexpr uint32_t WIDE_LMAX = 12288;        // survivor keys kept per query for the replay kernel (overflow -> in-kernel serial replay)
@@ -635,7 +639,10 @@ struct WideFast {                            // fast path: all tile boundaries o
     float vflo[WIDE_VCAP], vfhi[WIDE_VCAP];
 };
 constexpr uint32_t WIDE_TMAX = WIDE_SMALL ? 1024 : 2048;    // (peak, charge) probes per query handled by the block-index path
-constexpr int WIDE_WALK_UNROLL = 4;          // probes a warp walks concurrently (independent loads in flight)
+#ifndef SAGE_B200_WIDE_UNROLL
+#define SAGE_B200_WIDE_UNROLL 2
+#endif
+constexpr int WIDE_WALK_UNROLL = SAGE_B200_WIDE_UNROLL;          // probes a warp walks concurrently (independent loads in flight)
 constexpr uint32_t WIDE_SMAX = WIDE_SMALL ? 3072 : 6144;    // (block, probe) run starts resolved per block group (one batch of independent searches)
 constexpr uint32_t WIDE_QCAP = WIDE_THREADS;  // slots a tile may queue as survivors (one per thread in the ordering step); more -> the tile is scanned instead
 struct WideBlk {

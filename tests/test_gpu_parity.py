@@ -141,7 +141,7 @@ def test_open_search_multi_tile(small):
     sub = spectra.slice(0, 200)
     of, oc, _, octr = odb.score_batch(oracle_cfg(**kw), sub.as_dict(), counters=True)
     # both counting strategies of k_prelim_wide: the block-major m/z-sorted index copy (default) and page-slice streaming (the reference's loop)
-    for tile, pages_mode in ((1024, False), (4096, False), (81920, False), (512, False), (1024, True), (81920, True)):
+    for tile, pages_mode in ((1024, False), (4096, False), (32768, False), (512, False), (1024, True), (32768, True)):
         os.environ["SAGE_B200_NO_WIDE_INDEX"] = "1" if pages_mode else "0"
         try:
             sc = Scorer(gdb, **kw)

@@ -75,7 +75,7 @@ def test_random_configuration(seed):
               score_type=int(rng.random() < 0.2))
     sc = Scorer(gdb, **kw)
     sc.set_option("pep_cap", int(rng.choice([0, 64, 8192])))
-    sc.set_option("wide_tile", int(rng.choice([512, 4096, 81920])))
+    sc.set_option("wide_tile", int(rng.choice([512, 4096, 32768])))
     sc.set_option("pipeline_chunks", int(rng.choice([1, 2, 7])))
     sc.set_option("score_fast", int(rng.integers(2)))   # straight-line vs generic task body of k_score
     gf, gc = sc.score_batch(spectra)

@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-tag=${1:-r02_i}; out=gpurun_out/$tag; mkdir -p $out
+tag=${1:-r02_j}; out=gpurun_out/$tag; mkdir -p $out
 B="python bench.py --workload cfg4 --steps 5 --warmup 3 --no-extras"
 timeout 600 $B > $out/bench_cfg4_default.json 2> $out/bench_cfg4_default.err
 for v in sage_b200/lib/variants/libsage_b200_wide*.so; do
