@@ -230,6 +230,9 @@ int sage_b200_device_log(int device, int variant, const double* x, uint64_t n, d
 
 /* Page-locked host buffers: spectra/feature arrays placed here are copied by DMA without a staging memcpy. */
 void* sage_b200_host_alloc(size_t bytes);
+/* The same for a batch sage_b200_score_batch_multi cuts into n_devices contiguous blocks: the i-th of n equal parts of the buffer is placed on the
+ * NUMA node next to devices[i] (first touch by a bound thread), then the region is registered with CUDA. Release with sage_b200_host_free. */
+void* sage_b200_host_alloc_blocks(size_t bytes, const int* devices, int n_devices);
 void sage_b200_host_free(void* p);
 
 /* Message of the last failure on the calling thread. Returns the message length. */

@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = [
     "sage_b200_scorer_create", "sage_b200_scorer_destroy", "sage_b200_scorer_set_option", "sage_b200_score_batch", "sage_b200_batch_upload", "sage_b200_batch_run",
     "sage_b200_batch_download", "sage_b200_score_batch_multi", "sage_b200_quick_score", "sage_b200_initial_hits", "sage_b200_counters_get",
     "sage_b200_process_spectra", "sage_b200_find_reporter_ions", "sage_b200_host_alloc", "sage_b200_host_free", "sage_b200_last_error",
-    "sage_b200_host_log_variant", "sage_b200_host_log1pf_exact", "sage_b200_device_log", "sage_b200_bind_thread_to_device",
+    "sage_b200_host_log_variant", "sage_b200_host_log1pf_exact", "sage_b200_device_log", "sage_b200_bind_thread_to_device", "sage_b200_host_alloc_blocks",
 ]
 
 _lib = None
@@ -110,6 +110,8 @@ def load_library(build: bool = True):
     lib.sage_b200_host_alloc.restype = C.c_void_p
     lib.sage_b200_host_alloc.argtypes = [C.c_size_t]
     lib.sage_b200_host_free.argtypes = [C.c_void_p]
+    lib.sage_b200_host_alloc_blocks.restype = C.c_void_p
+    lib.sage_b200_host_alloc_blocks.argtypes = [C.c_size_t, C.c_void_p, C.c_int]
     lib.sage_b200_last_error.restype = C.c_size_t
     lib.sage_b200_initial_hits.restype = C.c_int64
     lib.sage_b200_db_destroy.argtypes = [C.c_void_p]
@@ -165,6 +167,21 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
     p = load_library().sage_b200_host_alloc(C.c_size_t(max(n, 16)))
+    if not p:
+        raise SageB200Error(-2, _last_error())
+    buf = (C.c_ubyte * max(n, 16)).from_address(p)
+    arr = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+    _PINNED[arr.ctypes.data] = p
+    return arr
+
+
+def pinned_empty_blocks(shape, dtype, devices) -> np.ndarray:
+    """Page-locked array whose i-th of len(devices) equal parts sits on the NUMA node next to devices[i] (sage_b200_host_alloc_blocks): the
+    input / output buffers of a score_batch_multi call."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+    p = load_library().sage_b200_host_alloc_blocks(C.c_size_t(max(n, 16)), dev, C.c_int(len(devices)))
     if not p:
         raise SageB200Error(-2, _last_error())
     buf = (C.c_ubyte * max(n, 16)).from_address(p)

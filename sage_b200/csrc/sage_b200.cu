@@ -1102,6 +1102,20 @@ static int chunk_download(sage_b200_scorer* S, Lane& L, sage_b200_feature* fdst,
     return 0;
 }
 
+// Open search keeps one survivor list (WIDE_LMAX keys, 96 KiB) per wide query and lane. The arena is bounded by a memory budget: a chunk whose
+// wide queries would need more is not re-run at its size — the call restarts with chunks small enough for the budget (internal code ERECHUNK).
+constexpr int SAGE_B200_ERECHUNK = -100;   // never returned to callers
+static uint64_t wide_arena_budget() {
+    if (const char* e = getenv("SAGE_B200_WIDE_ARENA_MB")) return std::max<uint64_t>(1, (uint64_t)atoll(e)) << 20;   // (tests use a tiny budget)
+    return 8ull << 30;
+}
+static uint64_t wide_max_chunk(double wide_per_spectrum, uint64_t otherwise) {
+    if (!(wide_per_spectrum > 0.0)) return otherwise;
+    const double per_spectrum = wide_per_spectrum * 1.1 * (double)WIDE_LMAX * 8.0;
+    const uint64_t fit = (uint64_t)std::max(1.0, (double)wide_arena_budget() / per_spectrum);
+    return std::min<uint64_t>(32768, std::max<uint64_t>(64, fit));   // open search: at most 32768 spectra per chunk
+}
+
 // Waits for everything queued on the lane and folds its counters / timings into S->last.
 static int lane_finish(sage_b200_scorer* S, Lane& L) {
     ChunkState& C = L.chunk;
@@ -1118,6 +1132,10 @@ static int lane_finish(sage_b200_scorer* S, Lane& L) {
             break;
         }
         if (attempt >= 2) return fail(SAGE_B200_ECUDA, "internal error: chunk re-run with exact work-list sizes did not fit");
+        S->nlist_per_spectrum = std::max(S->nlist_per_spectrum, 1.25 * (double)need / (double)C.n);
+        S->wide_per_spectrum = std::max(S->wide_per_spectrum, (double)nw / (double)C.n);
+        if (nw > C.wide_cap && nw * (uint64_t)WIDE_LMAX * 8 > wide_arena_budget() && C.n > wide_max_chunk(S->wide_per_spectrum, 65536))
+            return fail(SAGE_B200_ERECHUNK, "open-search chunk of %u spectra needs %llu survivor lists: restarting with smaller chunks", C.n, (unsigned long long)nw);
         // a work list was too small: the queries it could not hold reported no hits. Re-run the chunk with the sizes just counted.
         C.force_nlist = need;
         C.force_wide = nw;
@@ -1208,6 +1226,8 @@ static int drain_lanes(sage_b200_scorer* S, int rc) {
     return rc;
 }
 
+static int score_batch_chunks(sage_b200_scorer* S, const sage_b200_spectra* sp, sage_b200_feature* features, uint32_t* counts, bool annotate);
+
 extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectra* sp, sage_b200_feature* features, uint32_t* counts,
                                      sage_b200_fragment* fragments, uint64_t fragment_capacity, uint64_t* fragments_used) {
     if (!S) return fail(SAGE_B200_EINVAL, "score_batch: null scorer");
@@ -1229,11 +1249,37 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
         L.chunk.loaded = false; L.ran = false; L.downloading = false;
     }
     if (S->trace) { S->t_base = std::chrono::steady_clock::now(); CUDA_TRY(cudaEventRecord(S->ev_base, S->lanes[0].stream)); }
+    for (int restart = 0;; restart++) {
+        rc = score_batch_chunks(S, sp, features, counts, annotate);
+        if (rc != SAGE_B200_ERECHUNK) break;
+        drain_lanes(S, rc);   // nothing of this call is kept: the first chunk that needs the re-chunking is the first open-search chunk of the handle
+        if (restart >= 3) return fail(SAGE_B200_ELIMIT, "open search: survivor lists do not fit the arena budget even with the smallest chunks");
+        const uint64_t retries = S->last.chunk_retries;
+        S->last = sage_b200_counters{};
+        S->last.chunk_retries = retries + 1;
+        S->frag_dst = annotate ? fragments : nullptr;
+        S->frag_used = 0;
+    }
+    if (rc) return drain_lanes(S, rc);
+    finish_counters(S);
+    if (annotate) {
+        *fragments_used = S->frag_used;
+        S->frag_dst = nullptr;
+        if (S->frag_used > fragment_capacity)
+            return fail(SAGE_B200_ELIMIT, "fragment_capacity %llu too small: %llu fragments matched (features are complete; re-run with a larger array)",
+                        (unsigned long long)fragment_capacity, (unsigned long long)S->frag_used);
+    }
+    return 0;
+}
+
+// The chunk loop of score_batch (two pipelined lanes). Returns SAGE_B200_ERECHUNK when an open-search chunk must be cut smaller.
+static int score_batch_chunks(sage_b200_scorer* S, const sage_b200_spectra* sp, sage_b200_feature* features, uint32_t* counts, bool annotate) {
+    int rc = 0;
     const uint64_t max_peaks = 1ull << 25;
     // Chunks are as large as the staging bounds allow: on cfg2 one 50k chunk computes in 3.6 ms, two 25k chunks in 4.2 ms (the kernels process
     // spectra in precursor order, so a denser chunk shares more index lines). Inside a chunk the intensities copy overlaps setup + preliminary
     // scoring; across chunks (two lanes) the whole H2D of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i.
-    const uint64_t max_chunk = S->wide_per_spectrum > 0.0 ? 32768 : 65536;   // open search: one ~100 KB survivor list per query
+    const uint64_t max_chunk = wide_max_chunk(S->wide_per_spectrum, 65536);   // open search: one ~100 KB survivor list per query, bounded by the arena budget
     // A short first chunk (first_chunk_pct of the batch, at most 16384 spectra) lets the kernels start while most of the H2D is still in flight.
     uint64_t first = 0, rest = sp->n;
     if (S->pipeline_chunks <= 1 && sp->n >= 16384) { first = std::min<uint64_t>(sp->n * (uint64_t)S->first_chunk_pct / 100, 16384); rest = sp->n - first; }
@@ -1246,27 +1292,19 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
         uint64_t c1 = std::min<uint64_t>(sp->n, c0 + (c0 == 0 && first ? first : target));
         while (c1 > c0 + 1 && sp->peak_offsets[c1] - sp->peak_offsets[c0] > max_peaks) c1 = c0 + (c1 - c0) / 2;
         Lane& L = S->lanes[li];
-        if ((rc = lane_finish(S, L))) return drain_lanes(S, rc);   // the chunk that used this lane two iterations ago
+        if ((rc = lane_finish(S, L))) return rc;   // the chunk that used this lane two iterations ago
         const double ti0 = S->trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S->t_base).count() : 0.0;
-        if ((rc = chunk_upload(S, L, sp, c0, c1))) return drain_lanes(S, rc);
-        if ((rc = chunk_run(S, L, false))) return drain_lanes(S, rc);
-        if ((rc = chunk_download(S, L, features + c0 * S->sv.report_psms, counts + c0))) return drain_lanes(S, rc);
+        if ((rc = chunk_upload(S, L, sp, c0, c1))) return rc;
+        if ((rc = chunk_run(S, L, false))) return rc;
+        if ((rc = chunk_download(S, L, features + c0 * S->sv.report_psms, counts + c0))) return rc;
         if (S->trace) { L.chunk.t_issue0 = ti0; L.chunk.t_issue1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S->t_base).count(); }
-        if (annotate && (rc = lane_finish(S, L))) return drain_lanes(S, rc);   // fragment offsets are global: chunks run one after another
+        if (annotate && (rc = lane_finish(S, L))) return rc;   // fragment offsets are global: chunks run one after another
         c0 = c1;
         if (!annotate) li ^= 1;
     }
     for (Lane& L : S->lanes) {
-        if ((rc = lane_finish(S, L))) return drain_lanes(S, rc);
+        if ((rc = lane_finish(S, L))) return rc;
         L.chunk.loaded = false;
-    }
-    finish_counters(S);
-    if (annotate) {
-        *fragments_used = S->frag_used;
-        S->frag_dst = nullptr;
-        if (S->frag_used > fragment_capacity)
-            return fail(SAGE_B200_ELIMIT, "fragment_capacity %llu too small: %llu fragments matched (features are complete; re-run with a larger array)",
-                        (unsigned long long)fragment_capacity, (unsigned long long)S->frag_used);
     }
     return 0;
 }
@@ -1373,14 +1411,23 @@ extern "C" int sage_b200_quick_score(sage_b200_scorer* S, const sage_b200_spectr
     for (Lane& L : S->lanes) { L.chunk.loaded = false; L.ran = false; L.downloading = false; }
     S->quick_mode = prefilter_low_memory ? 2u : 1u;
     const uint64_t max_peaks = 1ull << 25;
-    uint64_t c0 = 0;
     Lane& L = S->lanes[0];
-    while (c0 < sp->n && rc == 0) {
-        uint64_t c1 = std::min<uint64_t>(sp->n, c0 + 32768);
-        while (c1 > c0 + 1 && sp->peak_offsets[c1] - sp->peak_offsets[c0] > max_peaks) c1 = c0 + (c1 - c0) / 2;
-        if ((rc = chunk_upload(S, L, sp, c0, c1)) == 0 && (rc = chunk_run(S, L, false)) == 0) rc = lane_finish(S, L);
-        c0 = c1;
+    for (int restart = 0; restart < 4; restart++) {
+        uint64_t c0 = 0;
+        rc = 0;
+        const uint64_t max_chunk = wide_max_chunk(S->wide_per_spectrum, 32768);
+        while (c0 < sp->n && rc == 0) {
+            uint64_t c1 = std::min<uint64_t>(sp->n, c0 + max_chunk);
+            while (c1 > c0 + 1 && sp->peak_offsets[c1] - sp->peak_offsets[c0] > max_peaks) c1 = c0 + (c1 - c0) / 2;
+            if ((rc = chunk_upload(S, L, sp, c0, c1)) == 0 && (rc = chunk_run(S, L, false)) == 0) rc = lane_finish(S, L);
+            c0 = c1;
+        }
+        if (rc != SAGE_B200_ERECHUNK) break;
+        drain_lanes(S, rc);   // overflowed attempts leave no keep[] marks (k_score), so the marks of the finished chunks stay valid
+        S->quick_mode = prefilter_low_memory ? 2u : 1u;
+        CUDA_TRY(cudaMemset(S->d_keep.p, 0, npep + 16));
     }
+    if (rc == SAGE_B200_ERECHUNK) rc = fail(SAGE_B200_ELIMIT, "open search: survivor lists do not fit the arena budget even with the smallest chunks");
     S->quick_mode = 0;
     L.chunk.loaded = false;
     if (rc) return drain_lanes(S, rc);
@@ -1416,7 +1463,10 @@ extern "C" int sage_b200_batch_run(sage_b200_scorer* S) {
     Lane& L = S->lanes[0];
     int rc = chunk_run(S, L, false);
     if (rc) return rc;
-    if ((rc = lane_finish(S, L))) return rc;
+    if ((rc = lane_finish(S, L))) {
+        if (rc == SAGE_B200_ERECHUNK) rc = fail(SAGE_B200_ELIMIT, "batch_run: the resident batch needs more open-search survivor lists than the arena budget allows; use score_batch");
+        return rc;
+    }
     finish_counters(S);
     return 0;
 }
@@ -1585,6 +1635,37 @@ extern "C" int sage_b200_counters_get(const sage_b200_scorer* S, sage_b200_count
     return 0;
 }
 
+// Page-locked buffer for a batch that sage_b200_score_batch_multi will cut into n contiguous blocks: block i is first-touched by a thread bound to
+// the NUMA node of devices[i] and then the whole region is registered with CUDA, so every GPU DMA-reads its block from the memory next to it
+// (one buffer allocated by one thread would sit on a single node and half of the GPUs of a two-socket box would pull across the socket link).
+static std::mutex g_blocks_mu;
+static std::vector<std::pair<void*, size_t>> g_blocks;
+extern "C" void* sage_b200_host_alloc_blocks(size_t bytes, const int* devices, int n_devices) {
+    if (bytes == 0) bytes = 16;
+    const size_t page = 4096, total = (bytes + page - 1) / page * page;
+    void* p = aligned_alloc(page, total);
+    if (!p) { fail(SAGE_B200_ECUDA, "host_alloc_blocks: out of memory (%zu bytes)", total); return nullptr; }
+    const int n = (devices && n_devices > 0) ? n_devices : 1;
+    std::vector<std::thread> th;
+    for (int g = 0; g < n; g++) {
+        const size_t a = (total / page) * (size_t)g / (size_t)n * page, b = (total / page) * (size_t)(g + 1) / (size_t)n * page;
+        th.emplace_back([=]() {
+            if (devices) sage_b200_bind_thread_to_device(devices[g]);
+            memset((char*)p + a, 0, b - a);   // first touch places the pages
+        });
+    }
+    for (auto& t : th) t.join();
+    if (cudaHostRegister(p, total, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        free(p);
+        fail(SAGE_B200_ECUDA, "host_alloc_blocks: cudaHostRegister(%zu) failed", total);
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(g_blocks_mu);
+    g_blocks.emplace_back(p, total);
+    return p;
+}
+
 extern "C" void* sage_b200_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable) != cudaSuccess) {
@@ -1595,7 +1676,18 @@ extern "C" void* sage_b200_host_alloc(size_t bytes) {
     return p;
 }
 extern "C" void sage_b200_host_free(void* p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(g_blocks_mu);
+        for (size_t i = 0; i < g_blocks.size(); i++)
+            if (g_blocks[i].first == p) {
+                cudaHostUnregister(p);
+                free(p);
+                g_blocks.erase(g_blocks.begin() + i);
+                return;
+            }
+    }
+    cudaFreeHost(p);
 }
 
 extern "C" size_t sage_b200_last_error(char* buf, size_t cap) {

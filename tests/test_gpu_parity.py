@@ -169,6 +169,26 @@ def test_open_search_multi_tile(small):
     assert_features_equal(gf, gc, of, oc, 1, what="wide, Da fragment tolerance")
 
 
+def test_open_search_arena_budget_forces_smaller_chunks(small):
+    # the survivor-list arena (96 KiB per open-search query and lane) is bounded by a budget; a first chunk that would need more is
+    # not re-run at its size (that used to end in a hard cudaMalloc failure for very large batches) — the call restarts with smaller chunks
+    pep, odb, gdb, spectra = small
+    kw = dict(precursor_tol=Tolerance.da(-500, 500), fragment_tol=Tolerance.ppm(-20, 20), min_isotope_err=-1, max_isotope_err=1, report_psms=2)
+    sub = spectra.slice(0, 400)
+    of, oc, _, _ = odb.score_batch(oracle_cfg(**kw), sub.as_dict())
+    os.environ["SAGE_B200_WIDE_ARENA_MB"] = "16"   # 170 lists: 400 spectra x 3 isotope queries do not fit one chunk
+    try:
+        sc = Scorer(gdb, **kw)
+        gf, gc = sc.score_batch(sub)
+        c = sc.counters()
+        g2, c2 = sc.score_batch(sub)   # second call: chunk size already learned, no restart
+    finally:
+        os.environ.pop("SAGE_B200_WIDE_ARENA_MB", None)
+    assert_features_equal(gf, gc, of, oc, 2, what="arena budget, first call")
+    assert_features_equal(g2, c2, of, oc, 2, what="arena budget, second call")
+    assert c["chunk_retries"] > 0 and c["wide_queries"] > 300
+
+
 def test_chimera(small):
     pep, odb, gdb, _ = small
     chim = synth.make_spectra(pep, 800, seed=13, chimeric=True)

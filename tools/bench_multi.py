@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--spectra-per-gpu", type=int, default=50_000)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--peptides", type=int, default=2_000_000)
+    ap.add_argument("--only", type=int, default=0, help="measure this GPU count only (plus 1 as the base)")
+    ap.add_argument("--numa-blocks", type=int, default=1, help="1: batch buffers from sage_b200_host_alloc_blocks (block g next to GPU g); 0: one pinned buffer")
     args = ap.parse_args()
     from sage_b200 import IndexedDatabase, Scorer, SpectraBatch, Tolerance, api, synth
     ndev = api.device_count()
@@ -44,10 +46,22 @@ def main():
     out = {"metric": "spectra/sec", "mode": "one host process, sage_b200_score_batch_multi", "spectra_per_gpu": args.spectra_per_gpu, "steps": args.steps, "runs": []}
     n = 1
     while n <= gmax:
+        if args.only and n not in (1, args.only):
+            n *= 2
+            continue
         sub = spectra.slice(0, args.spectra_per_gpu * n)
+        devs = list(range(n))
+        if args.numa_blocks:   # block g of every batch array on the NUMA node next to GPU g
+            def pin(a):
+                p = api.pinned_empty_blocks(a.shape, a.dtype, devs)
+                p[...] = a
+                return p
+            f = api.pinned_empty_blocks((len(sub),), api.FEATURE_DTYPE, devs)
+            c = api.pinned_empty_blocks((len(sub),), np.uint32, devs)
+        else:
+            f = api.pinned_empty((len(sub),), api.FEATURE_DTYPE)
+            c = api.pinned_empty((len(sub),), np.uint32)
         hs = SpectraBatch(**{**sub.__dict__, "masses": pin(sub.masses), "intensities": pin(sub.intensities)})
-        f = api.pinned_empty((len(sub),), api.FEATURE_DTYPE)
-        c = api.pinned_empty((len(sub),), np.uint32)
         for _ in range(3):
             api.score_batch_multi(scorers[:n], hs, f, c)
         t0 = time.perf_counter()
@@ -56,7 +70,7 @@ def main():
         dt = (time.perf_counter() - t0) / args.steps
         m = args.spectra_per_gpu
         same = bool(np.array_equal(np.array(c[:m]), ref_c) and np.array(f[:m]).tobytes() == ref_f.tobytes())
-        out["runs"].append({"n_gpus": n, "e2e_spectra_per_s": len(sub) / dt, "ms_per_call": dt * 1e3, "first_block_equals_single_gpu": same})
+        out["runs"].append({"n_gpus": n, "numa_blocks": bool(args.numa_blocks), "e2e_spectra_per_s": len(sub) / dt, "ms_per_call": dt * 1e3, "first_block_equals_single_gpu": same})
         f, c = np.array(f), np.array(c)
         api.pinned_free(hs.masses); api.pinned_free(hs.intensities)
         n *= 2
