@@ -15,6 +15,17 @@
 #include "device_common.cuh"
 #include "glibc_log.cuh"
 
+// Paths k_score rarely takes (the generic peak lookup of unsorted spectra, the warp-per-candidate scorer that only serves remove_matched_peaks,
+// the Fragments writer): kept out of line so that the hot loop's code stays compact in the instruction cache (A/B: profiles/r02_*).
+#ifndef SAGE_B200_RARE_NOINLINE
+#define SAGE_B200_RARE_NOINLINE 0
+#endif
+#if SAGE_B200_RARE_NOINLINE
+#define SB_RARE __noinline__
+#else
+#define SB_RARE __forceinline__
+#endif
+
 namespace sb {
 
 // ------------------------------------------------------------------------------------------------ setup
@@ -1355,7 +1366,7 @@ struct ScoreRec {
 };
 
 // select_most_intense_peak (spectrum.rs:134-159), offset None — exact binary_search_slice emulation (any input)
-__device__ __forceinline__ int select_most_intense_peak(const float* masses, const float* intens, uint32_t n, float center, const Tol& tol) {
+__device__ SB_RARE int select_most_intense_peak(const float* masses, const float* intens, uint32_t n, float center, const Tol& tol) {
     float lo, hi;
     tol_bounds(tol, center, lo, hi);
     lo = __fadd_rn(lo, 0.0f);
@@ -1435,7 +1446,7 @@ struct Run {
 // (kind, ion index, charge) with a ballot loop so the f32 accumulations (summed_b/y, ppm_difference) are bit-identical.
 struct SpecView { const float* masses; const float* intens; uint32_t np; bool use_lut; LutParams lp; const uint16_t* lut; };
 
-__device__ __forceinline__ void score_candidate_warp(const DbView& db, const ScorerView& sc, uint64_t key, const SpecView& sp, ScoreRec* out,
+__device__ SB_RARE void score_candidate_warp(const DbView& db, const ScorerView& sc, uint64_t key, const SpecView& sp, ScoreRec* out,
                                                      uint8_t* mark /*nullable: remove_matched_peaks marks*/) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t pep = key_peptide(key), charge = key_charge(key);
@@ -1803,7 +1814,7 @@ __device__ __forceinline__ void score_candidates_flat(const DbView& db, const Sc
 
 // Fragments of one reported PSM (scoring.rs:738-751), written by one warp in the reference's order (kind, ion index, charge) to
 // out[0 .. matched_b + matched_y). Same lookups as score_candidate_warp on the same spectrum state.
-__device__ __forceinline__ void annotate_candidate_warp(const DbView& db, const ScorerView& sc, uint32_t pep, uint32_t charge, const SpecView& sp,
+__device__ SB_RARE void annotate_candidate_warp(const DbView& db, const ScorerView& sc, uint32_t pep, uint32_t charge, const SpecView& sp,
                                                         FragmentOut* out, uint32_t cap_left) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t L = __ldg(db.pep_len + pep);

@@ -219,6 +219,10 @@ static int db_upload_peptides(sage_b200_db* db, const sage_b200_peptides* P, con
     CUDA_TRY(cudaMemcpy(db->d_ion_off, ion_off.data(), 4 * (n + 1), cudaMemcpyHostToDevice));
     // temporaries for ion generation
     void *t_off = nullptr, *t_seq = nullptr, *t_mods = nullptr, *t_nterm = nullptr, *t_res = nullptr;
+    struct Temps {   // freed on every exit of this function
+        void **a, **b, **c, **d, **e;
+        ~Temps() { for (void** p : {a, b, c, d, e}) if (*p) cudaFree(*p); }
+    } temps{&t_off, &t_seq, &t_mods, &t_nterm, &t_res};
     CUDA_TRY(cudaMalloc(&t_off, 4 * (n + 1) + 16));
     CUDA_TRY(cudaMalloc(&t_seq, nres + 16));
     CUDA_TRY(cudaMalloc(&t_mods, 4 * nres + 16));
@@ -244,7 +248,6 @@ static int db_upload_peptides(sage_b200_db* db, const sage_b200_peptides* P, con
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaDeviceSynchronize());
-    cudaFree(t_off); cudaFree(t_seq); cudaFree(t_mods); cudaFree(t_nterm); cudaFree(t_res);
     return 0;
 }
 
@@ -363,9 +366,13 @@ extern "C" int sage_b200_db_create(const sage_b200_peptides* peptides, const sag
     auto cleanup = [&]() { if (t_pep) cudaFree(t_pep); if (t_mz) cudaFree(t_mz); };
     if (nf) {
         if (cudaMalloc(&t_pep, 4 * nf) != cudaSuccess || cudaMalloc(&t_mz, 4 * nf) != cudaSuccess) { cleanup(); sage_b200_db_destroy(db); return fail(SAGE_B200_ECUDA, "cudaMalloc of upload temporaries failed"); }
-        cudaMemcpy(t_pep, index->fragment_peptide, 4 * nf, cudaMemcpyHostToDevice);
-        cudaMemcpy(t_mz, index->fragment_mz, 4 * nf, cudaMemcpyHostToDevice);
-        cudaMemcpy(db->d_bucket_min, index->bucket_min, 4 * index->n_buckets, cudaMemcpyHostToDevice);
+        cudaError_t ce = cudaMemcpy(t_pep, index->fragment_peptide, 4 * nf, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(t_mz, index->fragment_mz, 4 * nf, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(db->d_bucket_min, index->bucket_min, 4 * index->n_buckets, cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) {   // these errors are not sticky: a later synchronize would not report them and the index would be garbage
+            cleanup(); sage_b200_db_destroy(db);
+            return fail(SAGE_B200_ECUDA, "index upload failed: %s", cudaGetErrorString(ce));
+        }
         k_pack_fragments_soa<<<(unsigned)((nf + 255) / 256), 256>>>(nf, (const uint32_t*)t_pep, (const float*)t_mz, (uint2*)db->d_frag);
     }
     cudaError_t e = cudaDeviceSynchronize();
@@ -392,9 +399,8 @@ extern "C" int sage_b200_db_create(const sage_b200_peptides* peptides, const sag
         if (found >= 0) {
             void *acc = nullptr, *mis = nullptr;
             uint32_t mismatch = 1;
-            if (cudaMalloc(&acc, 8 * n) == cudaSuccess && cudaMalloc(&mis, 4) == cudaSuccess) {
-                cudaMemset(acc, 0, 8 * n);
-                cudaMemset(mis, 0, 4);
+            if (cudaMalloc(&acc, 8 * n) == cudaSuccess && cudaMalloc(&mis, 4) == cudaSuccess && cudaMemset(acc, 0, 8 * n) == cudaSuccess &&
+                cudaMemset(mis, 0, 4) == cudaSuccess) {
                 k_index_signature<<<(unsigned)((nf + 255) / 256), 256>>>(nf, db->v.frag, (uint32_t)n, (uint32_t*)acc);
                 k_index_verify<<<(unsigned)((n + 127) / 128), 128>>>((uint32_t)n, db->v.pep_len, db->v.ion_off, db->v.ions, db->v.n_kinds, db->v, (uint32_t)found,
                                                                     (const uint32_t*)acc, (uint32_t*)mis);
@@ -678,7 +684,8 @@ struct Lane {
     cudaStream_t stream = nullptr;   // kernels + D2H
     cudaStream_t copy = nullptr;     // H2D: masses first (all the counting kernels need), intensities behind them, overlapping setup + preliminary scoring
     cudaEvent_t ev[9] = {};   // 0/1 H2D, 6 run start, 2 setup end, 8 counting kernels end, 3 replay end, 4 k_score end, 7/5 D2H
-    cudaEvent_t ev_masses = nullptr, ev_intens = nullptr;
+    cudaStream_t copy2 = nullptr;    // H2D of the small per-spectrum blob: lands while the masses are still in flight, so k_setup_queries + sort overlap that copy
+    cudaEvent_t ev_masses = nullptr, ev_intens = nullptr, ev_small = nullptr;
     DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_dbgk, d_dbgm, d_sort, d_sorttmp, d_wlist, d_wslots,
         d_witems, d_citems, d_nlist, d_nslots;
     PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
@@ -697,6 +704,8 @@ struct Lane {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (ev_masses) cudaEventDestroy(ev_masses);
         if (ev_intens) cudaEventDestroy(ev_intens);
+        if (ev_small) cudaEventDestroy(ev_small);
+        if (copy2) cudaStreamDestroy(copy2);
         if (stream) cudaStreamDestroy(stream);
         if (copy) cudaStreamDestroy(copy);
     }
@@ -785,6 +794,8 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
         for (auto& e : L.ev) CUDA_TRY(cudaEventCreate(&e));
         CUDA_TRY(cudaEventCreate(&L.ev_masses));
         CUDA_TRY(cudaEventCreate(&L.ev_intens));
+        CUDA_TRY(cudaEventCreate(&L.ev_small));
+        CUDA_TRY(cudaStreamCreateWithFlags(&L.copy2, cudaStreamNonBlocking));
     }
     if (const char* e = getenv("SAGE_B200_PIPELINE_CHUNKS")) s->pipeline_chunks = std::max(1, atoi(e));
     if (const char* e = getenv("SAGE_B200_TRACE")) s->trace = e[0] == '1';
@@ -929,8 +940,10 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
         cudaStreamSynchronize(cp);   // the masses copy may still be reading the caller's array
         return rc;
     }
-    CUDA_TRY(cudaMemcpyAsync(L.d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, cp));
-    CUDA_TRY(cudaEventRecord(L.ev_masses, cp));   // setup + preliminary scoring can start: they never read intensities
+    // the small blob goes on its own stream (a second copy engine): it lands right away, k_setup_queries + the ordering sort only need it
+    CUDA_TRY(cudaMemcpyAsync(L.d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, L.copy2));
+    CUDA_TRY(cudaEventRecord(L.ev_small, L.copy2));
+    CUDA_TRY(cudaEventRecord(L.ev_masses, cp));   // preliminary scoring can start: it never reads intensities
     if (npk) {
         if (pin_i) CUDA_TRY(cudaMemcpyAsync(L.d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, cp));
         else if ((rc = staged_h2d(L.d_intens.p, src_i, 4 * npk, L.h_intens, cp))) { cudaStreamSynchronize(cp); return rc; }
@@ -981,7 +994,7 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     // kernels of the two lanes never overlap (measured: k_score of one chunk next to k_prelim_narrow of the other slows both); only
     // copies overlap kernels. ev[4] = end of the other lane's k_score (a never-recorded event counts as complete).
     CUDA_TRY(cudaStreamWaitEvent(st, S->lanes[(&L - S->lanes) ^ 1].ev[4], 0));
-    CUDA_TRY(cudaStreamWaitEvent(st, L.ev_masses, 0));
+    CUDA_TRY(cudaStreamWaitEvent(st, L.ev_small, 0));
     CUDA_TRY(cudaEventRecord(L.ev[6], st));
     CUDA_TRY(cudaMemsetAsync(L.d_counters.p, 0, 8 * (C_COUNT + (size_t)sv.qmax), st));
     const bool annotate = sv.annotate && S->frag_dst != nullptr;
@@ -1034,6 +1047,7 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
         bv.order = sv_out;
     }
     CUDA_TRY(cudaEventRecord(L.ev[2], st));
+    CUDA_TRY(cudaStreamWaitEvent(st, L.ev_masses, 0));   // the counting kernels read the peak masses
     uint64_t launches = 1;
 
     // ---- preliminary scoring. Both kernels are always queued: CTAs whose query belongs to the other kernel (or to nobody) exit at once.
@@ -1121,6 +1135,7 @@ static int lane_finish(sage_b200_scorer* S, Lane& L) {
     ChunkState& C = L.chunk;
     if (!C.loaded) return 0;
     CUDA_TRY(cudaStreamSynchronize(L.copy));
+    CUDA_TRY(cudaStreamSynchronize(L.copy2));
     for (int attempt = 0;; attempt++) {
         CUDA_TRY(cudaStreamSynchronize(L.stream));
         if (!L.ran) break;
@@ -1217,6 +1232,7 @@ static int drain_lanes(sage_b200_scorer* S, int rc) {
     const std::string msg = g_last_error;
     for (Lane& L : S->lanes) {
         if (L.copy) cudaStreamSynchronize(L.copy);
+        if (L.copy2) cudaStreamSynchronize(L.copy2);
         if (L.stream) cudaStreamSynchronize(L.stream);
         L.chunk.loaded = false; L.ran = false; L.downloading = false;
     }
@@ -1245,6 +1261,7 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
     S->frag_used = 0;
     for (Lane& L : S->lanes) {   // a previous call may have failed half-way: make sure nothing is still queued on the lanes
         CUDA_TRY(cudaStreamSynchronize(L.copy));
+        CUDA_TRY(cudaStreamSynchronize(L.copy2));
         CUDA_TRY(cudaStreamSynchronize(L.stream));
         L.chunk.loaded = false; L.ran = false; L.downloading = false;
     }
@@ -1312,7 +1329,31 @@ static int score_batch_chunks(sage_b200_scorer* S, const sage_b200_spectra* sp, 
 // Pins the calling host thread to the CPUs of the NUMA node the GPU hangs off (sysfs: PCI device -> numa_node -> cpulist), so that the thread's
 // pinned staging buffers (first touch) and its cudaMemcpyAsync submissions stay on the socket next to the GPU. Returns the node (>= 0), or -1
 // when the topology cannot be read (single-node hosts, containers without sysfs): the thread is left alone.
+static int device_numa_cpus(int device, cpu_set_t* want_out);
+
 extern "C" int sage_b200_bind_thread_to_device(int device) {
+    // topology lookups (sysfs) are cached per device: score_batch_multi binds its worker threads on every call
+    static std::mutex mu;
+    static int node_of[64];
+    static cpu_set_t cpus_of[64];
+    static bool known[64] = {};
+    cpu_set_t want;
+    int node;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (device >= 0 && device < 64 && known[device]) { node = node_of[device]; want = cpus_of[device]; }
+        else {
+            node = device_numa_cpus(device, &want);
+            if (device >= 0 && device < 64) { known[device] = true; node_of[device] = node; cpus_of[device] = want; }
+        }
+    }
+    if (node < 0) return -1;
+    if (pthread_setaffinity_np(pthread_self(), sizeof want, &want) != 0) return -1;
+    return node;
+}
+
+// NUMA node of the GPU and the CPUs of that node this process may run on (-1: unknown).
+static int device_numa_cpus(int device, cpu_set_t* want_out) {
     char bus[64] = {0};
     if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
     for (char* c = bus; *c; c++) *c = (char)tolower(*c);
@@ -1331,9 +1372,11 @@ extern "C" int sage_b200_bind_thread_to_device(int device) {
     const size_t got = fread(list, 1, sizeof list - 1, f);
     fclose(f);
     if (got == 0) return -1;
-    cpu_set_t cur, want;
+    // CPUs the process was given when the library was loaded (before any thread was bound by us): never widen that set
+    static const cpu_set_t initial = []() { cpu_set_t c; CPU_ZERO(&c); sched_getaffinity(0, sizeof c, &c); return c; }();
+    cpu_set_t cur = initial, want;
     CPU_ZERO(&want);
-    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return -1;
+    if (CPU_COUNT(&cur) == 0) return -1;
     int n_set = 0;
     for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {   // "0-31,64-95"
         int a = 0, b = 0;
@@ -1344,7 +1387,7 @@ extern "C" int sage_b200_bind_thread_to_device(int device) {
             if (CPU_ISSET(c, &cur)) { CPU_SET(c, &want); n_set++; }   // never widen the affinity the process was given
     }
     if (n_set == 0) return -1;
-    if (pthread_setaffinity_np(pthread_self(), sizeof want, &want) != 0) return -1;
+    *want_out = want;
     return node;
 }
 
