@@ -140,9 +140,10 @@ def measured_hbm_peak():
 
 
 def kernel_sources_sha():
-    """Hash of the CUDA sources the library is built from: profiles/traffic.json is only trusted when it was captured from these sources."""
+    """Hash of the DEVICE code the library is built from (DRAM traffic is a property of the kernels, not of the host runtime):
+    profiles/traffic.json is only trusted when it was captured from these sources."""
     h = hashlib.sha256()
-    for f in ("kernels.cuh", "device_common.cuh", "sage_b200.cu", "glibc_log.cuh"):
+    for f in ("kernels.cuh", "device_common.cuh", "glibc_log.cuh", "glibc_log_data.cuh"):
         h.update(open(os.path.join(ROOT, "sage_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 

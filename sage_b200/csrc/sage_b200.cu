@@ -684,7 +684,7 @@ struct Lane {
     cudaStream_t stream = nullptr;   // kernels + D2H
     cudaStream_t copy = nullptr;     // H2D: masses first (all the counting kernels need), intensities behind them, overlapping setup + preliminary scoring
     cudaEvent_t ev[9] = {};   // 0/1 H2D, 6 run start, 2 setup end, 8 counting kernels end, 3 replay end, 4 k_score end, 7/5 D2H
-    cudaStream_t copy2 = nullptr;    // H2D of the small per-spectrum blob: lands while the masses are still in flight, so k_setup_queries + sort overlap that copy
+    cudaStream_t copy2 = nullptr;    // (unused: a second H2D stream did not overtake the queued bulk copies, see chunk_upload)
     cudaEvent_t ev_masses = nullptr, ev_intens = nullptr, ev_small = nullptr;
     DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_dbgk, d_dbgm, d_sort, d_sorttmp, d_wlist, d_wslots,
         d_witems, d_citems, d_nlist, d_nslots;
@@ -940,9 +940,11 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
         cudaStreamSynchronize(cp);   // the masses copy may still be reading the caller's array
         return rc;
     }
-    // the small blob goes on its own stream (a second copy engine): it lands right away, k_setup_queries + the ordering sort only need it
-    CUDA_TRY(cudaMemcpyAsync(L.d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, L.copy2));
-    CUDA_TRY(cudaEventRecord(L.ev_small, L.copy2));
+    // The small blob follows the masses on the SAME stream. Measured (profiles/r02_final_trace_cfg2.txt): on a second stream it is not served
+    // by a second copy engine ahead of the queued bulk copies — it landed after BOTH of them (1.5 ms instead of 0.73 ms) and the whole
+    // pipeline started 0.75 ms later (e2e 3.48 -> 4.06 ms); k_setup_queries + sort (0.17 ms) therefore still start when the masses land.
+    CUDA_TRY(cudaMemcpyAsync(L.d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, cp));
+    CUDA_TRY(cudaEventRecord(L.ev_small, cp));
     CUDA_TRY(cudaEventRecord(L.ev_masses, cp));   // preliminary scoring can start: it never reads intensities
     if (npk) {
         if (pin_i) CUDA_TRY(cudaMemcpyAsync(L.d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, cp));

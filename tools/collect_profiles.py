@@ -67,7 +67,7 @@ for rep, wl, kernels in (("prof_cfg2.ncu-rep", "cfg2", ["k_score", "k_prelim_nar
     traffic[wl] = {}
     for e in summ:
         for k in kernels:
-            if k + "(" in e["Kernel Name"] or ("::" + k) in e["Kernel Name"].split("(")[0]:
+            if k in e["Kernel Name"].split("(")[0]:
                 def num(x):
                     v, u = x.split()[0], x.split()[1] if len(x.split()) > 1 else ""
                     m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)

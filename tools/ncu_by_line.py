@@ -47,10 +47,14 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 45
     raw = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kernel], stderr=subprocess.DEVNULL).decode()
     rows = list(csv.reader(raw.splitlines()))
-    hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-    hdr = rows[hi]
+    # a report with several kernels prints one block per launch: "Kernel Name" line, column header ("Address", ...), instructions
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] or [0]
+    blocks = [(rows[a][1] if len(rows[a]) > 1 else "", rows[a:b]) for a, b in zip(starts, starts[1:] + [len(rows)])]
+    name, blk = next(((n, b) for n, b in blocks if kernel in n.split("(")[0]), blocks[0])
+    hi = next(i for i, r in enumerate(blk) if r and r[0] == "Address")
+    hdr = blk[hi]
     col = {h: i for i, h in enumerate(hdr)}
-    inst = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    inst = [r for r in blk[hi + 1:] if len(r) == len(hdr) and r[0] != "Address"]
     sass = sass_lines(so, kernel)
     if len(sass) != len(inst):
         print(f"# warning: {len(inst)} instructions in the report vs {len(sass)} in the disassembly (different build?)", file=sys.stderr)
