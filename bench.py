@@ -101,25 +101,38 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.stop, self.th = gpu, [], threading.Event(), None
-
-    def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.check_output(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"], timeout=5).decode()
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.05)
+        self.gpu, self.rows, self.proc, self.path = gpu, [], None, None
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        # ONE nvidia-smi process polling every 50 ms, started (and past its driver initialisation) before the timed regions begin: spawning
+        # a fresh nvidia-smi per sample put its start-up (NVML init takes driver locks) inside the timed e2e calls.
+        import tempfile
+        fd, self.path = tempfile.mkstemp(prefix="sage_b200_clocks_", suffix=".csv")
+        os.close(fd)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            t0 = time.time()
+            while time.time() - t0 < 5.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.02)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.th.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.06)   # one more sample after the last timed call
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        try:
+            for ln in open(self.path).read().strip().splitlines():
+                self.rows.append([x.strip() for x in ln.split(",")])
+            os.unlink(self.path)
+        except Exception:
+            pass
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -310,8 +323,12 @@ def run_workload(name, wl, steps, warmup, rank, local_rank, world, gpus, D, cpu,
         # ---- timed: K steps end to end through sage_b200_score_batch (pinned host in, pinned host out)
         D.barrier()
         t0 = time.perf_counter()
+        per_call, in_lib = [], []
         for _ in range(steps):
+            t1 = time.perf_counter()
             scorer.score_batch(hspec, out, counts)
+            per_call.append(time.perf_counter() - t1)
+            in_lib.append(scorer.counters()["ms_wall"])
         D.barrier()
         wall_e2e = time.perf_counter() - t0
         e2e_c = scorer.counters()
@@ -364,7 +381,8 @@ def run_workload(name, wl, steps, warmup, rank, local_rank, world, gpus, D, cpu,
                 "step": {"algorithmic_bytes": int(last["algorithmic_bytes"]), "device_ms": step_s * 1e3,
                          "achieved": last["algorithmic_bytes"] / step_s / 1e9, "frac": last["algorithmic_bytes"] / step_s / 1e9 / peak}}
     e2e = {"value": e2e_value, "unit": "spectra/s", "h2d_bytes_per_step": int(e2e_c["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_c["d2h_bytes"]),
-           "ms_per_step": wall_e2e * 1000.0 / steps}
+           "ms_per_step": wall_e2e * 1000.0 / steps, "ms_per_call_median_rank0": float(np.median(per_call)) * 1000.0,
+           "ms_per_call_max_rank0": float(np.max(per_call)) * 1000.0, "ms_in_library_median_rank0": float(np.median(in_lib))}
     if wall_page is not None:
         e2e["pageable"] = {"value": total_spectra / wall_page, "unit": "spectra/s", "ms_per_step": wall_page * 1000.0 / steps,
                            "note": "same C-ABI call with ordinary (unpinned) host arrays in and out"}

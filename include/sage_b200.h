@@ -137,6 +137,7 @@ typedef struct {
     uint64_t chunk_retries;        /* chunks re-run because a device work list was sized too small (first batches of a scorer) */
     float ms_total, ms_h2d, ms_setup, ms_prelim, ms_score, ms_d2h; /* summed over chunks */
     float ms_prelim_count;         /* the part of ms_prelim before the heap-replay kernels: k_prelim_narrow_warp + k_prelim_narrow */
+    float ms_wall;                 /* host wall clock of the last score_batch call, entry to return (includes every copy and wait) */
 } sage_b200_counters;
 
 int sage_b200_device_count(void);

@@ -64,7 +64,7 @@ class CSpectra(C.Structure):
 
 COUNTER_U64 = ["spectra", "peaks", "queries", "tasks", "pages", "entries_scanned", "matched_fragments", "candidates_scored", "peptide_record_floats",
                "psms", "wide_queries", "pep_queries", "pep_fallbacks", "wide_overflows", "algorithmic_bytes", "prelim_bytes", "score_bytes", "h2d_bytes", "d2h_bytes", "kernel_launches", "chunk_retries"]
-COUNTER_F32 = ["ms_total", "ms_h2d", "ms_setup", "ms_prelim", "ms_score", "ms_d2h", "ms_prelim_count"]
+COUNTER_F32 = ["ms_total", "ms_h2d", "ms_setup", "ms_prelim", "ms_score", "ms_d2h", "ms_prelim_count", "ms_wall"]
 
 
 class CCounters(C.Structure):

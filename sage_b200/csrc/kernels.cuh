@@ -53,8 +53,12 @@ __device__ __forceinline__ uint32_t pep_partition(const DbView& db, float x, boo
 }
 
 __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t* sort_key, uint32_t* sort_val) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.n) return;
+    // The chunk-wide sums below go through one atomic per CTA: 50 000 threads adding to the same cache line cost ~85 us of a 100 us kernel
+    // (the L2 atomic unit serialises per address, ~0.85 cycles per lane).
+    __shared__ unsigned long long s_sum[4][8];   // [nq, list_need, npepq, maxpot][warp]
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long nq = 0, nwide = 0, maxpot = 0, npepq = 0, list_need = 0, ncta = 0;
+    if (s < b.n) {
     const float pmz = b.prec_mz[s];
     const uint32_t known = b.prec_charge[s];
     const float mz = __fsub_rn(pmz, PROTON);  // scoring.rs:420
@@ -63,7 +67,6 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
     uint32_t c1 = fold ? sc.max_charge : known;
     QueryDesc* out = b.queries + (size_t)s * sc.qmax;
     uint32_t qi = 0;
-    unsigned long long nq = 0, nwide = 0, maxpot = 0, npepq = 0, list_need = 0, ncta = 0;
     for (uint32_t z = c0; z <= c1 && qi < sc.qmax; z++) {
         const float precursor_mass = __fmul_rn(mz, (float)z);
         Tol ptol = sc.precursor_tol;
@@ -119,7 +122,6 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
         out[qi] = q;
     }
     if (sort_key) { sort_key[s] = out[0].mode ? out[0].pre_lo : 0xFFFFFFFFu; sort_val[s] = s; }
-    if (nq) atomicAdd(b.counters + C_QUERIES, nq);
     if (nwide) {   // compact work list of the open-search queries (one reservation per spectrum)
         unsigned long long w = atomicAdd(b.counters + C_WIDE, nwide);
         for (uint32_t j = 0; j < sc.qmax; j++)
@@ -134,10 +136,27 @@ __global__ void k_setup_queries(DbView db, ScorerView sc, BatchView b, uint32_t*
         ReplaySlot rs; rs.off = 0; rs.item = s * sc.qmax + j; rs.n_list = 0; rs.state = 1; rs.k = 0;
         b.nslots[(size_t)s * sc.qmax + j] = rs;
     }
-    if (list_need) atomicAdd(b.counters + C_NLIST_NEED, list_need);
-    if (npepq) atomicAdd(b.counters + C_PEPQ, npepq);
-    atomicMax(b.counters + C_MAXPOT, maxpot);
+    }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        nq += __shfl_down_sync(0xffffffffu, nq, o);
+        list_need += __shfl_down_sync(0xffffffffu, list_need, o);
+        npepq += __shfl_down_sync(0xffffffffu, npepq, o);
+        maxpot = max(maxpot, __shfl_down_sync(0xffffffffu, maxpot, o));
+    }
+    if (lane == 0) { s_sum[0][warp] = nq; s_sum[1][warp] = list_need; s_sum[2][warp] = npepq; s_sum[3][warp] = maxpot; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (uint32_t w = 1; w < (blockDim.x >> 5); w++) {
+            nq += s_sum[0][w]; list_need += s_sum[1][w]; npepq += s_sum[2][w]; maxpot = max(maxpot, s_sum[3][w]);
+        }
+        if (nq) atomicAdd(b.counters + C_QUERIES, nq);
+        if (list_need) atomicAdd(b.counters + C_NLIST_NEED, list_need);
+        if (npepq) atomicAdd(b.counters + C_PEPQ, npepq);
+        if (maxpot) atomicMax(b.counters + C_MAXPOT, maxpot);
+    }
 }
+
 
 // --------------------------------------------------------------------------------------------- block helpers
 __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* s_warp) {
@@ -528,13 +547,17 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
 // counts of the window live in the warp's slice of shared memory, sums are warp shuffles, and the ordered key list for k_replay
 // is emitted with ballots. grid = (ceil(n / WARPQ_WARPS) in precursor order, query slot): slot-major, so CTAs of slots no spectrum uses
 // (e.g. the charge fold of known-charge spectra) sit at the end of the grid and leave after one cached load.
-__global__ void __launch_bounds__(WARPQ_WARPS * 32, WARPQ_MIN_CTAS) k_prelim_narrow_warp(DbView db, ScorerView sc, BatchView b, uint64_t* nlist) {
+__global__ void __launch_bounds__(WARPQ_WARPS * 32, WARPQ_MIN_CTAS) k_prelim_narrow_warp(DbView db, ScorerView sc, BatchView b, uint64_t* nlist, uint32_t s_lo,
+                                                                                                uint32_t s_hi) {
     __shared__ uint32_t cnt_all[WARPQ_WARPS][WARPQ_CAP / 2];
     if (b.counters[C_COUNT + blockIdx.y] == 0ull) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t pos = blockIdx.x * WARPQ_WARPS + warp;
     if (pos >= b.n) return;
     const uint32_t s = b.order ? b.order[pos] : pos;
+    // [s_lo, s_hi): the spectra (caller order) whose peak masses are on the device when this launch runs — the host queues one launch per part
+    // of the masses copy, each still walking its spectra in precursor order
+    if (s < s_lo || s >= s_hi) return;
     const uint32_t item = s * sc.qmax + blockIdx.y;
     const QueryDesc q = b.queries[item];
     if (q.mode != 4) return;
@@ -1574,6 +1597,18 @@ struct __align__(16) CandHdr { uint32_t ion_off, base, next; uint16_t nions; uin
 
 __device__ __forceinline__ bool fast_tol_ok(float t) { const float a = fabsf(t); return t == 0.0f || (a >= 1e-9f && a <= 1e6f); }
 
+// Optional per-phase cycle accounting of k_score (variant builds only: -DSAGE_B200_PHASE_CLOCKS=1): thread 0 of every CTA adds the cycles
+// between consecutive marks to g_phase[i]; read back with sage_b200_debug_phase_cycles (tools/phase_cycles.py).
+#if SAGE_B200_PHASE_CLOCKS
+__device__ unsigned long long g_phase[16];
+__shared__ long long s_ph_prev;
+#define PH_START() do { if (threadIdx.x == 0) s_ph_prev = clock64(); } while (0)
+#define PH(i) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_phase[i], (unsigned long long)(n_ - s_ph_prev)); s_ph_prev = n_; } } while (0)
+#else
+#define PH_START() do {} while (0)
+#define PH(i) do {} while (0)
+#endif
+
 // Shared-memory tile of score_candidates_flat. Static (compile-time addresses: no base-pointer arithmetic in the task loop).
 struct ScoreTile {
     CandHdr hdr[K_MAX + 1];        // candidate headers + sentinel
@@ -1672,6 +1707,7 @@ __device__ __forceinline__ void score_candidates_flat(const DbView& db, const Sc
     for (uint32_t t0 = 0; t0 < T; t0 += tile) {
         const uint32_t tn = min(tile, T - t0);
         __syncthreads();   // headers written / previous tile's fold done with the tile arrays
+        PH(t0 == 0 ? 3 : 5);
         // ---- phase B: each warp takes a contiguous run of the tile; per iteration a lane owns SCORE_UNROLL tasks 32 apart (with 2: two
         // independent dependency chains, both ion loads issued before either is used)
         constexpr uint32_t STEP = 32 * SCORE_UNROLL;
@@ -1766,6 +1802,7 @@ __device__ __forceinline__ void score_candidates_flat(const DbView& db, const Sc
             }
         }
         __syncthreads();
+        PH(4);
         // ---- fold: thread c walks the set bits of candidate c's slice of the tile in ascending task order
         if (tid < ncand && total) {
             const uint32_t a = max(base, t0), b = min(base + total, t0 + tn);
@@ -1892,6 +1929,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
     __shared__ float s_tic;
 
     const uint32_t s = b.order ? b.order[blockIdx.x] : blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SCORE_THREADS / 32;
+    PH_START();
     const uint32_t p0 = b.peak_off[s];
     uint32_t np = b.peak_off[s + 1] - p0;
     // Stage the spectrum's peaks with the bulk-async copy engine (TMA 1-D): two cp.async.bulk copies complete on an mbarrier while the
@@ -1973,11 +2011,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
         s_tic = b.tic[s];
     }
     __syncthreads();
+    PH(0);
     if (dbg_keys != nullptr) {  // white-box dump of initial_hits
         for (uint32_t i = tid; i < s_ntot; i += SCORE_THREADS) dbg_keys[(size_t)s * sc.kparam + i] = tot[i];
         if (tid == 0) { dbg_meta[s * 4 + 0] = s_ntot; dbg_meta[s * 4 + 1] = (uint32_t)s_matched_peaks; dbg_meta[s * 4 + 2] = (uint32_t)s_scored; }
     }
     if (np) mbar_wait(&s_bar, 0);   // peaks have landed in shared memory
+    PH(1);
     if (tid == 0) masses[np] = INFINITY;   // sentinel behind the last peak (slack of the staging buffer): ends the LUT walk and the peak scans
     const uint32_t ncand = s_ncand;
     // quick_score accumulates into keep[] across chunks; a chunk whose work lists overflowed (the host re-runs it with exact sizes) has partial hit
@@ -1999,12 +2039,14 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
         np = s_np;
         sv.np = np;
         sv.use_lut = spectrum_lut_setup(masses, np, lut, sv.lp);
+        PH(2);
         if (tid == 0) s_nvalid = 0;
         if (sv.use_lut && sc.score_fast && sc.fragment_tol.kind == 0 && fast_tol_ok(sc.fragment_tol.lo) && fast_tol_ok(sc.fragment_tol.hi))
             score_candidates_flat<true>(db, sc, cur, ncand, sv, S, recs);
         else
             score_candidates_flat<false>(db, sc, cur, ncand, sv, S, recs);
         __syncthreads();
+        PH(5);
         if (quick_mode == 2) {
             // Scorer::quick_score, low-memory branch (scoring.rs:270-290): bounded_min_heapify(score_vector, report_psms) compares Score
             // with its DERIVED PartialOrd whose first field is the peptide index (heap.rs uses < and >), so the kept set is the
@@ -2140,6 +2182,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
         }
         __syncthreads();
     }
+    PH(6);
     if (tid == 0) {
         counts[s] = nout;
         if (nout) atomicAdd(b.counters + C_PSMS, (unsigned long long)nout);

@@ -20,6 +20,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -96,43 +98,95 @@ struct PinBuf {
     }
 };
 
-// Host -> device copy of a PAGEABLE array (a Rust Vec<f32>, a numpy array) through a pinned staging buffer: a few helper threads copy 2 MB pieces
+// Host -> device copy of a PAGEABLE array (a Rust Vec<f32>, a numpy array) through a pinned staging buffer: a few pool threads copy 2 MB pieces
 // into the staging buffer while the calling thread submits each piece's DMA as soon as it is staged, so the memcpy (one core moves ~10 GB/s,
-// PCIe 5 x16 ~55 GB/s) overlaps the transfer instead of preceding it.
-static int staged_h2d(void* dst, const void* src, size_t bytes, PinBuf& stage, cudaStream_t st) {
+// PCIe 5 x16 ~55 GB/s) overlaps the transfer instead of preceding it. The pool threads are persistent (one pool per pipeline lane, started by
+// the first pageable chunk): creating 6 threads per array cost ~0.25 ms of a 6 ms call. Measured on cfg2 (ms per 50k-spectrum call, 2 MB pieces):
+// 3 threads 6.5 | 6 -> 6.0 | 12 -> 7.2 | 16 x 1 MB 9.0 | 24 x 512 KB 9.5 (spawned per call; more copy threads only fight the DMA reads for the
+// memory controllers).
+struct StagePool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t gen = 0;
+    bool quit = false;
+    const char* src = nullptr;
+    char* dst = nullptr;
+    size_t bytes = 0, piece = 0, np = 0, done_cap = 0;
+    std::atomic<size_t> next{0};
+    std::atomic<int> busy{0};
+    std::unique_ptr<std::atomic<unsigned char>[]> done;
+
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || gen != seen; });
+                if (quit) return;
+                seen = gen;
+            }
+            for (;;) {
+                const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+                if (i >= np) break;
+                const size_t off = i * piece, len = std::min(piece, bytes - off);
+                memcpy(dst + off, src + off, len);
+                done[i].store(1, std::memory_order_release);
+            }
+            busy.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    // Copies src -> stage in pieces with the pool and submits piece i's DMA (stage -> device) as soon as pieces 0..i are staged.
+    cudaError_t run(void* dev, const void* s, size_t n, void* stage, size_t piece_bytes, size_t nthreads, cudaStream_t st) {
+        if (th.size() < nthreads) {
+            const size_t have = th.size();
+            for (size_t t = have; t < nthreads; t++) th.emplace_back([this] { worker(); });
+        }
+        const size_t pieces = (n + piece_bytes - 1) / piece_bytes;
+        if (pieces > done_cap) { done.reset(new std::atomic<unsigned char>[pieces]); done_cap = pieces; }
+        for (size_t i = 0; i < pieces; i++) done[i].store(0, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            src = (const char*)s; dst = (char*)stage; bytes = n; piece = piece_bytes; np = pieces;
+            next.store(0, std::memory_order_relaxed);
+            busy.store((int)th.size(), std::memory_order_relaxed);
+            gen++;
+        }
+        cv.notify_all();
+        cudaError_t e = cudaSuccess;
+        for (size_t i = 0; i < pieces; i++) {
+            while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+            const size_t off = i * piece_bytes, len = std::min(piece_bytes, n - off);
+            if (e == cudaSuccess) e = cudaMemcpyAsync((char*)dev + off, (char*)stage + off, len, cudaMemcpyHostToDevice, st);
+        }
+        while (busy.load(std::memory_order_acquire) != 0) std::this_thread::yield();   // every worker has left the job: its fields may change
+        return e;
+    }
+    ~StagePool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+};
+
+static int staged_h2d(void* dst, const void* src, size_t bytes, PinBuf& stage, StagePool& pool, cudaStream_t st) {
     if (bytes == 0) return 0;
     int rc = stage.reserve(bytes);
     if (rc) return rc;
-    const size_t piece = 2u << 20;
+    static const size_t piece = []() { const char* e = getenv("SAGE_B200_STAGE_PIECE_KB"); return (size_t)std::max(64, e ? atoi(e) : 2048) << 10; }();
+    static const size_t max_threads = []() { const char* e = getenv("SAGE_B200_STAGE_THREADS"); return (size_t)std::max(1, e ? atoi(e) : 6); }();
     const size_t np = (bytes + piece - 1) / piece;
-    if (np <= 2) {   // small: a plain copy is cheaper than starting threads
+    if (np <= 2) {   // small: a plain copy is cheaper than waking threads
         memcpy(stage.p, src, bytes);
         CUDA_TRY(cudaMemcpyAsync(dst, stage.p, bytes, cudaMemcpyHostToDevice, st));
         return 0;
     }
-    std::vector<std::atomic<unsigned char>> done(np);
-    for (auto& d : done) d.store(0, std::memory_order_relaxed);
-    std::atomic<size_t> next{0};
-    auto worker = [&]() {
-        for (;;) {
-            const size_t i = next.fetch_add(1, std::memory_order_relaxed);
-            if (i >= np) return;
-            const size_t off = i * piece, len = std::min(piece, bytes - off);
-            memcpy((char*)stage.p + off, (const char*)src + off, len);
-            done[i].store(1, std::memory_order_release);
-        }
-    };
     const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-    const size_t nthreads = std::min<size_t>({(size_t)6, (size_t)hw - 1, np});
-    std::vector<std::thread> th;
-    for (size_t t = 0; t < nthreads; t++) th.emplace_back(worker);
-    cudaError_t e = cudaSuccess;
-    for (size_t i = 0; i < np && e == cudaSuccess; i++) {
-        while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
-        const size_t off = i * piece, len = std::min(piece, bytes - off);
-        e = cudaMemcpyAsync((char*)dst + off, (char*)stage.p + off, len, cudaMemcpyHostToDevice, st);
-    }
-    for (auto& t : th) t.join();
+    const size_t nthreads = std::min<size_t>(max_threads, (size_t)hw - 1);
+    const cudaError_t e = pool.run(dst, src, bytes, stage.p, piece, nthreads, st);
     if (e != cudaSuccess) return fail(SAGE_B200_ECUDA, "staged host-to-device copy failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -666,8 +720,11 @@ extern "C" int sage_b200_host_log1pf_exact(void) {
 }
 
 // ------------------------------------------------------------------------------------------------ scorer
+constexpr int MASS_PARTS = 4;   // the masses copy of a chunk is cut into at most this many parts, each followed by its own counting launch
+
 struct ChunkState {
     bool loaded = false;
+    uint32_t nparts = 1, part_lo[MASS_PARTS + 1] = {0, 0, 0, 0, 0};   // spectra [part_lo[p], part_lo[p+1]) belong to part p of the masses copy
     uint32_t n = 0, pmax = 2, zmax = 1, base = 0;
     uint64_t npk = 0;
     size_t nitems = 0, smem = 0, small_bytes = 0;
@@ -686,6 +743,7 @@ struct Lane {
     cudaEvent_t ev[9] = {};   // 0/1 H2D, 6 run start, 2 setup end, 8 counting kernels end, 3 replay end, 4 k_score end, 7/5 D2H
     cudaStream_t copy2 = nullptr;    // (unused: a second H2D stream did not overtake the queued bulk copies, see chunk_upload)
     cudaEvent_t ev_masses = nullptr, ev_intens = nullptr, ev_small = nullptr;
+    cudaEvent_t ev_part[MASS_PARTS] = {};   // masses of the spectra [part_lo[p], part_lo[p+1]) are on the device
     DevBuf d_small, d_masses, d_intens, d_queries, d_hits, d_keys, d_features, d_counts, d_counters, d_dbgk, d_dbgm, d_sort, d_sorttmp, d_wlist, d_wslots,
         d_witems, d_citems, d_nlist, d_nslots;
     PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
@@ -697,7 +755,13 @@ struct Lane {
     sage_b200_feature* fdst = nullptr;
     uint32_t* cdst = nullptr;
     bool f_pinned = false, c_pinned = false;
+    // helper thread staging the intensities of a chunk whose caller arrays are pageable (chunk_upload starts it, chunk_run joins it)
+    std::thread stager;
+    std::unique_ptr<StagePool> pool{new StagePool};   // copy threads of staged_h2d (started by the first pageable chunk)
+    int stager_rc = 0;
+    char stager_msg[256] = {0};
     void release() {
+        if (stager.joinable()) stager.join();
         for (DevBuf* b : {&d_small, &d_masses, &d_intens, &d_queries, &d_hits, &d_keys, &d_features, &d_counts, &d_counters, &d_dbgk, &d_dbgm, &d_sort, &d_sorttmp,
                           &d_wlist, &d_wslots, &d_witems, &d_citems, &d_nlist, &d_nslots, &d_frags}) b->release();
         for (PinBuf* b : {&h_small, &h_masses, &h_intens, &h_features, &h_counts, &h_counters}) b->release();
@@ -705,6 +769,7 @@ struct Lane {
         if (ev_masses) cudaEventDestroy(ev_masses);
         if (ev_intens) cudaEventDestroy(ev_intens);
         if (ev_small) cudaEventDestroy(ev_small);
+        for (auto& e : ev_part) if (e) cudaEventDestroy(e);
         if (copy2) cudaStreamDestroy(copy2);
         if (stream) cudaStreamDestroy(stream);
         if (copy) cudaStreamDestroy(copy);
@@ -728,6 +793,7 @@ struct sage_b200_scorer {
     // learned work-list sizes (per spectrum of a chunk): narrow key-list arena entries and open-search queries. A chunk that needs more than
     // its capacity is re-run once with the exact sizes it counted, and the estimates grow.
     double nlist_per_spectrum = 512.0, wide_per_spectrum = 0.0;
+    int mass_parts = 2;        // measured on cfg2 (e2e ms per 50k-spectrum call): see chunk_upload
     int first_chunk_pct = 0;   // measured on cfg2 (e2e ms per 50k-spectrum call): 0 -> 3.44, 10 -> 3.46, 20 -> 3.52, 35 -> 3.53 (profiles/r02_e_*)
     // SAGE_B200_TRACE=1: per-chunk device timeline (ms since the start of the call) on stderr
     bool trace = false;
@@ -795,10 +861,12 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
         CUDA_TRY(cudaEventCreate(&L.ev_masses));
         CUDA_TRY(cudaEventCreate(&L.ev_intens));
         CUDA_TRY(cudaEventCreate(&L.ev_small));
+        for (auto& e : L.ev_part) CUDA_TRY(cudaEventCreate(&e));
         CUDA_TRY(cudaStreamCreateWithFlags(&L.copy2, cudaStreamNonBlocking));
     }
     if (const char* e = getenv("SAGE_B200_PIPELINE_CHUNKS")) s->pipeline_chunks = std::max(1, atoi(e));
     if (const char* e = getenv("SAGE_B200_TRACE")) s->trace = e[0] == '1';
+    if (const char* e = getenv("SAGE_B200_MASS_PARTS")) s->mass_parts = std::min(MASS_PARTS, std::max(1, atoi(e)));
     if (const char* e = getenv("SAGE_B200_FIRST_CHUNK_PCT")) s->first_chunk_pct = std::min(50, std::max(0, atoi(e)));
     CUDA_TRY(cudaEventCreate(&s->ev_base));
     *out = s;
@@ -855,6 +923,14 @@ extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Waits for the lane's staging thread (if one is running) and reports its error as this thread's.
+static int lane_join_stager(Lane& L) {
+    if (!L.stager.joinable()) return 0;
+    L.stager.join();
+    if (L.stager_rc) return fail(L.stager_rc, "%s", L.stager_msg);
+    return 0;
+}
+
 // ---- one chunk of spectra through the device pipeline, in three phases:
 //   chunk_upload   pack + H2D (spectra become device-resident)
 //   chunk_run      k_setup_queries -> k_prelim_{narrow,wide} -> k_score (results stay on the device)
@@ -883,17 +959,27 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
     if ((rc = L.d_small.reserve(C.small_bytes))) return rc;
     if ((rc = L.d_masses.reserve(4 * npk + 16))) return rc;
     if ((rc = L.d_intens.reserve(4 * npk + 16))) return rc;
-    // The peak masses (half of the H2D bytes) go first and need no host preparation: their copy is in flight while the per-spectrum
-    // arrays are validated and packed below.
+    // Copy order on the lane's copy stream (one DMA queue, served in issue order):
+    //   pinned caller arrays:   first quarter of the peak masses (needs no host preparation; in flight while the per-spectrum arrays are
+    //                           validated and packed) -> per-spectrum blob -> rest of the masses -> intensities.  k_setup_queries + the
+    //                           precursor sort need only the blob, so they run under the rest of the masses copy instead of after it.
+    //   pageable caller arrays: blob first (the host, not the link, is the bottleneck: nothing is lost by packing before the first DMA),
+    //                           then the masses through the staging buffer, then the intensities staged by a helper thread while this
+    //                           thread already queues the kernels (chunk_run joins it before k_score is queued).
     cudaStream_t cp = L.copy;
+    if ((rc = lane_join_stager(L))) return rc;
     CUDA_TRY(cudaEventRecord(L.ev[0], cp));
     const float* src_m = sp->masses + pk0;
     const float* src_i = sp->intensities + pk0;
     const bool pin_m = npk == 0 || is_pinned(src_m), pin_i = npk == 0 || is_pinned(src_i);
-    if (npk) {
-        if (pin_m) CUDA_TRY(cudaMemcpyAsync(L.d_masses.p, src_m, 4 * npk, cudaMemcpyHostToDevice, cp));
-        else if ((rc = staged_h2d(L.d_masses.p, src_m, 4 * npk, L.h_masses, cp))) return rc;   // pageable caller memory: staged + overlapped
-    }
+    // Pinned masses are also cut into `nparts` runs of spectra (caller order), each followed by its own event: the counting kernel is queued
+    // once per part and starts on part p while part p + 1 is still in flight (it walks its spectra in precursor order either way).
+    C.nparts = (pin_m && npk > (1u << 21) && n >= 4096) ? (uint32_t)S->mass_parts : 1u;
+    for (uint32_t q = 0; q <= C.nparts; q++) C.part_lo[q] = (uint32_t)((uint64_t)n * q / C.nparts);
+    auto part_off = [&](uint32_t q) -> uint64_t { return sp->peak_offsets[c0 + C.part_lo[q]] - pk0; };
+    // floats of the masses sent ahead of the blob: half of part 0 (a quarter of everything when there is one part)
+    const uint64_t npk_a = !pin_m ? 0 : (npk > (1u << 21) ? (C.nparts > 1 ? part_off(1) / 2 : npk / 4) : npk);
+    if (npk_a) CUDA_TRY(cudaMemcpyAsync(L.d_masses.p, src_m, 4 * npk_a, cudaMemcpyHostToDevice, cp));
     unsigned char* hs = (unsigned char*)L.h_small.p;
     auto pack = [&]() -> int {   // small per-spectrum arrays -> one pinned blob -> one H2D
         uint32_t* h_off = (uint32_t*)(hs + C.o_off);
@@ -940,18 +1026,44 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
         cudaStreamSynchronize(cp);   // the masses copy may still be reading the caller's array
         return rc;
     }
-    // The small blob follows the masses on the SAME stream. Measured (profiles/r02_final_trace_cfg2.txt): on a second stream it is not served
-    // by a second copy engine ahead of the queued bulk copies — it landed after BOTH of them (1.5 ms instead of 0.73 ms) and the whole
-    // pipeline started 0.75 ms later (e2e 3.48 -> 4.06 ms); k_setup_queries + sort (0.17 ms) therefore still start when the masses land.
+    // The blob travels on the SAME stream as the bulk copies. Measured (profiles/r02_final_trace_cfg2.txt): on a second stream it is not served
+    // by a second copy engine ahead of the queued bulk copies — it landed after BOTH of them and the whole pipeline started 0.75 ms later.
     CUDA_TRY(cudaMemcpyAsync(L.d_small.p, hs, C.small_bytes, cudaMemcpyHostToDevice, cp));
     CUDA_TRY(cudaEventRecord(L.ev_small, cp));
-    CUDA_TRY(cudaEventRecord(L.ev_masses, cp));   // preliminary scoring can start: it never reads intensities
-    if (npk) {
-        if (pin_i) CUDA_TRY(cudaMemcpyAsync(L.d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, cp));
-        else if ((rc = staged_h2d(L.d_intens.p, src_i, 4 * npk, L.h_intens, cp))) { cudaStreamSynchronize(cp); return rc; }
+    if (!pin_m) {
+        if (npk && (rc = staged_h2d(L.d_masses.p, src_m, 4 * npk, L.h_masses, *L.pool, cp))) { cudaStreamSynchronize(cp); return rc; }   // pageable caller memory: staged + overlapped
+        CUDA_TRY(cudaEventRecord(L.ev_part[0], cp));
+    } else {
+        uint64_t sent = npk_a;
+        for (uint32_t q = 0; q < C.nparts; q++) {
+            const uint64_t end = q + 1 == C.nparts ? npk : part_off(q + 1);
+            if (end > sent) {
+                CUDA_TRY(cudaMemcpyAsync(L.d_masses.as<float>() + sent, src_m + sent, 4 * (end - sent), cudaMemcpyHostToDevice, cp));
+                sent = end;
+            }
+            CUDA_TRY(cudaEventRecord(L.ev_part[q], cp));
+        }
     }
-    CUDA_TRY(cudaEventRecord(L.ev_intens, cp));
-    CUDA_TRY(cudaEventRecord(L.ev[1], cp));
+    CUDA_TRY(cudaEventRecord(L.ev_masses, cp));   // preliminary scoring can start: it never reads intensities
+    if (npk && !pin_i) {
+        if ((rc = L.h_intens.reserve(4 * npk))) { cudaStreamSynchronize(cp); return rc; }
+        L.stager_rc = 0;
+        L.stager_msg[0] = 0;
+        const int device = S->device;
+        void* dst = L.d_intens.p;
+        Lane* lane = &L;
+        L.stager = std::thread([lane, device, dst, src_i, npk, cp]() {
+            cudaSetDevice(device);
+            int r = staged_h2d(dst, src_i, 4 * npk, lane->h_intens, *lane->pool, cp);
+            if (r == 0 && (cudaEventRecord(lane->ev_intens, cp) != cudaSuccess || cudaEventRecord(lane->ev[1], cp) != cudaSuccess)) r = fail(SAGE_B200_ECUDA, "event record failed after the staged copy");
+            if (r) snprintf(lane->stager_msg, sizeof lane->stager_msg, "%s", g_last_error.c_str());
+            lane->stager_rc = r;
+        });
+    } else {
+        if (npk) CUDA_TRY(cudaMemcpyAsync(L.d_intens.p, src_i, 4 * npk, cudaMemcpyHostToDevice, cp));
+        CUDA_TRY(cudaEventRecord(L.ev_intens, cp));
+        CUDA_TRY(cudaEventRecord(L.ev[1], cp));
+    }
     S->last.h2d_bytes += C.small_bytes + 8 * npk;
     C.loaded = true;
     C.force_nlist = C.force_wide = 0;
@@ -1017,11 +1129,13 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     uint32_t *sk_in = nullptr, *sk_out = nullptr, *sv_in = nullptr, *sv_out = nullptr;
     int sort_bits = 1;   // keys are PeptideIx < n_pep (spectra without a query sort last within those bits: the order only matters for locality)
     while (sort_bits < 32 && (db->v.n_pep >> sort_bits)) sort_bits++;
+    // the top 16 bits are enough for that (two 8-bit radix passes instead of three on a 2M-peptide index: windows span hundreds of peptides)
+    const int sort_lo = std::max(0, sort_bits - 16);
     size_t sort_tmp = 0;
     if (S->sort_spectra && n > 1) {  // process spectra in ascending precursor-window order: neighbouring CTAs then touch the same index lines
         if ((rc = L.d_sort.reserve(16 * (size_t)n))) return rc;
         sk_in = L.d_sort.as<uint32_t>(); sk_out = sk_in + n; sv_in = sk_out + n; sv_out = sv_in + n;
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, sort_bits, st));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, sort_lo, sort_bits, st));
         if ((rc = L.d_sorttmp.reserve(sort_tmp + 16))) return rc;
     }
     // Work-list capacities come from what earlier chunks needed (S->nlist_per_spectrum / wide_per_spectrum) or, on a re-run, from the
@@ -1045,17 +1159,23 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     k_setup_queries<<<(n + 127) / 128, 128, 0, st>>>(db->v, svq, bv, sk_in, sv_in);
     CUDA_TRY(cudaGetLastError());
     if (sk_in) {
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(L.d_sorttmp.p, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, 0, sort_bits, st));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(L.d_sorttmp.p, sort_tmp, sk_in, sk_out, sv_in, sv_out, (int)n, sort_lo, sort_bits, st));
         bv.order = sv_out;
     }
     CUDA_TRY(cudaEventRecord(L.ev[2], st));
-    CUDA_TRY(cudaStreamWaitEvent(st, L.ev_masses, 0));   // the counting kernels read the peak masses
+    if (C.nparts <= 1) CUDA_TRY(cudaStreamWaitEvent(st, L.ev_masses, 0));   // the counting kernels read the peak masses
     uint64_t launches = 1;
 
     // ---- preliminary scoring. Both kernels are always queued: CTAs whose query belongs to the other kernel (or to nobody) exit at once.
     const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
-    k_prelim_narrow_warp<<<dim3((n + WARPQ_WARPS - 1) / WARPQ_WARPS, sv.qmax), WARPQ_WARPS * 32, 0, st>>>(db->v, svq, bv, L.d_nlist.as<uint64_t>());
-    CUDA_TRY(cudaGetLastError());
+    for (uint32_t q = 0; q < C.nparts; q++) {   // one launch per part of the masses copy (a resident batch has one part)
+        if (C.nparts > 1) CUDA_TRY(cudaStreamWaitEvent(st, L.ev_part[q], 0));
+        k_prelim_narrow_warp<<<dim3((n + WARPQ_WARPS - 1) / WARPQ_WARPS, sv.qmax), WARPQ_WARPS * 32, 0, st>>>(db->v, svq, bv, L.d_nlist.as<uint64_t>(), C.part_lo[q],
+                                                                                                          C.part_lo[q + 1]);
+        CUDA_TRY(cudaGetLastError());
+        launches += q > 0;
+    }
+    if (C.nparts > 1) CUDA_TRY(cudaStreamWaitEvent(st, L.ev_masses, 0));
     k_prelim_narrow<<<(unsigned)std::min<uint64_t>(C.nitems, (uint64_t)db->sm_count * 6), PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>());
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(L.ev[8], st));   // narrow counting kernels done (the open-search kernel, when present, is timed with the replays)
@@ -1082,6 +1202,7 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     CUDA_TRY(cudaEventRecord(L.ev[3], st));
 
     // ---- candidate scoring + feature assembly (first reader of the intensities)
+    if ((rc = lane_join_stager(L))) return rc;   // ev_intens is recorded by the staging thread of a pageable chunk
     CUDA_TRY(cudaStreamWaitEvent(st, L.ev_intens, 0));
     k_score<<<n, SCORE_THREADS, C.smem, st>>>(db->v, sv, bv, L.d_features.as<FeatureOut>(), L.d_counts.as<uint32_t>(), C.pmax,
                                              dbg ? L.d_dbgk.as<uint64_t>() : nullptr, dbg ? L.d_dbgm.as<uint32_t>() : nullptr,
@@ -1136,6 +1257,7 @@ static uint64_t wide_max_chunk(double wide_per_spectrum, uint64_t otherwise) {
 static int lane_finish(sage_b200_scorer* S, Lane& L) {
     ChunkState& C = L.chunk;
     if (!C.loaded) return 0;
+    { const int jrc = lane_join_stager(L); if (jrc) return jrc; }
     CUDA_TRY(cudaStreamSynchronize(L.copy));
     CUDA_TRY(cudaStreamSynchronize(L.copy2));
     for (int attempt = 0;; attempt++) {
@@ -1233,6 +1355,7 @@ static int check_spectra(const sage_b200_spectra* sp) {
 static int drain_lanes(sage_b200_scorer* S, int rc) {
     const std::string msg = g_last_error;
     for (Lane& L : S->lanes) {
+        if (L.stager.joinable()) L.stager.join();   // it reads the caller's arrays
         if (L.copy) cudaStreamSynchronize(L.copy);
         if (L.copy2) cudaStreamSynchronize(L.copy2);
         if (L.stream) cudaStreamSynchronize(L.stream);
@@ -1249,6 +1372,7 @@ static int score_batch_chunks(sage_b200_scorer* S, const sage_b200_spectra* sp, 
 extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectra* sp, sage_b200_feature* features, uint32_t* counts,
                                      sage_b200_fragment* fragments, uint64_t fragment_capacity, uint64_t* fragments_used) {
     if (!S) return fail(SAGE_B200_EINVAL, "score_batch: null scorer");
+    const auto t_call = std::chrono::steady_clock::now();
     int rc = check_spectra(sp);
     if (rc) return rc;
     if (sp->n && (!features || !counts)) return fail(SAGE_B200_EINVAL, "score_batch: null output");
@@ -1281,6 +1405,7 @@ extern "C" int sage_b200_score_batch(sage_b200_scorer* S, const sage_b200_spectr
     }
     if (rc) return drain_lanes(S, rc);
     finish_counters(S);
+    S->last.ms_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_call).count();
     if (annotate) {
         *fragments_used = S->frag_used;
         S->frag_dst = nullptr;
@@ -1496,7 +1621,10 @@ extern "C" int sage_b200_batch_upload(sage_b200_scorer* S, const sage_b200_spect
     S->last = sage_b200_counters{};
     Lane& L = S->lanes[0];
     if ((rc = chunk_upload(S, L, sp, 0, sp->n))) return rc;
-    return lane_finish(S, L);
+    if ((rc = lane_finish(S, L))) return rc;
+    L.chunk.nparts = 1;   // everything is resident: batch_run queues one counting launch
+    L.chunk.part_lo[1] = L.chunk.n;
+    return 0;
 }
 extern "C" int sage_b200_batch_run(sage_b200_scorer* S) {
     if (!S) return fail(SAGE_B200_EINVAL, "batch_run: null scorer");
@@ -1741,3 +1869,12 @@ extern "C" size_t sage_b200_last_error(char* buf, size_t cap) {
     }
     return g_last_error.size();
 }
+
+#if SAGE_B200_PHASE_CLOCKS
+// variant builds only (not declared in the header): cycles per k_score phase summed over CTAs since the last reset
+extern "C" int sage_b200_debug_phase_cycles(unsigned long long* out16, int reset) {
+    if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_phase, sizeof(unsigned long long) * 16));
+    if (reset) { unsigned long long z[16] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_phase, z, sizeof z)); }
+    return 0;
+}
+#endif

@@ -69,11 +69,12 @@ def main():
     srcs = {}
     def text(f, n):
         if f not in srcs:
-            p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "sage_b200", "csrc", f)
+            p = os.path.join(os.environ.get("SAGE_B200_SRC_DIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "sage_b200", "csrc"), f)
             srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []
         return srcs[f][n - 1].strip()[:110] if 0 < n <= len(srcs[f]) else ""
     print(f"# {kernel}: total warp inst {tot_i:.0f} samples {tot_s:.0f} thread-eff {tot_t / max(tot_i, 1):.2f}")
-    for line, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    by = 2 if os.environ.get("SORT_BY_STALL") else 0   # SORT_BY_STALL=1: rank lines by stall samples instead of executed instructions
+    for line, a in sorted(agg.items(), key=lambda kv: -kv[1][by])[:top]:
         print(f"{line[0][:14]:14s}:{line[1]:4d} inst {100 * a[0] / tot_i:5.1f}% stall {100 * a[2] / max(tot_s, 1):5.1f}% eff {a[1] / max(a[0], 1):4.1f} | {text(*line)}")
 
 
