@@ -327,6 +327,72 @@ __device__ __forceinline__ void index_probe(const DbView& db, const QueryDesc& q
     }
 }
 
+// The same probe against the NARROW BLOCK INDEX (a second copy of the fragments: blocks of `nv.block` consecutive PeptideIx, ascending m/z inside
+// a block, one m/z LUT per block — the open-search layout with small blocks). A precursor window of a few hundred peptides lies in one or two
+// blocks, so a probe is: LUT cell of `flo` (one cell early: float rounding) -> walk the block's entries until m/z > fhi, counting those inside
+// [flo, fhi] whose PeptideIx is in the window. Same matched set as index_probe by construction (every index entry with PeptideIx in the window
+// lies in these blocks); two dependent loads before the walk instead of five, no page loop, no bisection.
+//
+// One warp = 32 probes of one query. Most walks are one or two entries, but a peak at a fragment mass that MANY peptides share (y1 of K / R, b2
+// of frequent dipeptides) matches a run of up to a few hundred entries: walked by its own lane that run set the trip count of the whole warp
+// (CPU statistics of cfg2: mean 3.5 loads per probe, mean of the per-warp maximum 24). So a lane walks at most WALK_SOLO entries alone; runs
+// still open after that are finished by the whole warp, 32 consecutive entries per step (coalesced 256-byte reads). Counting kernel on cfg2 (ms):
+// every lane walks alone 0.546 | WALK_SOLO 2 0.698 | 4 0.588 | 8 0.494 | 16 0.500 | 32 0.520; finishing four runs at a time with 8-lane groups
+// 0.52-0.53 at WALK_SOLO 4-12 (each cooperative step costs a full memory latency, so only the genuinely long runs should get there).
+// The reference's page / entry work counters are not produced on this path (sage_b200.cu: option "narrow_index"). Measured and dropped: fetching a
+// 32-byte sector (4 entries) per step — counting kernel 0.634 ms instead of 0.546.
+#ifndef SAGE_B200_WALK_SOLO
+#define SAGE_B200_WALK_SOLO 8
+#endif
+constexpr uint32_t WALK_SOLO = SAGE_B200_WALK_SOLO;
+__device__ __forceinline__ void block_probe_warp(const WideIndexView& nv, const QueryDesc& q, uint32_t b0, uint32_t b1, bool act, float flo, float fhi,
+                                                 uint32_t* cnt32, uint32_t& matched) {
+    const uint32_t lane = threadIdx.x & 31;
+    const float tt = (flo - nv.base) * nv.inv_w;
+    const int c = tt > 1.0f ? (int)fminf(tt, (float)(nv.cells - 1)) - 1 : 0;
+    for (uint32_t blk = b0; blk <= b1; blk++) {   // warp-uniform: b0, b1 belong to the query
+        const uint64_t base = __ldg(nv.blk_off + blk);
+        const uint32_t cnt = (uint32_t)(__ldg(nv.blk_off + blk + 1) - base);
+        const uint2* fr = nv.frag + base;
+        uint32_t e = cnt;
+        if (act) {
+            e = __ldg(nv.lut + (size_t)blk * (nv.cells + 1) + c);
+            for (uint32_t k = 0; k < WALK_SOLO && e < cnt; k++, e++) {
+                const uint2 f = __ldg(fr + e);
+                const float fmz = __uint_as_float(f.y);
+                if (fmz > fhi) { e = cnt; break; }
+                if (fmz >= flo && f.x >= q.eff_lo && f.x <= q.eff_hi) {
+                    const uint32_t idx = f.x - q.pre_lo;
+                    atomicAdd(&cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                    matched++;
+                }
+            }
+        }
+        uint32_t pend = __ballot_sync(0xffffffffu, e < cnt);   // runs still open
+        while (pend) {
+            const int src = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const uint32_t e0 = __shfl_sync(0xffffffffu, e, src);
+            const float lo_s = __shfl_sync(0xffffffffu, flo, src), hi_s = __shfl_sync(0xffffffffu, fhi, src);
+            for (uint32_t pos = e0; pos < cnt; pos += 32) {
+                const uint32_t i = pos + lane;
+                bool stop = i >= cnt;
+                if (!stop) {
+                    const uint2 f = __ldg(fr + i);
+                    const float fmz = __uint_as_float(f.y);
+                    stop = fmz > hi_s;
+                    if (!stop && fmz >= lo_s && f.x >= q.eff_lo && f.x <= q.eff_hi) {
+                        const uint32_t idx = f.x - q.pre_lo;
+                        atomicAdd(&cnt32[idx >> 1], 1u << ((idx & 1) * 16));
+                        matched++;   // counted on the lane that saw the entry: the warp sums `matched` afterwards
+                    }
+                }
+                if (__any_sync(0xffffffffu, stop)) break;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------- preliminary scoring, narrow
 // One CTA per (spectrum, query); the dense per-window counts live in shared memory. Two interchangeable ways to fill them
 // (identical counts: the matched set is {fragment in index : mz in [flo,fhi](peak*charge), PeptideIx in [eff_lo,eff_hi]}):
@@ -547,8 +613,9 @@ __global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, Sco
 // counts of the window live in the warp's slice of shared memory, sums are warp shuffles, and the ordered key list for k_replay
 // is emitted with ballots. grid = (ceil(n / WARPQ_WARPS) in precursor order, query slot): slot-major, so CTAs of slots no spectrum uses
 // (e.g. the charge fold of known-charge spectra) sit at the end of the grid and leave after one cached load.
+template <bool BLK>
 __global__ void __launch_bounds__(WARPQ_WARPS * 32, WARPQ_MIN_CTAS) k_prelim_narrow_warp(DbView db, ScorerView sc, BatchView b, uint64_t* nlist, uint32_t s_lo,
-                                                                                                uint32_t s_hi) {
+                                                                                                uint32_t s_hi, WideIndexView nv) {
     __shared__ uint32_t cnt_all[WARPQ_WARPS][WARPQ_CAP / 2];
     if (b.counters[C_COUNT + blockIdx.y] == 0ull) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -573,12 +640,18 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32, WARPQ_MIN_CTAS) k_prelim_nar
     const uint32_t p0 = b.peak_off[s], np = b.peak_off[s + 1] - p0;
     const uint32_t nfc = q.nfc, ntask = np * nfc;
     uint32_t matched = 0, pages = 0, entries = 0;
-    for (uint32_t t = lane; t < ntask; t += 32) {
-        const uint32_t p = t / nfc, fc = t - p * nfc + 1;
-        const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
-        float flo, fhi;
-        tol_bounds(sc.fragment_tol, mass, flo, fhi);
-        index_probe(db, q, flo, fhi, cnt32, matched, pages, entries);
+    const uint32_t blk0 = BLK ? q.pre_lo / nv.block : 0u, blk1 = BLK ? min(q.pre_hi, db.n_pep - 1) / nv.block : 0u;
+    for (uint32_t t0 = 0; t0 < ntask; t0 += 32) {   // warp-uniform trip count: the block path finishes long runs cooperatively
+        const uint32_t t = t0 + lane;
+        const bool act = t < ntask;
+        float flo = 0.0f, fhi = 0.0f;
+        if (act) {
+            const uint32_t p = t / nfc, fc = t - p * nfc + 1;
+            const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
+            tol_bounds(sc.fragment_tol, mass, flo, fhi);
+        }
+        if (BLK) block_probe_warp(nv, q, blk0, blk1, act, flo, fhi, cnt32, matched);
+        else if (act) index_probe(db, q, flo, fhi, cnt32, matched, pages, entries);
     }
     for (int o = 16; o > 0; o >>= 1) {
         matched += __shfl_xor_sync(0xffffffffu, matched, o);
@@ -2488,6 +2561,16 @@ __global__ void k_wide_block_offsets(uint64_t n_frag, const uint64_t* key64, uin
     const uint64_t want = (uint64_t)b << 32;
     while (lo < hi) { const uint64_t m = (lo + hi) >> 1; if (key64[m] < want) lo = m + 1; else hi = m; }
     blk_off[b] = lo;
+}
+// rng[0] = min, rng[1] = max of the m/z bit patterns (fragment m/z are positive floats: bit order == value order)
+__global__ void k_frag_mz_range(uint64_t n_frag, const uint2* frag, uint32_t* rng) {
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_frag; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = frag[i].y;
+        lo = min(lo, y); hi = max(hi, y);
+    }
+    for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(rng, lo); atomicMax(rng + 1, hi); }
 }
 __global__ void k_wide_lut(WideIndexView w, uint32_t* lut) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -201,6 +201,18 @@ static bool is_pinned(const void* p) {
 }
 
 // ------------------------------------------------------------------------------------------------ db
+struct BlockIndexSlot {
+    WideIndexView v{};
+    void *d_frag = nullptr, *d_blk = nullptr, *d_lut = nullptr;
+    int failed = 0;
+    uint64_t bytes = 0;
+    void release() {
+        for (void** p : {&d_frag, &d_blk, &d_lut}) { if (*p) cudaFree(*p); *p = nullptr; }
+        v = WideIndexView{};
+        bytes = 0;
+    }
+};
+
 struct sage_b200_db {
     int device = 0;
     DbView v{};
@@ -209,12 +221,10 @@ struct sage_b200_db {
          *d_pep_flags = nullptr, *d_pep_missed = nullptr;
     uint64_t total_residues = 0, device_bytes = 0;
     int sm_count = 148;
-    // secondary index for open search (WideIndexView), built lazily by the first scorer that meets a wide window; guarded by wmu
+    // secondary copies of the fragments in peptide-block-major order (WideIndexView), built lazily and guarded by wmu: `wide` (blocks = the
+    // open-search count tile, built by the first scorer that meets a wide window) and `narrow` (small blocks, built by the first narrow chunk)
     mutable std::mutex wmu;
-    mutable WideIndexView wv{};
-    mutable void *d_wfrag = nullptr, *d_wblk = nullptr, *d_wlut = nullptr;
-    mutable int wide_failed = 0;
-    mutable uint64_t wide_bytes = 0;
+    mutable BlockIndexSlot wide, narrow;
 };
 
 static int dmalloc(sage_b200_db* db, void** p, size_t bytes) {
@@ -332,7 +342,9 @@ extern "C" int sage_b200_device_count(void) {
 extern "C" void sage_b200_db_destroy(sage_b200_db* db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    void* ps[] = {db->d_wfrag, db->d_wblk, db->d_wlut, db->d_page_grid, db->d_bucket_lut, db->d_pep_lut, db->d_frag, db->d_bucket_min, db->d_pep_mono, db->d_ion_off, db->d_ions, db->d_pep_len, db->d_pep_flags, db->d_pep_missed};
+    db->wide.release();
+    db->narrow.release();
+    void* ps[] = {db->d_page_grid, db->d_bucket_lut, db->d_pep_lut, db->d_frag, db->d_bucket_min, db->d_pep_mono, db->d_ion_off, db->d_ions, db->d_pep_len, db->d_pep_flags, db->d_pep_missed};
     for (void* p : ps)
         if (p) cudaFree(p);
     delete db;
@@ -575,29 +587,24 @@ extern "C" int sage_b200_db_export_index(const sage_b200_db* db, uint32_t* fragm
 // Secondary index for open search (device_common.cuh: WideIndexView): fragments keyed by (PeptideIx / block, m/z), one LSD radix sort, block
 // offsets and a per-block m/z LUT. `block` = the scorer's count-tile size. Returns a view with frag == nullptr when the index cannot be built
 // (out of memory, SAGE_B200_NO_WIDE_INDEX=1): k_prelim_wide then streams the page slices as the reference does.
-static WideIndexView db_wide_index(const sage_b200_db* db, uint32_t block) {
-    std::lock_guard<std::mutex> lock(db->wmu);
+// Builds (or returns) one block-major copy of the fragments. `cells_for(entries per block)` picks the LUT resolution; wmu must be held.
+static WideIndexView build_block_index(const sage_b200_db* db, BlockIndexSlot& slot, uint32_t block, uint32_t cells) {
     WideIndexView none{};
-    if (const char* e = getenv("SAGE_B200_NO_WIDE_INDEX")) if (e[0] == '1') return none;   // A/B + tests: stream the page slices instead
-    if (db->wv.frag != nullptr && db->wv.block == block) return db->wv;
-    if (db->wide_failed || block == 0 || db->v.n_frag == 0 || db->v.n_pep == 0) return none;
+    if (slot.v.frag != nullptr && slot.v.block == block) return slot.v;
+    if (slot.failed || block == 0 || db->v.n_frag == 0 || db->v.n_pep == 0) return none;
     const uint64_t nf = db->v.n_frag;
     cudaDeviceSynchronize();   // a rebuild with another block size (tests) must not free arrays a kernel still reads
-    for (void** p : {&db->d_wfrag, &db->d_wblk, &db->d_wlut}) { if (*p) cudaFree(*p); *p = nullptr; }
-    db->wv = WideIndexView{};
-    void *k_a = nullptr, *k_b = nullptr, *p_a = nullptr, *p_b = nullptr, *tmp = nullptr;
-    auto cleanup = [&]() { for (void* p : {k_a, k_b, p_a, p_b, tmp}) if (p) cudaFree(p); };
-    auto give_up = [&]() { cleanup(); for (void** p : {&db->d_wfrag, &db->d_wblk, &db->d_wlut}) { if (*p) cudaFree(*p); *p = nullptr; } cudaGetLastError(); db->wide_failed = 1; return WideIndexView{}; };
+    slot.release();
+    void *k_a = nullptr, *k_b = nullptr, *p_a = nullptr, *p_b = nullptr, *tmp = nullptr, *d_rng = nullptr;
+    auto cleanup = [&]() { for (void* p : {k_a, k_b, p_a, p_b, tmp, d_rng}) if (p) cudaFree(p); };
+    auto give_up = [&]() { cleanup(); slot.release(); cudaGetLastError(); slot.failed = 1; return WideIndexView{}; };
     const uint32_t n_block = (db->v.n_pep + block - 1) / block;
-    // ~2 M entries per 80 k-peptide block, most of them inside a third of the m/z range: 2^18 cells leave a few dozen entries per cell there,
-    // so the conservative (one cell early) start of a walk costs about one extra 32-entry fetch (measured: 2^16 cells -> ~8 extra fetches)
-    uint32_t cells = 1u << 18;
-    while (cells > 256 && (uint64_t)n_block * (cells + 1) * 4 > (1024ull << 20)) cells >>= 1;
-    if (cudaMalloc(&db->d_wfrag, 8 * nf + 64) != cudaSuccess || cudaMalloc(&db->d_wblk, 8 * ((size_t)n_block + 1)) != cudaSuccess ||
-        cudaMalloc(&db->d_wlut, 4 * (size_t)n_block * (cells + 1)) != cudaSuccess)
+    while (cells > 256 && (uint64_t)n_block * (cells + 1) * 4 > (1024ull << 20)) cells >>= 1;   // at most 1 GB of LUT
+    if (cudaMalloc(&slot.d_frag, 8 * nf + 64) != cudaSuccess || cudaMalloc(&slot.d_blk, 8 * ((size_t)n_block + 1)) != cudaSuccess ||
+        cudaMalloc(&slot.d_lut, 4 * (size_t)n_block * (cells + 1)) != cudaSuccess)
         return give_up();
     if (cudaMalloc(&k_a, 8 * nf) != cudaSuccess || cudaMalloc(&k_b, 8 * nf) != cudaSuccess || cudaMalloc(&p_a, 4 * nf) != cudaSuccess ||
-        cudaMalloc(&p_b, 4 * nf) != cudaSuccess)
+        cudaMalloc(&p_b, 4 * nf) != cudaSuccess || cudaMalloc(&d_rng, 8) != cudaSuccess)
         return give_up();
     k_wide_keys<<<(unsigned)((nf + 255) / 256), 256>>>(nf, db->v.frag, block, (uint64_t*)k_a, (uint32_t*)p_a);
     int nb_bits = 1;
@@ -608,39 +615,50 @@ static WideIndexView db_wide_index(const sage_b200_db* db, uint32_t block) {
         cudaMalloc(&tmp, tb + 16) != cudaSuccess ||
         cub::DeviceRadixSort::SortPairs(tmp, tb, (const uint64_t*)k_a, (uint64_t*)k_b, (const uint32_t*)p_a, (uint32_t*)p_b, (int)nf, 0, 32 + nb_bits) != cudaSuccess)
         return give_up();
-    k_wide_pack<<<(unsigned)((nf + 255) / 256), 256>>>(nf, (const uint64_t*)k_b, (const uint32_t*)p_b, (uint2*)db->d_wfrag);
-    k_wide_block_offsets<<<(n_block + 1 + 255) / 256, 256>>>(nf, (const uint64_t*)k_b, n_block, (uint64_t*)db->d_wblk);
-    if (cudaDeviceSynchronize() != cudaSuccess) return give_up();
+    k_wide_pack<<<(unsigned)((nf + 255) / 256), 256>>>(nf, (const uint64_t*)k_b, (const uint32_t*)p_b, (uint2*)slot.d_frag);
+    k_wide_block_offsets<<<(n_block + 1 + 255) / 256, 256>>>(nf, (const uint64_t*)k_b, n_block, (uint64_t*)slot.d_blk);
+    // m/z range of the index (positive floats order like their bit patterns)
+    const uint32_t rng0[2] = {0xFFFFFFFFu, 0u};
+    if (cudaMemcpy(d_rng, rng0, 8, cudaMemcpyHostToDevice) != cudaSuccess) return give_up();
+    k_frag_mz_range<<<(unsigned)std::min<uint64_t>((nf + 255) / 256, 4096), 256>>>(nf, db->v.frag, (uint32_t*)d_rng);
+    uint32_t rng[2];
+    if (cudaMemcpy(rng, d_rng, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return give_up();
     cleanup();
-    k_a = k_b = p_a = p_b = tmp = nullptr;
-    // m/z range of the index: smallest = first bucket minimum, largest = the largest last entry of any block
-    std::vector<uint64_t> off(n_block + 1);
-    if (cudaMemcpy(off.data(), db->d_wblk, 8 * ((size_t)n_block + 1), cudaMemcpyDeviceToHost) != cudaSuccess) return give_up();
-    float lo = INFINITY, hi = -INFINITY;
-    for (uint32_t bI = 0; bI < n_block; bI++) {
-        if (off[bI + 1] == off[bI]) continue;
-        uint2 first, last;
-        if (cudaMemcpy(&first, (const uint2*)db->d_wfrag + off[bI], 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-            cudaMemcpy(&last, (const uint2*)db->d_wfrag + off[bI + 1] - 1, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
-            return give_up();
-        float a, z;
-        memcpy(&a, &first.y, 4); memcpy(&z, &last.y, 4);
-        lo = std::min(lo, a); hi = std::max(hi, z);
-    }
+    k_a = k_b = p_a = p_b = tmp = d_rng = nullptr;
+    float lo, hi;
+    memcpy(&lo, &rng[0], 4); memcpy(&hi, &rng[1], 4);
     WideIndexView w{};
-    w.frag = (const uint2*)db->d_wfrag; w.blk_off = (const uint64_t*)db->d_wblk; w.lut = (const uint32_t*)db->d_wlut;
+    w.frag = (const uint2*)slot.d_frag; w.blk_off = (const uint64_t*)slot.d_blk; w.lut = (const uint32_t*)slot.d_lut;
     w.block = block; w.n_block = n_block; w.cells = cells;
     const float width = (hi - lo) / (float)cells;
-    w.base = std::isfinite(lo) ? lo : 0.0f;
-    w.inv_w = (std::isfinite(width) && width > 0.0f) ? 1.0f / width : 0.0f;
+    w.base = (std::isfinite(lo) && lo > 0.0f) ? lo : 0.0f;
+    w.inv_w = (std::isfinite(width) && width > 0.0f && lo > 0.0f) ? 1.0f / width : 0.0f;
     if (w.inv_w > 0.0f) {
         const uint64_t total = (uint64_t)n_block * (cells + 1);
-        k_wide_lut<<<(unsigned)((total + 255) / 256), 256>>>(w, (uint32_t*)db->d_wlut);
-    } else if (cudaMemset(db->d_wlut, 0, 4 * (size_t)n_block * (cells + 1)) != cudaSuccess) return give_up();   // degenerate range: every walk starts at the block start
+        k_wide_lut<<<(unsigned)((total + 255) / 256), 256>>>(w, (uint32_t*)slot.d_lut);
+    } else if (cudaMemset(slot.d_lut, 0, 4 * (size_t)n_block * (cells + 1)) != cudaSuccess) return give_up();   // degenerate range: every walk starts at the block start
     if (cudaDeviceSynchronize() != cudaSuccess) return give_up();
-    db->wv = w;
-    db->wide_bytes = 8 * nf + 8 * ((uint64_t)n_block + 1) + 4ull * n_block * (cells + 1);
+    slot.v = w;
+    slot.bytes = 8 * nf + 8 * ((uint64_t)n_block + 1) + 4ull * n_block * (cells + 1);
     return w;
+}
+
+static WideIndexView db_wide_index(const sage_b200_db* db, uint32_t block) {
+    std::lock_guard<std::mutex> lock(db->wmu);
+    if (const char* e = getenv("SAGE_B200_NO_WIDE_INDEX")) if (e[0] == '1') return WideIndexView{};   // A/B + tests: stream the page slices instead
+    // ~2 M entries per 80 k-peptide block, most of them inside a third of the m/z range: 2^18 cells leave a few dozen entries per cell there,
+    // so the conservative (one cell early) start of a walk costs about one extra 32-entry fetch (measured: 2^16 cells -> ~8 extra fetches)
+    return build_block_index(db, db->wide, block, 1u << 18);
+}
+
+// The narrow-search copy: blocks of `block` peptides (a +-20 ppm window holds a few hundred), LUT cells ~ `cells_x` per block entry.
+static WideIndexView db_narrow_index(const sage_b200_db* db, uint32_t block, uint32_t cells_x) {
+    std::lock_guard<std::mutex> lock(db->wmu);
+    const uint32_t n_block = (db->v.n_pep + block - 1) / std::max(block, 1u);
+    const uint64_t per_block = n_block ? db->v.n_frag / n_block : 0;
+    uint32_t cells = 1024;
+    while (cells < (1u << 18) && (uint64_t)cells < per_block * cells_x) cells <<= 1;
+    return build_block_index(db, db->narrow, block, cells);
 }
 
 // Dynamic shared-memory opt-in of the kernels that need more than 48 KB: set ONCE per device to the device maximum (the attribute is per-function,
@@ -793,7 +811,12 @@ struct sage_b200_scorer {
     // learned work-list sizes (per spectrum of a chunk): narrow key-list arena entries and open-search queries. A chunk that needs more than
     // its capacity is re-run once with the exact sizes it counted, and the estimates grow.
     double nlist_per_spectrum = 512.0, wide_per_spectrum = 0.0;
-    int mass_parts = 2;        // measured on cfg2 (e2e ms per 50k-spectrum call): see chunk_upload
+    // narrow windows are counted against the small-block copy of the index (block_probe) unless narrow_index == 0: then the reference's loop
+    // order probes the page index and the page / entry work counters are produced (tests, bench's work_per_step pass)
+    int narrow_index = 1;
+    uint32_t narrow_block = 256, narrow_cells_x = 4;   // measured on cfg2 (counting kernel ms; page index 0.628): 1024 x2 0.736 | 512 x2 0.644 | 1024 x4 0.637 |
+                                                       // 512 x4 0.585 | 256 x2 0.585 | 256 x4 0.546 | 256 x8 0.546 | 128 x4 0.555 (profiles/r02_nblk*)
+    int mass_parts = 2;        // measured on cfg2 (e2e ms per 50k-spectrum call, profiles/r02_parts): 1 part 3.24 | 2 -> 3.17 | 3 -> 3.38 | 4 -> 3.41
     int first_chunk_pct = 0;   // measured on cfg2 (e2e ms per 50k-spectrum call): 0 -> 3.44, 10 -> 3.46, 20 -> 3.52, 35 -> 3.53 (profiles/r02_e_*)
     // SAGE_B200_TRACE=1: per-chunk device timeline (ms since the start of the call) on stderr
     bool trace = false;
@@ -866,6 +889,9 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     }
     if (const char* e = getenv("SAGE_B200_PIPELINE_CHUNKS")) s->pipeline_chunks = std::max(1, atoi(e));
     if (const char* e = getenv("SAGE_B200_TRACE")) s->trace = e[0] == '1';
+    if (const char* e = getenv("SAGE_B200_NARROW_INDEX")) s->narrow_index = atoi(e) != 0;
+    if (const char* e = getenv("SAGE_B200_NARROW_BLOCK")) s->narrow_block = (uint32_t)std::max(64, atoi(e));
+    if (const char* e = getenv("SAGE_B200_NARROW_CELLS_X")) s->narrow_cells_x = (uint32_t)std::max(1, atoi(e));
     if (const char* e = getenv("SAGE_B200_MASS_PARTS")) s->mass_parts = std::min(MASS_PARTS, std::max(1, atoi(e)));
     if (const char* e = getenv("SAGE_B200_FIRST_CHUNK_PCT")) s->first_chunk_pct = std::min(50, std::max(0, atoi(e)));
     CUDA_TRY(cudaEventCreate(&s->ev_base));
@@ -878,6 +904,17 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
     std::lock_guard<std::mutex> lock(s->mu);
     if (!strcmp(name, "sort_spectra")) { s->sort_spectra = value != 0; return 0; }
     if (!strcmp(name, "pipeline_chunks")) { s->pipeline_chunks = (int)std::max<int64_t>(1, value); return 0; }
+    if (!strcmp(name, "narrow_index")) { s->narrow_index = value != 0; return 0; }
+    if (!strcmp(name, "narrow_block")) {   // test hook: peptides per block of the narrow-search copy (rebuilds it on the next batch)
+        if (value < 64 || value > (1 << 20)) return fail(SAGE_B200_EINVAL, "narrow_block must be 64..1048576");
+        s->narrow_block = (uint32_t)value;
+        return 0;
+    }
+    if (!strcmp(name, "mass_parts")) {
+        if (value < 1 || value > MASS_PARTS) return fail(SAGE_B200_EINVAL, "mass_parts must be 1..%d", MASS_PARTS);
+        s->mass_parts = (int)value;
+        return 0;
+    }
     if (!strcmp(name, "wide_lmax")) {  // test hook: a tiny survivor list forces the overflow -> in-kernel serial replay path
         if (value < (int64_t)K_MAX || value > (int64_t)WIDE_LMAX) return fail(SAGE_B200_EINVAL, "wide_lmax must be in %d..%u", K_MAX, WIDE_LMAX);
         s->sv.wide_lmax = (uint32_t)value;
@@ -1168,10 +1205,16 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
 
     // ---- preliminary scoring. Both kernels are always queued: CTAs whose query belongs to the other kernel (or to nobody) exit at once.
     const size_t rsm = (size_t)sv.kparam * REPLAY_THREADS * 8;
+    // the small-block copy of the index: built on first use; never for wide-window (DIA) scorers
+    // (nor for open-search tolerances, whose windows exceed the warp kernel's cap: the copy would only cost memory)
+    const float ptol_span = std::max(std::fabs(sv.precursor_tol.lo), std::fabs(sv.precursor_tol.hi));
+    const bool narrow_tol = ptol_span <= (sv.precursor_tol.kind == 0 ? 2000.0f : sv.precursor_tol.kind == 1 ? 0.2f : 5.0f);   // ppm / percent / Da
+    const WideIndexView nv = (S->narrow_index && !sv.wide_window && narrow_tol) ? db_narrow_index(db, S->narrow_block, S->narrow_cells_x) : WideIndexView{};
     for (uint32_t q = 0; q < C.nparts; q++) {   // one launch per part of the masses copy (a resident batch has one part)
         if (C.nparts > 1) CUDA_TRY(cudaStreamWaitEvent(st, L.ev_part[q], 0));
-        k_prelim_narrow_warp<<<dim3((n + WARPQ_WARPS - 1) / WARPQ_WARPS, sv.qmax), WARPQ_WARPS * 32, 0, st>>>(db->v, svq, bv, L.d_nlist.as<uint64_t>(), C.part_lo[q],
-                                                                                                          C.part_lo[q + 1]);
+        const dim3 wgrid((n + WARPQ_WARPS - 1) / WARPQ_WARPS, sv.qmax);
+        if (nv.frag != nullptr) k_prelim_narrow_warp<true><<<wgrid, WARPQ_WARPS * 32, 0, st>>>(db->v, svq, bv, L.d_nlist.as<uint64_t>(), C.part_lo[q], C.part_lo[q + 1], nv);
+        else k_prelim_narrow_warp<false><<<wgrid, WARPQ_WARPS * 32, 0, st>>>(db->v, svq, bv, L.d_nlist.as<uint64_t>(), C.part_lo[q], C.part_lo[q + 1], nv);
         CUDA_TRY(cudaGetLastError());
         launches += q > 0;
     }

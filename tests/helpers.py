@@ -75,3 +75,10 @@ def assert_features_equal(gf, gc, of, oc, report_psms, what="", f64_exact=None):
             raise AssertionError(f"{what}: field {f} differs at rows {bad} ({'bit-exact' if f64_exact else 'rtol 1e-6'} compare, {int((~ok).sum())} rows): "
                                  f"gpu={[float(x).hex() for x in a[bad]]} oracle={[float(x).hex() for x in b[bad]]}")
     return int(sel.sum())
+
+
+def valid_rows(features, counts, report_psms):
+    """The rows of a score_batch result that hold PSMs (spectrum i: rows i*report_psms .. +counts[i]); the rest of the array is never written."""
+    import numpy as np
+    k = np.arange(len(features)) % report_psms
+    return features[k < np.repeat(np.asarray(counts), report_psms)]

@@ -5,7 +5,7 @@ import pytest
 
 from sage_b200 import IndexedDatabase, Scorer, Tolerance, synth
 
-from helpers import assert_features_equal, oracle_cfg, oracle_db_from_peptides
+from helpers import assert_features_equal, oracle_cfg, oracle_db_from_peptides, valid_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -63,6 +63,35 @@ def test_cfg2_sample_parity_and_properties(full):
     sc.set_option("pipeline_chunks", 3)
     g3, c3 = sc.score_batch(spectra)
     assert np.array_equal(c3, gc) and g3[sel].tobytes() == gf[sel].tobytes()
+
+
+def test_host_paths_agree_bitwise(full):
+    """The same 50k batch through every host path of sage_b200_score_batch gives the same bytes: pageable caller arrays (staged through the lane's
+    pinned buffers by the pool + helper thread), pinned caller arrays with the peak-mass copy in 1, 2 and 4 parts (one counting launch per part),
+    and two pipelined chunks."""
+    from sage_b200 import SpectraBatch, api
+    pep, spectra, gdb, _ = full
+    kw = dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20))
+    sc = Scorer(gdb, **kw)
+    ref_f, ref_c = sc.score_batch(spectra)      # pageable numpy arrays
+    ref_f, ref_c = valid_rows(ref_f, ref_c, 1).copy(), ref_c.copy()
+    assert ref_c.sum() > 45_000
+    pm, pi = api.pinned_empty(spectra.masses.shape, np.float32), api.pinned_empty(spectra.intensities.shape, np.float32)
+    pm[...] = spectra.masses
+    pi[...] = spectra.intensities
+    pinned = SpectraBatch(**{**spectra.__dict__, "masses": pm, "intensities": pi})
+    try:
+        for parts in (1, 2, 4):
+            sc.set_option("mass_parts", parts)
+            f, c = sc.score_batch(pinned)
+            assert np.array_equal(c, ref_c) and valid_rows(f, c, 1).tobytes() == ref_f.tobytes(), f"pinned, {parts} part(s)"
+        sc.set_option("pipeline_chunks", 2)
+        for batch, what in ((pinned, "pinned"), (spectra, "pageable")):
+            f, c = sc.score_batch(batch)
+            assert np.array_equal(c, ref_c) and valid_rows(f, c, 1).tobytes() == ref_f.tobytes(), f"{what}, two chunks"
+    finally:
+        api.pinned_free(pm)
+        api.pinned_free(pi)
 
 
 def test_cfg4_sample_parity(full):

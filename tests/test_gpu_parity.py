@@ -8,7 +8,7 @@ import sage_b200
 from sage_b200 import IndexedDatabase, Precursor, ProcessedSpectrum, Scorer, SpectraBatch, Tolerance, synth
 from oracle import oracle as O
 
-from helpers import assert_features_equal, f64_exact_default, oracle_cfg, oracle_db_from_peptides, peptides_from_oracle
+from helpers import assert_features_equal, f64_exact_default, oracle_cfg, oracle_db_from_peptides, peptides_from_oracle, valid_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -23,15 +23,19 @@ def small():
 
 
 def run_both(odb, gdb, spectra, pep_caps=(2048, 0), **kw):
-    """Scores with the CUDA path under each prelim strategy (default = peptide-centric for small windows, 0 = always probe the
-    fragment index in the reference's loop order) and requires both to equal the oracle."""
+    """Scores with the CUDA path under each preliminary-scoring strategy — peptide-centric counting for small windows (pep_cap > 0), probing
+    the small-block copy of the index (pep_cap 0, narrow_index 1: the default), probing the page index in the reference's loop order
+    (narrow_index 0; last, so that the returned scorer's counters are the reference's work terms) — and requires each to equal the oracle."""
     of, oc, _, octr = odb.score_batch(oracle_cfg(**kw), spectra.as_dict(), counters=True)
-    for cap in pep_caps:
+    modes = [(cap, 1) for cap in pep_caps] + [(0, 0)]
+    for cap, narrow_index in modes:
         sc = Scorer(gdb, **kw)
         if cap is not None:
             sc.set_option("pep_cap", cap)
+        sc.set_option("narrow_index", narrow_index)
         gf, gc = sc.score_batch(spectra)
-        n = assert_features_equal(gf, gc, of, oc, kw.get("report_psms", 1), what=str({"pep_cap": cap, **{k: v for k, v in kw.items() if "tol" not in k}}),
+        n = assert_features_equal(gf, gc, of, oc, kw.get("report_psms", 1),
+                                  what=str({"pep_cap": cap, "narrow_index": narrow_index, **{k: v for k, v in kw.items() if "tol" not in k}}),
                                   f64_exact=f64_exact_default(kw.get("score_type", 0)))
     return sc, n, octr
 
@@ -88,6 +92,25 @@ def test_narrow_search(small):
     sc2.score_batch(spectra)
     c2 = sc2.counters()
     assert c2["pep_queries"] == c2["queries"] and c2["pep_fallbacks"] == 0 and c2["matched_fragments"] == c["matched_fragments"]
+
+
+def test_narrow_block_index_block_sizes(small):
+    """The small-block copy of the index with blocks of 64 .. 8192 peptides (windows inside one block, straddling two, spanning many) and the page
+    index give the same rows and the same matched-fragment / candidate counts."""
+    pep, odb, gdb, spectra = small
+    kw = dict(precursor_tol=Tolerance.ppm(-50, 50), fragment_tol=Tolerance.ppm(-20, 20), report_psms=3, min_isotope_err=-1, max_isotope_err=2)
+    ref = Scorer(gdb, **kw)
+    ref.set_option("narrow_index", 0)
+    rf, rc = ref.score_batch(spectra)
+    rf, rc, rctr = valid_rows(rf, rc, 3).copy(), rc.copy(), ref.counters()
+    assert rc.sum() > 500 and rctr["pages"] > 0
+    for block in (64, 300, 1024, 8192):
+        sc = Scorer(gdb, **kw)
+        sc.set_option("narrow_block", block)
+        f, c = sc.score_batch(spectra)
+        ctr = sc.counters()
+        assert np.array_equal(c, rc) and valid_rows(f, c, 3).tobytes() == rf.tobytes(), block
+        assert ctr["matched_fragments"] == rctr["matched_fragments"] and ctr["candidates_scored"] == rctr["candidates_scored"] and ctr["pages"] == 0, block
 
 
 def test_narrow_report5_fragcharge1(small):
@@ -324,7 +347,11 @@ def test_unsorted_peaks_fall_back_to_index_path(small):
         perm = rng.permutation(200)
         m[r], it[r] = m[r][perm], it[r][perm]
     shuffled = SpectraBatch(**{**sub.__dict__, "masses": m.ravel(), "intensities": it.ravel()})
-    sc, _, _ = run_both(odb, gdb, shuffled, pep_caps=(2048,), precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), min_matched_peaks=1)
+    kw = dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), min_matched_peaks=1)
+    run_both(odb, gdb, shuffled, pep_caps=(2048,), **kw)
+    sc = Scorer(gdb, **kw)
+    sc.set_option("pep_cap", 2048)
+    sc.score_batch(shuffled)
     assert sc.counters()["pep_fallbacks"] == 32
 
 

@@ -55,7 +55,7 @@ def main():
     hdr = blk[hi]
     col = {h: i for i, h in enumerate(hdr)}
     inst = [r for r in blk[hi + 1:] if len(r) == len(hdr) and r[0] != "Address"]
-    sass = sass_lines(so, kernel)
+    sass = sass_lines(so, os.environ.get("SASS_NAME") or kernel)   # SASS_NAME: mangled-name substring when several instantiations share the name
     if len(sass) != len(inst):
         print(f"# warning: {len(inst)} instructions in the report vs {len(sass)} in the disassembly (different build?)", file=sys.stderr)
     agg = {}
