@@ -399,7 +399,7 @@ def run_workload(name, wl, steps, warmup, rank, local_rank, world, gpus, D, cpu,
               "data": "synthetic", "config": config, "e2e": e2e,
               "gpu_launches": (int(last["kernel_launches"]) + int(e2e_c["kernel_launches"])) * steps * gpus,   # own kernels in both timed regions (cub sorts not counted)
               "roofline": roofline, "clocks": clocks.summary(),
-              "index": {"n_peptides": len(pep), "n_fragments": int(gdb.info["n_fragments"]), "hbm_bytes": int(gdb.info["device_bytes"]), "build_s": round(build_s, 2)},
+              "index": {"n_peptides": len(pep), "n_fragments": int(gdb.info["n_fragments"]), "hbm_bytes": int(gdb.device_bytes()), "hbm_bytes_page_index": int(gdb.info["device_bytes"]), "build_s": round(build_s, 2)},
               "phases_ms_per_step": {"setup": ph["setup"] / steps, "prelim": ph["prelim"] / steps, "prelim_count": ph["count"] / steps, "score": ph["score"] / steps,
                                      "resident_wall": wall_resident * 1000.0 / steps, "e2e_h2d": e2e_c["ms_h2d"], "e2e_d2h": e2e_c["ms_d2h"]},
               "work_per_step": {k: int(work[k]) for k in ("queries", "tasks", "pages", "entries_scanned", "matched_fragments", "candidates_scored", "psms",

@@ -162,12 +162,13 @@ void sage_b200_scorer_destroy(sage_b200_scorer* scorer);
  *                     probing the fragment index (default 0 = always probe the index, the reference's loop order)
  *   "sort_spectra"    1 (default): process spectra in ascending precursor order for cache locality; results are returned in input order
  *   "pipeline_chunks" cut every batch into at least this many pipelined chunks (default 1: chunks of <= 65536 spectra)
- *   "narrow_index"    1 (default): precursor windows of at most 1024 peptides are counted against a second, peptide-block-major copy of the
+ *   "narrow_index"    1 (default): narrow precursor windows (up to 8192 peptides) are counted against a second, peptide-block-major copy of the
  *                     fragment index (one short m/z run per probe); 0: the reference's loop order against the page index — identical results,
  *                     and the only mode that fills the counters `pages` / `entries_scanned` (the reference algorithm's work terms)
  *   "mass_parts"      1..4 (default 2): the peak-mass copy of a chunk from PINNED caller memory is cut into this many runs of spectra and the
  *                     counting kernel is queued once per run, so it starts while the rest of the copy is in flight
- *   "wide_tile", "wide_lmax", "worklist_reset", "narrow_block"   test hooks (tile size / survivor-list size of the open-search kernel; forget learned list sizes) */
+ *   "wide_tile", "wide_lmax", "worklist_reset", "narrow_block"   test hooks (tile size / survivor-list size of the open-search kernel; forget learned
+ *                     list sizes; peptides per block of the narrow-search copy, 0 = sized by the average precursor window) */
 int sage_b200_scorer_set_option(sage_b200_scorer* scorer, const char* name, int64_t value);
 
 /* Scorer::score over a batch (runner.rs:311-325 `par_iter().flat_map(|s| scorer.score(s))`).

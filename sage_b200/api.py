@@ -370,6 +370,12 @@ class IndexedDatabase:
         _check(load_library().sage_b200_db_get_info(self._h, C.byref(info)))
         self.info = {k: getattr(info, k) for k, _ in CDbInfo._fields_}
 
+    def device_bytes(self) -> int:
+        """HBM held by the index right now, including the block-major copies scorers have built on first use."""
+        info = CDbInfo()
+        _check(load_library().sage_b200_db_get_info(self._h, C.byref(info)))
+        return int(info.device_bytes)
+
     def __del__(self):
         try:
             if self._h:

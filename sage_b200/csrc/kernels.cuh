@@ -405,7 +405,7 @@ __device__ __forceinline__ void block_probe_warp(const WideIndexView& nv, const 
 //    (bounds computed with the reference's f32 ops; both arrays are monotone in the peak mass, which is verified per
 //    spectrum — otherwise the CTA falls back to the index path).
 __device__ __forceinline__ void narrow_cta_query(const DbView& db, const ScorerView& sc, const BatchView& b, uint32_t pmax, uint64_t* nlist, uint32_t item,
-                                                 float* bounds_smem) {
+                                                 float* bounds_smem, const WideIndexView& nv) {
     __shared__ uint32_t cnt32[NARROW_CAP / 2 + 1];
     __shared__ uint32_t s_warp[40];
     ReplaySlot* const nslots = b.nslots;
@@ -498,6 +498,20 @@ __device__ __forceinline__ void narrow_cta_query(const DbView& db, const ScorerV
                     my_matched += c_here;
                 }
             }
+        }
+    } else if (nv.frag != nullptr) {
+        // small-block copy of the index: every warp takes 32 probes at a time (block_probe_warp finishes long runs warp-wide)
+        const uint32_t blk0 = q.pre_lo / nv.block, blk1 = min(q.pre_hi, db.n_pep - 1) / nv.block;
+        for (uint32_t t0 = warp * 32; t0 < ntask; t0 += PRELIM_THREADS) {
+            const uint32_t t = t0 + lane;
+            const bool act = t < ntask;
+            float flo = 0.0f, fhi = 0.0f;
+            if (act) {
+                const uint32_t p = t / nfc, fc = t - p * nfc + 1;
+                const float mass = __fmul_rn(__ldg(b.masses + p0 + p), (float)fc);  // scoring.rs:360
+                tol_bounds(sc.fragment_tol, mass, flo, fhi);
+            }
+            block_probe_warp(nv, q, blk0, blk1, act, flo, fhi, cnt32, my_matched);
         }
     } else {
         for (uint32_t t = tid; t < ntask; t += PRELIM_THREADS) {
@@ -599,11 +613,11 @@ __device__ __forceinline__ void narrow_cta_query(const DbView& db, const ScorerV
 
 // Queries counted by a whole CTA (windows of WARPQ_CAP+1..NARROW_CAP peptides, and the peptide-centric path): a fixed-size grid walks the
 // compacted list k_setup_queries wrote.
-__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b, uint32_t pmax, uint64_t* nlist) {
+__global__ void __launch_bounds__(PRELIM_THREADS) k_prelim_narrow(DbView db, ScorerView sc, BatchView b, uint32_t pmax, uint64_t* nlist, WideIndexView nv) {
     extern __shared__ float bounds_smem[];  // LO[nfc][np] then HI[nfc][np] (peptide-centric path only)
     const uint32_t total = (uint32_t)min(b.counters[C_NCTA], (unsigned long long)b.n * sc.qmax);
     for (uint32_t i = blockIdx.x; i < total; i += gridDim.x) {
-        narrow_cta_query(db, sc, b, pmax, nlist, b.cta_items[i], bounds_smem);
+        narrow_cta_query(db, sc, b, pmax, nlist, b.cta_items[i], bounds_smem, nv);
         __syncthreads();   // shared arrays are reused by the next query
     }
 }
@@ -2561,6 +2575,17 @@ __global__ void k_wide_block_offsets(uint64_t n_frag, const uint64_t* key64, uin
     const uint64_t want = (uint64_t)b << 32;
     while (lo < hi) { const uint64_t m = (lo + hi) >> 1; if (key64[m] < want) lo = m + 1; else hi = m; }
     blk_off[b] = lo;
+}
+// Sum of the precursor-window sizes (peptides inside Tolerance::bounds of the peptide's own mass) of `samples` peptides spread evenly over the
+// index: the host sizes the blocks of the narrow-search copy by the average (sage_b200.cu: narrow_block_for).
+__global__ void k_window_sample(DbView db, Tol ptol, uint32_t samples, unsigned long long* sum) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= samples || db.n_pep == 0) return;
+    const uint32_t i = (uint32_t)((uint64_t)k * db.n_pep / samples);
+    float lo, hi;
+    tol_bounds(ptol, __ldg(db.pep_mono + i), lo, hi);
+    const uint32_t a = pep_partition(db, lo, false), b = pep_partition(db, hi, true);
+    atomicAdd(sum, (unsigned long long)(b > a ? b - a : 0u));
 }
 // rng[0] = min, rng[1] = max of the m/z bit patterns (fragment m/z are positive floats: bit order == value order)
 __global__ void k_frag_mz_range(uint64_t n_frag, const uint2* frag, uint32_t* rng) {

@@ -561,7 +561,11 @@ extern "C" int sage_b200_db_build(const sage_b200_peptides* peptides, uint64_t b
 extern "C" int sage_b200_db_get_info(const sage_b200_db* db, sage_b200_db_info* info) {
     if (!db || !info) return fail(SAGE_B200_EINVAL, "db_info: null argument");
     info->n_peptides = db->v.n_pep; info->n_fragments = db->v.n_frag; info->n_buckets = db->v.n_bucket; info->bucket_size = db->v.bucket_size;
-    info->n_ion_kinds = db->v.n_kinds; info->total_residues = db->total_residues; info->device_bytes = db->device_bytes; info->device = db->device;
+    info->n_ion_kinds = db->v.n_kinds; info->total_residues = db->total_residues; info->device = db->device;
+    {   // + the lazily built block-major copies (open search / narrow search), as far as they exist now
+        std::lock_guard<std::mutex> lock(db->wmu);
+        info->device_bytes = db->device_bytes + db->wide.bytes + db->narrow.bytes;
+    }
     return 0;
 }
 
@@ -652,8 +656,11 @@ static WideIndexView db_wide_index(const sage_b200_db* db, uint32_t block) {
 }
 
 // The narrow-search copy: blocks of `block` peptides (a +-20 ppm window holds a few hundred), LUT cells ~ `cells_x` per block entry.
-static WideIndexView db_narrow_index(const sage_b200_db* db, uint32_t block, uint32_t cells_x) {
+static WideIndexView db_narrow_index(const sage_b200_db* db, uint32_t block, uint32_t cells_x, bool exact) {
     std::lock_guard<std::mutex> lock(db->wmu);
+    // an automatically sized request accepts an existing copy whose blocks are within a factor of two (scorers with different tolerances
+    // sharing one index must not rebuild it in turns)
+    if (!exact && db->narrow.v.frag != nullptr && db->narrow.v.block * 2 >= block && db->narrow.v.block <= block * 2) return db->narrow.v;
     const uint32_t n_block = (db->v.n_pep + block - 1) / std::max(block, 1u);
     const uint64_t per_block = n_block ? db->v.n_frag / n_block : 0;
     uint32_t cells = 1024;
@@ -814,7 +821,9 @@ struct sage_b200_scorer {
     // narrow windows are counted against the small-block copy of the index (block_probe) unless narrow_index == 0: then the reference's loop
     // order probes the page index and the page / entry work counters are produced (tests, bench's work_per_step pass)
     int narrow_index = 1;
-    uint32_t narrow_block = 256, narrow_cells_x = 4;   // measured on cfg2 (counting kernel ms; page index 0.628): 1024 x2 0.736 | 512 x2 0.644 | 1024 x4 0.637 |
+    uint32_t narrow_block_auto = 0;   // block size narrow_block_for chose for this scorer's precursor tolerance
+    int narrow_cta = 1;   // windows of WARPQ_CAP+1..NARROW_CAP peptides (one CTA per query) use the copy too
+    uint32_t narrow_block = 0 /* 0 = sized by the average precursor window, see narrow_block_for */, narrow_cells_x = 4;   // measured on cfg2 (counting kernel ms; page index 0.628): 1024 x2 0.736 | 512 x2 0.644 | 1024 x4 0.637 |
                                                        // 512 x4 0.585 | 256 x2 0.585 | 256 x4 0.546 | 256 x8 0.546 | 128 x4 0.555 (profiles/r02_nblk*)
     int mass_parts = 2;        // measured on cfg2 (e2e ms per 50k-spectrum call, profiles/r02_parts): 1 part 3.24 | 2 -> 3.17 | 3 -> 3.38 | 4 -> 3.41
     int first_chunk_pct = 0;   // measured on cfg2 (e2e ms per 50k-spectrum call): 0 -> 3.44, 10 -> 3.46, 20 -> 3.52, 35 -> 3.53 (profiles/r02_e_*)
@@ -890,7 +899,8 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     if (const char* e = getenv("SAGE_B200_PIPELINE_CHUNKS")) s->pipeline_chunks = std::max(1, atoi(e));
     if (const char* e = getenv("SAGE_B200_TRACE")) s->trace = e[0] == '1';
     if (const char* e = getenv("SAGE_B200_NARROW_INDEX")) s->narrow_index = atoi(e) != 0;
-    if (const char* e = getenv("SAGE_B200_NARROW_BLOCK")) s->narrow_block = (uint32_t)std::max(64, atoi(e));
+    if (const char* e = getenv("SAGE_B200_NARROW_CTA")) s->narrow_cta = atoi(e) != 0;
+    if (const char* e = getenv("SAGE_B200_NARROW_BLOCK")) s->narrow_block = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("SAGE_B200_NARROW_CELLS_X")) s->narrow_cells_x = (uint32_t)std::max(1, atoi(e));
     if (const char* e = getenv("SAGE_B200_MASS_PARTS")) s->mass_parts = std::min(MASS_PARTS, std::max(1, atoi(e)));
     if (const char* e = getenv("SAGE_B200_FIRST_CHUNK_PCT")) s->first_chunk_pct = std::min(50, std::max(0, atoi(e)));
@@ -906,7 +916,7 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
     if (!strcmp(name, "pipeline_chunks")) { s->pipeline_chunks = (int)std::max<int64_t>(1, value); return 0; }
     if (!strcmp(name, "narrow_index")) { s->narrow_index = value != 0; return 0; }
     if (!strcmp(name, "narrow_block")) {   // test hook: peptides per block of the narrow-search copy (rebuilds it on the next batch)
-        if (value < 64 || value > (1 << 20)) return fail(SAGE_B200_EINVAL, "narrow_block must be 64..1048576");
+        if (value != 0 && (value < 64 || value > (1 << 20))) return fail(SAGE_B200_EINVAL, "narrow_block must be 0 (automatic) or 64..1048576");
         s->narrow_block = (uint32_t)value;
         return 0;
     }
@@ -959,6 +969,30 @@ extern "C" void sage_b200_scorer_destroy(sage_b200_scorer* s) {
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Peptides per block of the narrow-search copy of the index: the power of two at or above the average precursor window of this scorer
+// (sampled on the device from the peptide masses themselves), 128..4096. A probe then reads one or two short m/z runs. Measured (counting
+// kernels, ms per step): cfg2 (windows ~180 peptides) 128 -> 0.555, 256 -> 0.546, 512 -> 0.585, 1024 -> 0.637; cfg3 (windows ~1500) 256 -> 20.4,
+// 512 -> 14.0, 1024 -> 10.4, 2048 -> 9.0 (page index: 22-28).
+static int narrow_block_for(sage_b200_scorer* S) {
+    if (S->narrow_block_auto) return 0;
+    const uint32_t samples = 4096;
+    unsigned long long* d_sum = nullptr;
+    unsigned long long sum = 0;
+    CUDA_TRY(cudaMalloc(&d_sum, 8));
+    cudaError_t e = cudaMemset(d_sum, 0, 8);
+    if (e == cudaSuccess) {
+        k_window_sample<<<(samples + 255) / 256, 256>>>(S->db->v, S->sv.precursor_tol, samples, d_sum);
+        e = cudaMemcpy(&sum, d_sum, 8, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_sum);
+    if (e != cudaSuccess) return fail(SAGE_B200_ECUDA, "window sampling failed: %s", cudaGetErrorString(e));
+    const double avg = (double)sum / samples;
+    uint32_t block = 128;
+    while (block < 4096 && (double)block < avg) block <<= 1;
+    S->narrow_block_auto = block;
+    return 0;
+}
 
 // Waits for the lane's staging thread (if one is running) and reports its error as this thread's.
 static int lane_join_stager(Lane& L) {
@@ -1209,7 +1243,11 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     // (nor for open-search tolerances, whose windows exceed the warp kernel's cap: the copy would only cost memory)
     const float ptol_span = std::max(std::fabs(sv.precursor_tol.lo), std::fabs(sv.precursor_tol.hi));
     const bool narrow_tol = ptol_span <= (sv.precursor_tol.kind == 0 ? 2000.0f : sv.precursor_tol.kind == 1 ? 0.2f : 5.0f);   // ppm / percent / Da
-    const WideIndexView nv = (S->narrow_index && !sv.wide_window && narrow_tol) ? db_narrow_index(db, S->narrow_block, S->narrow_cells_x) : WideIndexView{};
+    WideIndexView nv{};
+    if (S->narrow_index && !sv.wide_window && narrow_tol) {
+        if (S->narrow_block == 0 && (rc = narrow_block_for(S))) return rc;
+        nv = db_narrow_index(db, S->narrow_block ? S->narrow_block : S->narrow_block_auto, S->narrow_cells_x, S->narrow_block != 0);
+    }
     for (uint32_t q = 0; q < C.nparts; q++) {   // one launch per part of the masses copy (a resident batch has one part)
         if (C.nparts > 1) CUDA_TRY(cudaStreamWaitEvent(st, L.ev_part[q], 0));
         const dim3 wgrid((n + WARPQ_WARPS - 1) / WARPQ_WARPS, sv.qmax);
@@ -1219,7 +1257,8 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
         launches += q > 0;
     }
     if (C.nparts > 1) CUDA_TRY(cudaStreamWaitEvent(st, L.ev_masses, 0));
-    k_prelim_narrow<<<(unsigned)std::min<uint64_t>(C.nitems, (uint64_t)db->sm_count * 6), PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>());
+    k_prelim_narrow<<<(unsigned)std::min<uint64_t>(C.nitems, (uint64_t)db->sm_count * 6), PRELIM_THREADS, pep_smem, st>>>(db->v, svq, bv, C.pmax, L.d_nlist.as<uint64_t>(),
+                                                                                                                         S->narrow_cta ? nv : WideIndexView{});
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(L.ev[8], st));   // narrow counting kernels done (the open-search kernel, when present, is timed with the replays)
     // narrow windows (<= NARROW_CAP peptides): 32-bit heap keys, half the shared memory
