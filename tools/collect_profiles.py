@@ -2,7 +2,7 @@
 """Turns the scratch output of tools/gpu_final_profile.sh (gpurun_out/<tag>/) into the committed summaries under profiles/ (names r02_final_*):
 bench JSON lines, ncu launch list + per-kernel summary, key metrics of the `ncu --set full` captures, per-source-line tables, traffic.json.
 
-    python tools/collect_profiles.py gpurun_out/r02_final /tmp/lib_r02_final.so
+    python tools/collect_profiles.py gpurun_out/r02_final3 sage_b200/lib/libsage_b200.so [tag]
 """
 import csv
 import json
@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 src, lib = sys.argv[1], sys.argv[2]
 P = os.path.join(ROOT, "profiles")
-tag = "r02_final"
+tag = sys.argv[3] if len(sys.argv) > 3 else "r02_final3"
 
 
 def json_line(path):
@@ -24,7 +24,7 @@ def json_line(path):
     raise RuntimeError("no JSON line in " + path)
 
 
-for name in ("bench_cfg2_full", "bench_reference_arm", "bench_cfg4", "bench_cfg5", "bench_cfg3", "bench_cfg2_rare_noinline"):
+for name in ("bench_cfg2_full", "bench_reference_arm", "bench_cfg4", "bench_cfg5", "bench_cfg3", "bench_cfg2_page_index"):
     f = os.path.join(src, name + ".json")
     if os.path.exists(f):
         try:
@@ -40,7 +40,7 @@ if os.path.exists(lf):
     hdr = rows[hi]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
     with open(os.path.join(P, f"{tag}_launches_cfg2.csv"), "w") as o:
-        o.write("# ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 80: python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras\nkernel,duration_us\n")
+        o.write("# ncu --metrics gpu__time_duration.sum --clock-control none -s 80 -c 80: python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras\nkernel,duration_us\n")
         agg = {}
         for r in rows[hi + 1:]:
             if len(r) > vi:
@@ -72,15 +72,20 @@ for rep, wl, kernels in (("prof_cfg2.ncu-rep", "cfg2", ["k_score", "k_prelim_nar
                     v, u = x.split()[0], x.split()[1] if len(x.split()) > 1 else ""
                     m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
                     return float(v) * m
-                traffic[wl][k] = int(num(e["dram__bytes_read.sum"]) + num(e["dram__bytes_write.sum"]))
+                tb = num(e["dram__bytes_read.sum"]) + num(e["dram__bytes_write.sum"])
+                if tb == tb:   # ncu reports nan for a launch it could not attribute DRAM counters to: keep the kernel out of traffic.json
+                    traffic[wl][k] = int(tb)
     for k in kernels[:3] if wl == "cfg2" else kernels[:1]:
         try:
-            out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), rp, lib, k, "45"], stderr=subprocess.DEVNULL).decode()
+            env = dict(os.environ)
+            if k == "k_prelim_narrow_warp":
+                env["SASS_NAME"] = "k_prelim_narrow_warpILb1"   # the block-index instantiation is the one the timed steps run
+            out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), rp, lib, k, "45"], stderr=subprocess.DEVNULL, env=env).decode()
             open(os.path.join(P, f"{tag}_{k}_by_source_line.txt"), "w").write(out)
         except Exception as e:
             print("by-line failed", k, e)
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
-for name in ("sanitizer_memcheck.txt", "tests.log", "trace_cfg2.err", "smi.txt"):
+for name in ("sanitizer_memcheck.txt", "tests.log", "trace_cfg2.err", "smi.txt", "phase_cycles_cfg2.txt"):
     f = os.path.join(src, name)
     if os.path.exists(f):
         txt = open(f).read()
