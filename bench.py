@@ -379,8 +379,9 @@ def run_workload(name, wl, steps, warmup, rank, local_rank, world, gpus, D, cpu,
     step_s = dev_s / steps
     notes = {"k_score": "instruction-issue / latency bound, not byte bound: per candidate ~2(L-1)Z sorted-array lookups in shared memory; its algorithmic bytes "
                         "(candidate records + intensities) are small, see DESIGN.md",
-             "k_prelim_narrow_warp": "dependent-probe (latency / divergent-issue) bound, not stream bound: `frac` counts the reference algorithm's probe bytes "
-                                     "(work terms of one untimed step in the reference's loop order), `dram_frac` what DRAM really moved; see DESIGN.md",
+             "k_prelim_narrow_warp": "dependent-probe (latency / divergent-issue) bound, not stream bound: `frac` counts the REFERENCE algorithm's probe bytes "
+                                     "(work terms of one untimed step in the reference's loop order) and can exceed 1 because the timed path answers the probes "
+                                     "from the small-block copy of the index without visiting those pages; `dram_frac` is what DRAM really moved; see DESIGN.md",
              "k_prelim_wide": "open-search counting kernel; see DESIGN.md"}
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
                 "traffic": dom["traffic"], "dram_frac": dom["dram_frac"], "traffic_note": dom["traffic_note"], "peak_source": peak_src,
