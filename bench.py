@@ -8,7 +8,7 @@ A "step" is one pass of the hot path over one batch of synthetic spectra. The he
 50k MS2 spectra x 200 peaks vs a ~2M-peptide tryptic index, +-20 ppm precursor / +-20 ppm fragment; per GPU the work is fixed (weak
 scaling: every rank scores its own 50k spectra against a replicated index; no collective on the data path).
 
-  value      spectra/s with the spectra already resident in HBM: K x (k_setup_queries -> k_prelim_* -> k_replay -> k_score), timed with CUDA
+  value      spectra/s with the spectra already resident in HBM: K x (k_setup_queries -> k_prelim_* -> k_replay -> k_score [-> k_fold -> k_features -> k_rows]), timed with CUDA
              events on the launching stream (sage_b200_batch_run), max over ranks.
   e2e        spectra/s through the C-ABI call sage_b200_score_batch with pinned HOST buffers: H2D of the spectra and D2H of the Feature rows
              inside the timed region; `e2e.pageable` is the same call with ordinary (malloc'd) host arrays, as a Rust Vec<f32> would be.
@@ -377,7 +377,8 @@ def run_workload(name, wl, steps, warmup, rank, local_rank, world, gpus, D, cpu,
                            "dram_frac": (tr / t / 1e9 / peak if (tr and t > 0) else None), "traffic_note": tr_note})
     dom = max(per_kernel, key=lambda r: r["launch_ms"])
     step_s = dev_s / steps
-    notes = {"k_score": "instruction-issue / latency bound, not byte bound: per candidate ~2(L-1)Z sorted-array lookups in shared memory; its algorithmic bytes "
+    notes = {"k_score": "the scoring phase: k_score<true> (matching, one CTA per spectrum) + k_fold + k_features + k_rows (one thread per candidate / row) for non-chimeric "
+                        "searches, the fused k_score otherwise. Instruction-issue / latency bound, not byte bound: per candidate ~2(L-1)Z sorted-array lookups in shared memory; its algorithmic bytes "
                         "(candidate records + intensities) are small, see DESIGN.md",
              "k_prelim_narrow_warp": "dependent-probe (latency / divergent-issue) bound, not stream bound: `frac` counts the REFERENCE algorithm's probe bytes "
                                      "(work terms of one untimed step in the reference's loop order) and can exceed 1 because the timed path answers the probes "

@@ -165,6 +165,8 @@ void sage_b200_scorer_destroy(sage_b200_scorer* scorer);
  *   "narrow_index"    1 (default): narrow precursor windows (up to 8192 peptides) are counted against a second, peptide-block-major copy of the
  *                     fragment index (one short m/z run per probe); 0: the reference's loop order against the page index — identical results,
  *                     and the only mode that fills the counters `pages` / `entries_scanned` (the reference algorithm's work terms)
+ *   "score_split"     1 (default): non-chimeric scoring runs as three kernels (match per spectrum; fold and rank / rows one thread per candidate);
+ *                     0: one fused kernel per spectrum (always used for chimera, annotate_matches, quick_score) — identical results
  *   "mass_parts"      1..4 (default 2): the peak-mass copy of a chunk from PINNED caller memory is cut into this many runs of spectra and the
  *                     counting kernel is queued once per run, so it starts while the rest of the copy is in flight
  *   "wide_tile", "wide_lmax", "worklist_reset", "narrow_block"   test hooks (tile size / survivor-list size of the open-search kernel; forget learned

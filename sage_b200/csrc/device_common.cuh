@@ -23,6 +23,10 @@ constexpr int SCORE_MIN_CTAS = SAGE_B200_SCORE_MIN_CTAS;   // k_score CTAs per S
 #ifndef SAGE_B200_SCORE_UNROLL
 #define SAGE_B200_SCORE_UNROLL 1
 #endif
+#ifndef SAGE_B200_SCORE_MIN_CTAS_SPLIT
+#define SAGE_B200_SCORE_MIN_CTAS_SPLIT 11   /* measured on cfg2 (score phase, ms): 10 -> 1.071, 11 -> 1.059 (40 registers, 30 bytes of spills) */
+#endif
+constexpr int SCORE_MIN_CTAS_SPLIT = SAGE_B200_SCORE_MIN_CTAS_SPLIT;   // k_score<true> keeps no records / order / marks in shared memory
 constexpr uint32_t SCORE_UNROLL = SAGE_B200_SCORE_UNROLL;   // tasks per lane and iteration of k_score's phase B (1 or 2; measured, profiles/r02_*)
 constexpr uint32_t SCORE_TILE = SAGE_B200_SCORE_TILE;      // tasks (theoretical-fragment lookups) per shared-memory tile of k_score (multiple of 256)
 constexpr int MAX_KINDS = 6;
@@ -183,7 +187,8 @@ struct ReplaySlot { unsigned long long off; uint32_t item, n_list, state /*0 = r
 
 // Device counters (u64 slots)
 enum { C_TASKS = 0, C_PAGES, C_ENTRIES, C_MATCHED, C_CANDS, C_PEPFLOATS, C_PSMS, C_QUERIES, C_WIDE, C_MAXPOT, C_WORK, C_ERR, C_PEPQ, C_PEPFALLBACK, C_WSLOT, C_WOVERFLOW, C_FRAGS,
-       C_NLIST /* bump cursor of the narrow key-list arena */, C_NCTA /* queries listed in cta_items */, C_NLIST_NEED /* arena entries this chunk needs (exact upper bound) */, C_COUNT };
+       C_NLIST /* bump cursor of the narrow key-list arena */, C_NCTA /* queries listed in cta_items */, C_NLIST_NEED /* arena entries this chunk needs (exact upper bound) */,
+       C_HITS /* bump cursor of the split scorer's hit arena (entries reserved = tasks of the spectrum) */, C_COUNT };
 
 struct DbView {
     const uint2* frag;        // {peptide_index, fragment_mz bits}, reference bucket layout

@@ -1684,6 +1684,36 @@ struct __align__(16) CandHdr { uint32_t ion_off, base, next; uint16_t nions; uin
 
 __device__ __forceinline__ bool fast_tol_ok(float t) { const float a = fabsf(t); return t == 0.0f || (a >= 1e-9f && a <= 1e6f); }
 
+// ---- split scoring (k_score<true> -> k_fold -> k_features). A spectrum's CTA spends a third of its life in phases that keep one thread per
+// candidate (or one thread) busy: the ordered fold, the records (f64 ln), the rank count and the Feature rows. With SPLIT the CTA only matches:
+// it leaves the hits of its candidates in task order in a global arena and the candidate headers beside them; k_fold then folds ONE CANDIDATE PER
+// THREAD over all spectra of the chunk (dense lanes instead of 39 of 128), k_features ranks and writes the rows, again one thread per candidate.
+// Same arithmetic in the same order: sums, runs, ppm, hyperscore, rank, rows are bit-identical to the fused kernel (tests run both).
+struct CandOut { uint64_t key; uint32_t h0, hcnt; uint16_t nions; uint8_t nfc, plen; uint32_t pad; };   // hits [h0, h0 + hcnt) of the spectrum's arena slice
+struct SpecMeta { unsigned long long hit_base, matched_peaks, scored; uint32_t ncand, pad; };
+struct SplitOut {
+    CandOut* cand;              // [n][kparam]
+    SpecMeta* meta;             // [n]
+    uint16_t* hit_k;            // kind << 13 | ion index
+    float* hit_i;               // matched intensity
+    float* hit_t;               // ppm term
+    unsigned long long hit_cap; // entries of the three hit arrays
+    struct ScoreRec* recs;      // [n][kparam]
+    unsigned long long* hkey;   // [n][kparam] sort key of build_features: order-preserving integer image of the hyperscore, 0 = below min_matched_peaks
+    unsigned long long* counters;
+};
+
+// Order-preserving map f64 -> u64 (x < y <=> key(x) < key(y) for non-NaN x, y; -0.0 is folded into +0.0 first) and its inverse. The rank count of
+// k_features compares these keys: 64-bit integer compares instead of FP64 ones (the FP64 pipe made that kernel 0.23 ms).
+__device__ __forceinline__ unsigned long long f64_sort_key(double d) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d + 0.0);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_from_sort_key(unsigned long long k) {
+    const unsigned long long u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
 // Optional per-phase cycle accounting of k_score (variant builds only: -DSAGE_B200_PHASE_CLOCKS=1): thread 0 of every CTA adds the cycles
 // between consecutive marks to g_phase[i]; read back with sage_b200_debug_phase_cycles (tools/phase_cycles.py).
 #if SAGE_B200_PHASE_CLOCKS
@@ -1706,7 +1736,17 @@ struct ScoreTile {
     uint16_t hits[SCORE_TILE];     // per-warp compact lists of hit slots (bit 15: already final, skip in phase B')
     uint16_t lut[SPEC_LUT_CELLS];  // spectrum LUT (spectrum_lut_setup)
     uint32_t scan[SCORE_THREADS / 32];
+    unsigned long long hit_base;   // SPLIT: this spectrum's slice of the hit arena
+    uint32_t hit_room;             // SPLIT: 0 when the arena is too small (the host re-runs the chunk with the exact size)
 };
+
+// (kind, ion index) of entry ki of a candidate's ion table (kinds concatenated, `nions` ions each): kind << 13 | index (<= 6 kinds, < 255 ions)
+__device__ __forceinline__ uint32_t kind_index(uint32_t ki, uint32_t nions) {
+    uint32_t kind = ki >= nions;   // two ion kinds (b/y) in practice: one compare; more kinds finish in the loop
+    uint32_t idx = ki - (kind ? nions : 0);
+    while (idx >= nions) { idx -= nions; kind++; }
+    return kind << 13 | idx;
+}
 
 // One task of phase B, FAST preconditions checked by the caller (nfc <= 3, ion in [1, 1e20]): returns true when the tolerance window of the
 // theoretical fragment holds at least one peak; mz / first in-window peak are left in `mz`, `idx`.
@@ -1729,9 +1769,9 @@ __device__ __forceinline__ bool fast_task(float ion, uint32_t fc, float tlo, flo
     return pm[idx] <= hi;
 }
 
-template <bool FAST>
+template <bool FAST, bool SPLIT>
 __device__ __forceinline__ void score_candidates_flat(const DbView& db, const ScorerView& sc, const uint64_t* cur, uint32_t ncand, const SpecView& sp,
-                                                      ScoreTile& S, ScoreRec* recs) {
+                                                      ScoreTile& S, ScoreRec* recs, const SplitOut& so, uint32_t spec) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SCORE_THREADS / 32;
     constexpr uint32_t tile = SCORE_TILE;
     // ---- phase A: candidate headers + exclusive scan of the task counts
@@ -1763,6 +1803,15 @@ __device__ __forceinline__ void score_candidates_flat(const DbView& db, const Sc
     }
     if (tid < ncand) { CandHdr h; h.ion_off = ion_off; h.base = base; h.next = base + total; h.nions = (uint16_t)nions; h.nfc = (uint8_t)nfc; h.pad = 0; S.hdr[tid] = h; }
     if (tid == 0) { CandHdr h; h.ion_off = 0; h.base = T; h.next = 0xFFFFFFFFu; h.nions = 0; h.nfc = 1; h.pad = 0; S.hdr[ncand] = h; }   // sentinel: stops every cursor
+    uint32_t hcnt = 0, hits_before = 0;   // SPLIT: hits of candidate tid so far / hits of the tiles done
+    if (SPLIT && tid == 0) {   // reserve T entries (an upper bound: a task has at most one hit); the hits are written compactly from the slice's start
+        const unsigned long long hb = atomicAdd(so.counters + C_HITS, (unsigned long long)T);
+        const bool room = hb + T <= so.hit_cap;
+        S.hit_base = hb;
+        S.hit_room = room ? 1u : 0u;
+        so.meta[spec].hit_base = hb;
+        if (!room) so.meta[spec].ncand = 0;
+    }
     // fold state of candidate tid (registers, carried across tiles)
     uint32_t mb = 0, my = 0;
     float sb = 0.f, sy = 0.f, ppm = 0.f;
@@ -1890,6 +1939,55 @@ __device__ __forceinline__ void score_candidates_flat(const DbView& db, const Sc
         }
         __syncthreads();
         PH(4);
+        if (SPLIT) {
+            // ---- emit: the tile's hits go to the arena in task order. Position = hits of earlier tiles + set bits below the slot.
+            const uint32_t nwords = (tn + 31) >> 5;
+            const uint32_t mw = lane < nwords ? S.mask[lane] : 0u;   // every warp scans the (<= 32) words of the tile
+            uint32_t incl = (uint32_t)__popc(mw);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            const uint32_t pre = incl - (uint32_t)__popc(mw), tile_total = __shfl_sync(0xffffffffu, incl, 31);
+            // four threads per 32-slot word, eight slots each
+            const uint32_t word = tid >> 2, q8 = (tid & 3) * 8;
+            const uint32_t wm = word < nwords ? S.mask[word] : 0u;
+            const uint32_t p = __shfl_sync(0xffffffffu, pre, word & 31);
+            uint32_t m8 = (wm >> q8) & 0xFFu;
+            const bool room = S.hit_room != 0;
+            while (m8) {
+                const uint32_t bit = q8 + (uint32_t)__ffs(m8) - 1;
+                m8 &= m8 - 1;
+                const uint32_t slot = (word << 5) + bit, t = t0 + slot;
+                uint32_t lo = 0, hi = ncand;   // candidate of the task: largest c with base[c] <= t, skipping zero-length ones
+                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.hdr[mid].base <= t) lo = mid; else hi = mid; }
+                while (t >= S.hdr[lo].next) lo++;
+                const CandHdr hh = S.hdr[lo];
+                const uint32_t f = t - hh.base;
+                const uint32_t ki = hh.nfc == 1 ? f : (hh.nfc == 2 ? f >> 1 : f / hh.nfc);
+                if (room) {
+                    const unsigned long long g = S.hit_base + hits_before + p + (uint32_t)__popc(wm & ((1u << bit) - 1u));
+                    so.hit_k[g] = (uint16_t)kind_index(ki, hh.nions);
+                    so.hit_i[g] = S.inten[slot];
+                    so.hit_t[g] = S.term[slot];
+                }
+            }
+            if (tid < ncand && total) {   // hits of candidate tid in this tile
+                const uint32_t a = max(base, t0), b = min(base + total, t0 + tn);
+                if (a < b) {
+                    const uint32_t sa = a - t0, se = b - t0 - 1;
+                    for (uint32_t w = sa >> 5; w <= se >> 5; w++) {
+                        uint32_t m = S.mask[w];
+                        if (w == sa >> 5) m &= 0xffffffffu << (sa & 31);
+                        if (w == se >> 5) m &= 0xffffffffu >> (31 - (se & 31));
+                        hcnt += (uint32_t)__popc(m);
+                    }
+                }
+            }
+            hits_before += tile_total;
+            continue;
+        }
         // ---- fold: thread c walks the set bits of candidate c's slice of the tile in ascending task order
         if (tid < ncand && total) {
             const uint32_t a = max(base, t0), b = min(base + total, t0 + tn);
@@ -1921,6 +2019,26 @@ __device__ __forceinline__ void score_candidates_flat(const DbView& db, const Sc
                 }
             }
         }
+    }
+    if (SPLIT) {   // candidate headers: hits of candidate c start where the hits of candidates 0..c-1 end (task order)
+        uint32_t inc2 = hcnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc2, o);
+            if (lane >= (uint32_t)o) inc2 += v;
+        }
+        __syncthreads();   // S.scan is free again; every thread is done with the tile arrays
+        if (lane == 31) S.scan[warp] = inc2;
+        __syncthreads();
+        uint32_t h0 = inc2 - hcnt;
+#pragma unroll
+        for (uint32_t w = 0; w < nwarps; w++) if (w < warp) h0 += S.scan[w];
+        if (tid < ncand) {
+            CandOut co;
+            co.key = key; co.h0 = h0; co.hcnt = hcnt; co.nions = (uint16_t)nions; co.nfc = (uint8_t)nfc; co.plen = (uint8_t)L; co.pad = 0;
+            so.cand[(size_t)spec * sc.kparam + tid] = co;
+        }
+        return;
     }
     if (tid < ncand) {
         ScoreRec r;
@@ -1995,11 +2113,12 @@ __device__ __forceinline__ bool spectrum_lut_setup(const float* masses /*masses[
     return true;
 }
 
-// One CTA per spectrum.
-__global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
+// One CTA per spectrum. SPLIT: matching only (see SplitOut); the caller guarantees no chimera, no annotation, quick_mode 0, no debug dump.
+template <bool SPLIT>
+__global__ void __launch_bounds__(SCORE_THREADS, SPLIT ? SCORE_MIN_CTAS_SPLIT : SCORE_MIN_CTAS) k_score(DbView db, ScorerView sc, BatchView b, FeatureOut* features, uint32_t* counts, uint32_t pmax,
                                                          uint64_t* dbg_keys /*nullable: initial_hits dump*/, uint32_t* dbg_meta, FragmentOut* frag_out /*nullable*/,
                                                          unsigned long long frag_cap, uint32_t quick_mode /*0 score, 1 keep all prelim, 2 low-memory*/,
-                                                         uint8_t* keep /*quick_score: one byte per peptide*/) {
+                                                         uint8_t* keep /*quick_score: one byte per peptide*/, SplitOut so) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // dynamic layout: masses_raw[pmax+4] intens_raw[pmax+4] cur[lcap] tot[lcap] recs[kparam] order[kparam] mark[pmax]   (pmax % 4 == 0)
     float* masses_raw = reinterpret_cast<float*>(smem_raw);
@@ -2107,6 +2226,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
     PH(1);
     if (tid == 0) masses[np] = INFINITY;   // sentinel behind the last peak (slack of the staging buffer): ends the LUT walk and the peak scans
     const uint32_t ncand = s_ncand;
+    if (SPLIT && tid == 0) {
+        SpecMeta m;
+        m.hit_base = 0; m.matched_peaks = s_matched_peaks; m.scored = s_scored; m.ncand = ncand; m.pad = 0;
+        so.meta[s] = m;
+    }
     // quick_score accumulates into keep[] across chunks; a chunk whose work lists overflowed (the host re-runs it with exact sizes) has partial hit
     // sets and must not leave marks behind. Both counters are final after k_setup_queries.
     const bool lists_fit = b.counters[C_NLIST_NEED] <= b.nlist_cap && b.counters[C_WIDE] <= (unsigned long long)b.wide_cap;
@@ -2129,9 +2253,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
         PH(2);
         if (tid == 0) s_nvalid = 0;
         if (sv.use_lut && sc.score_fast && sc.fragment_tol.kind == 0 && fast_tol_ok(sc.fragment_tol.lo) && fast_tol_ok(sc.fragment_tol.hi))
-            score_candidates_flat<true>(db, sc, cur, ncand, sv, S, recs);
+            score_candidates_flat<true, SPLIT>(db, sc, cur, ncand, sv, S, recs, so, s);
         else
-            score_candidates_flat<false>(db, sc, cur, ncand, sv, S, recs);
+            score_candidates_flat<false, SPLIT>(db, sc, cur, ncand, sv, S, recs, so, s);
+        if (SPLIT) return;   // k_fold / k_features take it from here
         __syncthreads();
         PH(5);
         if (quick_mode == 2) {
@@ -2273,6 +2398,145 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_CTAS) k_score(DbView 
     if (tid == 0) {
         counts[s] = nout;
         if (nout) atomicAdd(b.counters + C_PSMS, (unsigned long long)nout);
+    }
+}
+
+// SPLIT, second kernel: one thread per (spectrum, candidate) folds the candidate's hits in the reference's order (score_candidate,
+// scoring.rs:675-767: per matched fragment in (kind, ion index, charge) order — the arena order) and writes the ScoreRec.
+__global__ void __launch_bounds__(128) k_fold(DbView db, ScorerView sc, SplitOut so, uint32_t n) {
+    __shared__ unsigned long long s_floats[4];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = (uint32_t)(i / sc.kparam), c = (uint32_t)(i - (uint64_t)s * sc.kparam);
+    const bool me = s < n && c < so.meta[s].ncand;
+    // SURVEY.md §8d peptide-record term: 2L+2 floats per scored candidate (one atomic per CTA)
+    unsigned long long a_floats = me ? 2ull * so.cand[(size_t)s * sc.kparam + c].plen + 2ull : 0ull;
+    for (int o = 16; o > 0; o >>= 1) a_floats += __shfl_down_sync(0xffffffffu, a_floats, o);
+    if ((threadIdx.x & 31) == 0) s_floats[threadIdx.x >> 5] = a_floats;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = s_floats[0] + s_floats[1] + s_floats[2] + s_floats[3];
+        if (t) atomicAdd(so.counters + C_PEPFLOATS, t);
+    }
+    if (!me) return;
+    const SpecMeta m = so.meta[s];
+    const CandOut co = so.cand[(size_t)s * sc.kparam + c];
+    uint32_t mb = 0, my = 0;
+    float sb = 0.f, sy = 0.f, ppm = 0.f;
+    Run brun = {0, 0, 0, 0}, yrun = {0, 0, 0, 0};
+    const unsigned long long h0 = m.hit_base + co.h0;
+    for (uint32_t k = 0; k < co.hcnt; k++) {
+        const uint32_t x = so.hit_k[h0 + k];
+        const float it = so.hit_i[h0 + k];
+        ppm = __fadd_rn(ppm, so.hit_t[h0 + k]);
+        const uint32_t kind_i = x >> 13, idx = x & 0x1FFFu;
+        if ((db.nterm_mask >> kind_i) & 1) { mb++; sb = __fadd_rn(sb, it); brun.matched(idx); }
+        else { my++; sy = __fadd_rn(sy, it); yrun.matched(idx); }
+    }
+    ScoreRec r;
+    r.peptide = key_peptide(co.key); r.charge = key_charge(co.key); r.iso = key_iso(co.key);
+    r.matched_b = mb & 0xFFFF; r.matched_y = my & 0xFFFF; r.summed_b = sb; r.summed_y = sy;
+    r.longest_b = brun.longest; r.longest_y = yrun.longest;
+    r.hyperscore = hyperscore_of(sc, r.matched_b, r.matched_y, sb, sy);                  // scoring.rs:756
+    r.ppm_difference = __fdiv_rn(ppm, __fadd_rn(sb, sy));                                // scoring.rs:759
+    r.valid = ((r.matched_b + r.matched_y) & 0xFFFF) >= sc.min_matched_peaks;            // scoring.rs:491
+    r.plen = co.plen;
+    so.recs[(size_t)s * sc.kparam + c] = r;
+    so.hkey[(size_t)s * sc.kparam + c] = r.valid ? f64_sort_key(r.hyperscore) : 0ull;   // valid scores are finite, so their keys are > 0
+}
+
+// SPLIT, third kernel: the sort of build_features (scoring.rs:495: stable, by hyperscore descending) as a rank count over integer sort keys — one
+// thread per (spectrum, candidate), nothing but the count: a candidate among the report_psms best leaves its index in the spectrum's rank slot
+// (slots are preset to "empty"). Everything a row needs beyond that is computed by k_rows, one thread per (spectrum, rank): done here by the one
+// ranked lane of a warp, those ~1000 instructions (f64 ln, 128-byte row) would cost every warp, and so would the best / next-best bookkeeping.
+constexpr uint32_t RANK_EMPTY = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(128) k_features(ScorerView sc, uint32_t n, SplitOut so, uint32_t* rank_slots) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = (uint32_t)(i / sc.kparam), c = (uint32_t)(i - (uint64_t)s * sc.kparam);
+    if (s >= n) return;
+    const uint32_t ncand = so.meta[s].ncand;
+    if (c >= ncand) return;
+    const unsigned long long* hk = so.hkey + (size_t)s * sc.kparam;
+    const unsigned long long h = hk[c];
+    if (h == 0) return;   // below min_matched_peaks: never ranked
+    uint32_t pos = 0;
+    for (uint32_t j = 0; j < ncand; j++) {
+        const unsigned long long hj = hk[j];
+        pos += (hj > h) || (hj == h && j < c);
+    }
+    if (pos < sc.report_psms) rank_slots[(size_t)s * sc.report_psms + pos] = c;
+}
+
+// SPLIT, fourth kernel: the Feature rows (scoring.rs:499-593), one thread per (spectrum, rank). delta_next needs the hyperscore ranked right behind
+// the row's candidate (0.0 when there is none), delta_best the best one: both are re-derived here from the sort keys.
+__global__ void __launch_bounds__(128) k_rows(DbView db, ScorerView sc, BatchView b, SplitOut so, const uint32_t* rank_slots, uint32_t* counts, FeatureOut* features) {
+    __shared__ unsigned long long s_acc[2][4];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = (uint32_t)(i / sc.report_psms), pos = (uint32_t)(i - (uint64_t)s * sc.report_psms);
+    unsigned long long a_cands = 0, a_psms = 0;
+    if (s < b.n) {
+        const SpecMeta m = so.meta[s];
+        const uint32_t cand = rank_slots[(size_t)s * sc.report_psms + pos];
+        if (pos == 0) {   // ranks are dense from 0: the count is the number of filled slots
+            uint32_t cnt = 0;
+            while (cnt < sc.report_psms && rank_slots[(size_t)s * sc.report_psms + cnt] != RANK_EMPTY) cnt++;
+            counts[s] = cnt;
+            a_cands = m.ncand; a_psms = cnt;
+        }
+        if (cand != RANK_EMPTY) {
+            const unsigned long long* hk = so.hkey + (size_t)s * sc.kparam;
+            const unsigned long long h = hk[cand];
+            unsigned long long knext = 0, kbest = 0;
+            for (uint32_t j = 0; j < m.ncand; j++) {
+                const unsigned long long hj = hk[j];
+                kbest = max(kbest, hj);
+                const bool higher = (hj > h) || (hj == h && j < cand);
+                if (!higher && j != cand) knext = max(knext, hj);   // ranked behind this candidate
+            }
+            const double next = knext != 0 ? f64_from_sort_key(knext) : 0.0, best = f64_from_sort_key(kbest);   // scoring.rs:512-516
+            const ScoreRec r = so.recs[(size_t)s * sc.kparam + cand];
+            const double lambda = (double)m.matched_peaks / (double)m.scored;  // scoring.rs:499
+            const float mzp = __fsub_rn(b.prec_mz[s], PROTON);
+            const uint32_t k = (r.matched_b + r.matched_y) & 0xFFFF;
+            const double log10_poisson = ((double)k * ref_ln(sc, lambda) - lambda - lnfact(sc, k)) / 2.302585092994045684;
+            const float precursor_mass = __fmul_rn(mzp, (float)r.charge);
+            const float iso = __fmul_rn((float)r.iso, NEUTRON);
+            const float mono = db.pep_mono[r.peptide];
+            // scoring.rs:530-531
+            const float delta_mass = __fdiv_rn(__fmul_rn(__fsub_rn(__fsub_rn(precursor_mass, mono), iso), 2E6f), __fadd_rn(__fsub_rn(precursor_mass, iso), mono));
+            const uint32_t plen = r.plen;
+            const float sum = __fadd_rn(r.summed_b, r.summed_y);
+            FeatureOut f;
+            f.spectrum = b.spectrum_base + s; f.peptide_idx = r.peptide; f.peptide_len = plen;
+            f.rank = pos + 1;
+            f.label = (db.pep_flags[r.peptide] & 1) ? -1 : 1;
+            f.expmass = precursor_mass; f.calcmass = mono; f.charge = r.charge;
+            f.rt = b.rt ? b.rt[s] : 0.0f;
+            f.ims = (b.ims && !isnan(b.ims[s])) ? b.ims[s] : 0.0f;
+            f.delta_mass = delta_mass; f.isotope_error = iso; f.average_ppm = r.ppm_difference; f._pad0 = 0;
+            f.hyperscore = r.hyperscore; f.delta_next = r.hyperscore - next; f.delta_best = best - r.hyperscore;
+            f.matched_peaks = k; f.longest_b = r.longest_b; f.longest_y = r.longest_y;
+            f.longest_y_pct = __fdiv_rn((float)r.longest_y, (float)plen);
+            f.missed_cleavages = db.pep_missed[r.peptide];
+            f.matched_intensity_pct = __fdiv_rn(__fmul_rn(100.0f, sum), b.tic[s]);
+            f.scored_candidates = (uint32_t)m.scored;
+            f.ms2_intensity = sum;
+            f.poisson = isfinite(log10_poisson) ? log10_poisson : -INFINITY;
+            f.fragment_offset = 0; f.fragment_count = 0;
+            features[(size_t)s * sc.report_psms + pos] = f;
+        }
+    }
+    // chunk-wide sums: one atomic per CTA and counter
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        a_cands += __shfl_down_sync(0xffffffffu, a_cands, o);
+        a_psms += __shfl_down_sync(0xffffffffu, a_psms, o);
+    }
+    if (lane == 0) { s_acc[0][warp] = a_cands; s_acc[1][warp] = a_psms; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (uint32_t w = 1; w < (blockDim.x >> 5); w++) { a_cands += s_acc[0][w]; a_psms += s_acc[1][w]; }
+        if (a_cands) atomicAdd(b.counters + C_CANDS, a_cands);
+        if (a_psms) atomicAdd(b.counters + C_PSMS, a_psms);
     }
 }
 

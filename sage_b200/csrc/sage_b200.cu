@@ -687,7 +687,8 @@ static int ensure_kernel_attributes(int device) {
     CUDA_TRY(raise((const void*)k_replay<true>));
     CUDA_TRY(raise((const void*)k_replay<false>));
     CUDA_TRY(raise((const void*)k_prelim_wide));
-    CUDA_TRY(raise((const void*)k_score));
+    CUDA_TRY(raise((const void*)k_score<false>));
+    CUDA_TRY(raise((const void*)k_score<true>));
     CUDA_TRY(raise((const void*)k_process_ms2));
     if (device >= 0 && device < 64) done[device] = true;
     return 0;
@@ -755,6 +756,7 @@ struct ChunkState {
     size_t nitems = 0, smem = 0, small_bytes = 0;
     size_t o_off = 0, o_pmz = 0, o_tic = 0, o_ilo = 0, o_ihi = 0, o_rt = 0, o_ims = 0, o_chg = 0;
     bool timed_upload = false;
+    uint64_t hits_cap = 0, force_hits = 0;   // split scoring: entries of the hit arena / exact need of a re-run
     uint64_t nlist_cap = 0, force_nlist = 0, force_wide = 0;   // work-list capacities of the current attempt / exact needs for a re-run
     uint32_t wide_cap = 0;
     double t_issue0 = 0, t_issue1 = 0;   // host time (ms since the call started) when queueing this chunk began / ended (trace only)
@@ -773,6 +775,7 @@ struct Lane {
         d_witems, d_citems, d_nlist, d_nslots;
     PinBuf h_small, h_masses, h_intens, h_features, h_counts, h_counters;
     DevBuf d_frags;
+    DevBuf d_cand, d_meta, d_recs, d_hkey, d_emit, d_hitk, d_hiti, d_hitt;   // split scoring (k_score<true> -> k_fold -> k_features)
     ChunkState chunk;
     // pending work of the chunk in flight
     bool ran = false, downloading = false, dbg = false;
@@ -788,7 +791,7 @@ struct Lane {
     void release() {
         if (stager.joinable()) stager.join();
         for (DevBuf* b : {&d_small, &d_masses, &d_intens, &d_queries, &d_hits, &d_keys, &d_features, &d_counts, &d_counters, &d_dbgk, &d_dbgm, &d_sort, &d_sorttmp,
-                          &d_wlist, &d_wslots, &d_witems, &d_citems, &d_nlist, &d_nslots, &d_frags}) b->release();
+                          &d_wlist, &d_wslots, &d_witems, &d_citems, &d_nlist, &d_nslots, &d_frags, &d_cand, &d_meta, &d_recs, &d_hkey, &d_emit, &d_hitk, &d_hiti, &d_hitt}) b->release();
         for (PinBuf* b : {&h_small, &h_masses, &h_intens, &h_features, &h_counts, &h_counters}) b->release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (ev_masses) cudaEventDestroy(ev_masses);
@@ -820,6 +823,8 @@ struct sage_b200_scorer {
     double nlist_per_spectrum = 512.0, wide_per_spectrum = 0.0;
     // narrow windows are counted against the small-block copy of the index (block_probe) unless narrow_index == 0: then the reference's loop
     // order probes the page index and the page / entry work counters are produced (tests, bench's work_per_step pass)
+    int score_split = 1;            // non-chimeric scoring runs as k_score<true> -> k_fold -> k_features -> k_rows (0: the fused kernel; tests compare both)
+    double hits_per_spectrum = 0.0; // learned: hit-arena entries (= scoring tasks) a spectrum needs
     int narrow_index = 1;
     uint32_t narrow_block_auto = 0;   // block size narrow_block_for chose for this scorer's precursor tolerance
     int narrow_cta = 1;   // windows of WARPQ_CAP+1..NARROW_CAP peptides (one CTA per query) use the copy too
@@ -898,6 +903,7 @@ extern "C" int sage_b200_scorer_create(const sage_b200_db* db, const sage_b200_s
     }
     if (const char* e = getenv("SAGE_B200_PIPELINE_CHUNKS")) s->pipeline_chunks = std::max(1, atoi(e));
     if (const char* e = getenv("SAGE_B200_TRACE")) s->trace = e[0] == '1';
+    if (const char* e = getenv("SAGE_B200_SCORE_SPLIT")) s->score_split = atoi(e) != 0;
     if (const char* e = getenv("SAGE_B200_NARROW_INDEX")) s->narrow_index = atoi(e) != 0;
     if (const char* e = getenv("SAGE_B200_NARROW_CTA")) s->narrow_cta = atoi(e) != 0;
     if (const char* e = getenv("SAGE_B200_NARROW_BLOCK")) s->narrow_block = (uint32_t)std::max(0, atoi(e));
@@ -914,6 +920,7 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
     std::lock_guard<std::mutex> lock(s->mu);
     if (!strcmp(name, "sort_spectra")) { s->sort_spectra = value != 0; return 0; }
     if (!strcmp(name, "pipeline_chunks")) { s->pipeline_chunks = (int)std::max<int64_t>(1, value); return 0; }
+    if (!strcmp(name, "score_split")) { s->score_split = value != 0; return 0; }
     if (!strcmp(name, "narrow_index")) { s->narrow_index = value != 0; return 0; }
     if (!strcmp(name, "narrow_block")) {   // test hook: peptides per block of the narrow-search copy (rebuilds it on the next batch)
         if (value != 0 && (value < 64 || value > (1 << 20))) return fail(SAGE_B200_EINVAL, "narrow_block must be 0 (automatic) or 64..1048576");
@@ -939,6 +946,7 @@ extern "C" int sage_b200_scorer_set_option(sage_b200_scorer* s, const char* name
         if (value < 0) return fail(SAGE_B200_EINVAL, "worklist_reset takes a non-negative entry count");
         s->nlist_per_spectrum = (double)value;
         s->wide_per_spectrum = 0.0;
+        s->hits_per_spectrum = value > 0 ? (double)value : 0.0;   // > 0: start the split scorer's hit arena at that many entries per spectrum too
         return 0;
     }
     if (!strcmp(name, "score_fast")) {  // 0: k_score always takes the generic task body (tests compare both)
@@ -1138,6 +1146,7 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
     S->last.h2d_bytes += C.small_bytes + 8 * npk;
     C.loaded = true;
     C.force_nlist = C.force_wide = 0;
+    C.force_hits = 0;
     C.timed_upload = true;
     L.ran = false;
     L.downloading = false;
@@ -1286,12 +1295,44 @@ static int chunk_run(sage_b200_scorer* S, Lane& L, bool dbg) {
     // ---- candidate scoring + feature assembly (first reader of the intensities)
     if ((rc = lane_join_stager(L))) return rc;   // ev_intens is recorded by the staging thread of a pageable chunk
     CUDA_TRY(cudaStreamWaitEvent(st, L.ev_intens, 0));
-    k_score<<<n, SCORE_THREADS, C.smem, st>>>(db->v, sv, bv, L.d_features.as<FeatureOut>(), L.d_counts.as<uint32_t>(), C.pmax,
-                                             dbg ? L.d_dbgk.as<uint64_t>() : nullptr, dbg ? L.d_dbgm.as<uint32_t>() : nullptr,
-                                             annotate ? L.d_frags.as<FragmentOut>() : nullptr, (unsigned long long)S->frag_cap, S->quick_mode,
-                                             S->d_keep.as<uint8_t>());
-    CUDA_TRY(cudaGetLastError());
-    launches++;
+    const bool split = S->score_split && !sv.chimera && !annotate && !dbg && S->quick_mode == 0;
+    if (split) {
+        // hit arena: one entry per scoring task is reserved (sparsely used); sized from what earlier chunks needed, exact on a re-run
+        C.hits_cap = std::max<uint64_t>(C.force_hits, (uint64_t)std::ceil((S->hits_per_spectrum > 0.0 ? S->hits_per_spectrum : 4096.0) * (double)n) + 65536);
+        if ((rc = L.d_cand.reserve((size_t)n * sv.kparam * sizeof(CandOut)))) return rc;
+        if ((rc = L.d_meta.reserve((size_t)n * sizeof(SpecMeta)))) return rc;
+        if ((rc = L.d_recs.reserve((size_t)n * sv.kparam * sizeof(ScoreRec)))) return rc;
+        if ((rc = L.d_hkey.reserve((size_t)n * sv.kparam * 8))) return rc;
+        if ((rc = L.d_emit.reserve((size_t)n * sv.report_psms * 4 + 16))) return rc;
+        if ((rc = L.d_hitk.reserve(2 * C.hits_cap + 16))) return rc;
+        if ((rc = L.d_hiti.reserve(4 * C.hits_cap + 16))) return rc;
+        if ((rc = L.d_hitt.reserve(4 * C.hits_cap + 16))) return rc;
+        SplitOut so{};
+        so.cand = L.d_cand.as<CandOut>(); so.meta = L.d_meta.as<SpecMeta>(); so.hit_k = L.d_hitk.as<uint16_t>(); so.hit_i = L.d_hiti.as<float>();
+        so.hit_t = L.d_hitt.as<float>(); so.hit_cap = C.hits_cap; so.recs = L.d_recs.as<ScoreRec>(); so.hkey = L.d_hkey.as<unsigned long long>(); so.counters = bv.counters;
+        // k_score<true> stages the peaks and the hit lists only (no records / order / marks)
+        const size_t smem_split = (size_t)(C.pmax + 4) * 8 + (size_t)sv.lcap * 16 + 32;
+        k_score<true><<<n, SCORE_THREADS, smem_split, st>>>(db->v, sv, bv, L.d_features.as<FeatureOut>(), L.d_counts.as<uint32_t>(), C.pmax, nullptr, nullptr, nullptr, 0ull, 0u,
+                                                            nullptr, so);
+        CUDA_TRY(cudaGetLastError());
+        const uint64_t nthr = (uint64_t)n * sv.kparam, nrow = (uint64_t)n * sv.report_psms;
+        CUDA_TRY(cudaMemsetAsync(L.d_emit.p, 0xFF, 4 * nrow, st));   // rank slots: RANK_EMPTY
+        k_fold<<<(unsigned)((nthr + 127) / 128), 128, 0, st>>>(db->v, sv, so, n);
+        CUDA_TRY(cudaGetLastError());
+        k_features<<<(unsigned)((nthr + 127) / 128), 128, 0, st>>>(sv, n, so, L.d_emit.as<uint32_t>());
+        CUDA_TRY(cudaGetLastError());
+        k_rows<<<(unsigned)((nrow + 127) / 128), 128, 0, st>>>(db->v, sv, bv, so, L.d_emit.as<uint32_t>(), L.d_counts.as<uint32_t>(), L.d_features.as<FeatureOut>());
+        CUDA_TRY(cudaGetLastError());
+        launches += 4;
+    } else {
+        C.hits_cap = 0;
+        k_score<false><<<n, SCORE_THREADS, C.smem, st>>>(db->v, sv, bv, L.d_features.as<FeatureOut>(), L.d_counts.as<uint32_t>(), C.pmax,
+                                                        dbg ? L.d_dbgk.as<uint64_t>() : nullptr, dbg ? L.d_dbgm.as<uint32_t>() : nullptr,
+                                                        annotate ? L.d_frags.as<FragmentOut>() : nullptr, (unsigned long long)S->frag_cap, S->quick_mode,
+                                                        S->d_keep.as<uint8_t>(), SplitOut{});
+        CUDA_TRY(cudaGetLastError());
+        launches++;
+    }
     CUDA_TRY(cudaEventRecord(L.ev[4], st));
     CUDA_TRY(cudaMemcpyAsync(L.h_counters.p, L.d_counters.p, 8 * C_COUNT, cudaMemcpyDeviceToHost, st));
     L.launches = launches;
@@ -1346,8 +1387,9 @@ static int lane_finish(sage_b200_scorer* S, Lane& L) {
         CUDA_TRY(cudaStreamSynchronize(L.stream));
         if (!L.ran) break;
         const unsigned long long* hc = (const unsigned long long*)L.h_counters.p;
-        const uint64_t need = hc[C_NLIST_NEED], nw = hc[C_WIDE];
-        if (need <= C.nlist_cap && nw <= C.wide_cap) {   // the chunk fitted its work lists: remember what it needed
+        const uint64_t need = hc[C_NLIST_NEED], nw = hc[C_WIDE], nh = C.hits_cap ? hc[C_HITS] : 0;
+        if (nh) S->hits_per_spectrum = std::max(S->hits_per_spectrum, 1.25 * (double)nh / (double)C.n);
+        if (need <= C.nlist_cap && nw <= C.wide_cap && nh <= C.hits_cap) {   // the chunk fitted its work lists: remember what it needed
             S->nlist_per_spectrum = std::max(S->nlist_per_spectrum, 1.25 * (double)need / (double)C.n);
             S->wide_per_spectrum = std::max(S->wide_per_spectrum, (double)nw / (double)C.n);
             break;
@@ -1360,6 +1402,7 @@ static int lane_finish(sage_b200_scorer* S, Lane& L) {
         // a work list was too small: the queries it could not hold reported no hits. Re-run the chunk with the sizes just counted.
         C.force_nlist = need;
         C.force_wide = nw;
+        C.force_hits = nh;
         S->last.chunk_retries++;
         int rc;
         if ((rc = chunk_run(S, L, L.dbg))) return rc;

@@ -113,6 +113,34 @@ def test_narrow_block_index_block_sizes(small):
         assert ctr["matched_fragments"] == rctr["matched_fragments"] and ctr["candidates_scored"] == rctr["candidates_scored"] and ctr["pages"] == 0, block
 
 
+def test_split_scoring_equals_fused(small):
+    """k_score<true> -> k_fold -> k_features (default for non-chimeric scoring) against the fused kernel: same rows, same counters; also with a hit
+    arena that is too small at first (the chunk is re-run with the exact size)."""
+    pep, odb, gdb, spectra = small
+    for kw in (dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20)),
+               dict(precursor_tol=Tolerance.ppm(-50, 50), fragment_tol=Tolerance.ppm(-20, 20), report_psms=5, min_isotope_err=-1, max_isotope_err=2, min_matched_peaks=1),
+               dict(precursor_tol=Tolerance.da(-2, 2), fragment_tol=Tolerance.da(-0.02, 0.02), report_psms=3, max_fragment_charge=1, score_type=1),
+               dict(precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=64, min_matched_peaks=2)):
+        r = kw.get("report_psms", 1)
+        fused = Scorer(gdb, **kw)
+        fused.set_option("score_split", 0)
+        ff, fc = fused.score_batch(spectra)
+        ff, fc, fctr = valid_rows(ff, fc, r).copy(), fc.copy(), fused.counters()
+        assert fc.sum() > 100
+        for fast, reset in ((1, 0), (0, 0), (1, 1)):
+            sc = Scorer(gdb, **kw)
+            sc.set_option("score_fast", fast)
+            if reset:
+                sc.set_option("worklist_reset", 1)
+            f, c = sc.score_batch(spectra)
+            ctr = sc.counters()
+            assert np.array_equal(c, fc) and valid_rows(f, c, r).tobytes() == ff.tobytes(), (kw, fast, reset)
+            for k in ("psms", "candidates_scored", "peptide_record_floats", "matched_fragments"):
+                assert ctr[k] == fctr[k], (k, ctr[k], fctr[k])
+            if reset:
+                assert ctr["chunk_retries"] >= 1
+
+
 def test_narrow_report5_fragcharge1(small):
     pep, odb, gdb, spectra = small
     run_both(odb, gdb, spectra, precursor_tol=Tolerance.ppm(-20, 20), fragment_tol=Tolerance.ppm(-20, 20), report_psms=5, max_fragment_charge=1,
