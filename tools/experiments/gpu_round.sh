@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call: fast GPU parity subset, then A/B bench lines of cfg2, then ncu of k_score. Output under gpurun_out/<tag>/.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_a}; out=gpurun_out/$tag; mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/smi.txt 2>&1
 timeout 900 python -m pytest tests/test_glibc_log.py tests/test_gpu_parity.py tests/test_gpu_random.py tests/test_gpu_process.py -m gpu -x -q > $out/tests.log 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of k_prelim_narrow_warp variants (flattened probe loop): parity tests on the main build, then phases of every variant.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_flat}; out=gpurun_out/$tag; mkdir -p $out
 ( time timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_random.py -m gpu -q -x ) > $out/tests.log 2>&1
 echo "tests exit $?" >> $out/tests.log

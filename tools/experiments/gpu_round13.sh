@@ -1,6 +1,6 @@
 #!/bin/bash
 # e2e timelines of chunked calls (SAGE_B200_TRACE) for several chunkings of the 50k-spectrum batch
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_chunks}; out=gpurun_out/$tag; mkdir -p $out
 for cfg in "SAGE_B200_PIPELINE_CHUNKS=1" "SAGE_B200_PIPELINE_CHUNKS=2" "SAGE_B200_PIPELINE_CHUNKS=3" "SAGE_B200_PIPELINE_CHUNKS=4" "SAGE_B200_FIRST_CHUNK_PCT=20"; do
   n=$(echo $cfg | tr '=' '_')

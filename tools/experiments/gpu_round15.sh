@@ -1,6 +1,6 @@
 #!/bin/bash
 # pageable staging knobs + per-call e2e distribution
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_stage}; out=gpurun_out/$tag; mkdir -p $out
 for cfg in "X=1" "SAGE_B200_STAGE_THREADS=12" "SAGE_B200_STAGE_THREADS=16 SAGE_B200_STAGE_PIECE_KB=1024" "SAGE_B200_STAGE_THREADS=3" "SAGE_B200_STAGE_THREADS=8 SAGE_B200_STAGE_PIECE_KB=512" "SAGE_B200_STAGE_THREADS=24 SAGE_B200_STAGE_PIECE_KB=512"; do
   n=$(echo $cfg | tr '= ' '__')

@@ -1,6 +1,6 @@
 #!/bin/bash
 # masses copy in parts + staging pool: GPU tests, then cfg2 bench lines for 1..4 parts
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_parts}; out=gpurun_out/$tag; mkdir -p $out
 ( time timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_fullsize.py ) > $out/tests.log 2>&1
 echo "tests exit $?" >> $out/tests.log

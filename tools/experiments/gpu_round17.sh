@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_phase}; out=gpurun_out/$tag; mkdir -p $out
 SAGE_B200_LIB=$PWD/sage_b200/lib/ab/phase.so timeout 600 python tools/phase_cycles.py cfg2 2>&1 | tee $out/phase_cfg2.txt
 timeout 300 python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline > $out/bench_cfg2.json 2> $out/bench_cfg2.err

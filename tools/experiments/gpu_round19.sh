@@ -1,6 +1,6 @@
 #!/bin/bash
 # ticketed (persistent) k_prelim_narrow_warp: parity tests on the default build (batch 4), phases for batch 0 / 1 / 4 / 16
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_ticket}; out=gpurun_out/$tag; mkdir -p $out
 ( time timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_fullsize.py ) > $out/tests.log 2>&1
 echo "tests exit $?" >> $out/tests.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # small-block narrow index, second sweep + one ncu capture of the block kernel
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_nblk2}; out=gpurun_out/$tag; mkdir -p $out
 ( time timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_fullsize.py ) > $out/tests.log 2>&1
 echo "tests exit $?" >> $out/tests.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # narrow block index as default: GPU tests, full bench line (extras incl. cfg3 / cfg5 with parity), vector-walk variant on cfg2, old path on cfg3/cfg5 for comparison
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_nblk3}; out=gpurun_out/$tag; mkdir -p $out
 ( time timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_fullsize.py ) > $out/tests.log 2>&1
 echo "tests exit $?" >> $out/tests.log

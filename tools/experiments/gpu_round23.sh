@@ -1,6 +1,6 @@
 #!/bin/bash
 # cooperative finishing of long runs in the block probe: GPU tests, cfg2 lines for WALK_SOLO 4 / 2 / 8, one ncu capture
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_coop}; out=gpurun_out/$tag; mkdir -p $out
 ( time timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_fullsize.py ) > $out/tests.log 2>&1
 echo "tests exit $?" >> $out/tests.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # WALK_SOLO x COOP_GROUP sweep of the block probe (cfg2 phases)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_coop2}; out=gpurun_out/$tag; mkdir -p $out
 for v in s16g32 s32g32 s4g8 s8g8 s8g4 s12g8; do
   lib=sage_b200/lib/ab/$v.so

@@ -1,6 +1,6 @@
 #!/bin/bash
 # block index in the CTA counting kernel: full GPU test suite (incl. cfg3 at size), cfg3 with / without it
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_cta}; out=gpurun_out/$tag; mkdir -p $out
 ( time timeout 2400 python -m pytest tests -m gpu -q ) > $out/tests.log 2>&1
 echo "tests exit $?" >> $out/tests.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_cfg3blk}; out=gpurun_out/$tag; mkdir -p $out
 for cfg in "SAGE_B200_NARROW_BLOCK=1024" "SAGE_B200_NARROW_BLOCK=2048" "SAGE_B200_NARROW_BLOCK=512"; do
   n=$(echo $cfg | tr '= ' '__')

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_c}; out=gpurun_out/$tag; mkdir -p $out
 python tools/debug_seed.py 23 > $out/seed23.log 2>&1
 timeout 900 python -m pytest tests/test_glibc_log.py tests/test_gpu_parity.py tests/test_gpu_random.py tests/test_gpu_process.py -m gpu -q > $out/tests.log 2>&1

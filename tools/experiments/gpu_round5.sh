@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_e}; out=gpurun_out/$tag; mkdir -p $out
 timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_fullsize.py::test_cfg3_index_matches_oracle_at_size --deselect tests/test_gpu_fullsize.py::test_cfg3_at_size_sample_parity > $out/tests.log 2>&1
 echo "tests exit $?" >> $out/tests.log

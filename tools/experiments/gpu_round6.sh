@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_f}; out=gpurun_out/$tag; mkdir -p $out
 timeout 600 python bench.py --workload cfg4 --steps 5 --warmup 3 --no-extras > $out/bench_cfg4.json 2> $out/bench_cfg4.err
 ( time timeout 2400 python -m pytest tests -m gpu -q --durations=12 ) > $out/tests.log 2>&1

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_g}; out=gpurun_out/$tag; mkdir -p $out
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_random.py tests/test_gpu_fullsize.py::test_cfg4_sample_parity tests/test_gpu_fullsize.py::test_cfg2_sample_parity_and_properties -m gpu -q > $out/tests.log 2>&1
 echo "tests exit $?" >> $out/tests.log

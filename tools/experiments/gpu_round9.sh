@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 tag=${1:-r02_j}; out=gpurun_out/$tag; mkdir -p $out
 B="python bench.py --workload cfg4 --steps 5 --warmup 3 --no-extras"
 timeout 600 $B > $out/bench_cfg4_default.json 2> $out/bench_cfg4_default.err
