@@ -206,8 +206,20 @@ struct BlockIndexSlot {
     void *d_frag = nullptr, *d_blk = nullptr, *d_lut = nullptr;
     int failed = 0;
     uint64_t bytes = 0;
+    std::vector<void*> retired;   // arrays of earlier builds: another scorer of the same db may still hold a view of them (freed with the db)
+    uint64_t retired_bytes = 0;
     void release() {
         for (void** p : {&d_frag, &d_blk, &d_lut}) { if (*p) cudaFree(*p); *p = nullptr; }
+        for (void* p : retired) cudaFree(p);
+        retired.clear();
+        retired_bytes = 0;
+        v = WideIndexView{};
+        bytes = 0;
+    }
+    // A rebuild with another block size keeps the old arrays alive: a chunk of another scorer, queued with the old view, may still run.
+    void retire() {
+        for (void** p : {&d_frag, &d_blk, &d_lut}) { if (*p) retired.push_back(*p); *p = nullptr; }
+        retired_bytes += bytes;
         v = WideIndexView{};
         bytes = 0;
     }
@@ -564,7 +576,7 @@ extern "C" int sage_b200_db_get_info(const sage_b200_db* db, sage_b200_db_info* 
     info->n_ion_kinds = db->v.n_kinds; info->total_residues = db->total_residues; info->device = db->device;
     {   // + the lazily built block-major copies (open search / narrow search), as far as they exist now
         std::lock_guard<std::mutex> lock(db->wmu);
-        info->device_bytes = db->device_bytes + db->wide.bytes + db->narrow.bytes;
+        info->device_bytes = db->device_bytes + db->wide.bytes + db->narrow.bytes + db->wide.retired_bytes + db->narrow.retired_bytes;
     }
     return 0;
 }
@@ -597,11 +609,10 @@ static WideIndexView build_block_index(const sage_b200_db* db, BlockIndexSlot& s
     if (slot.v.frag != nullptr && slot.v.block == block) return slot.v;
     if (slot.failed || block == 0 || db->v.n_frag == 0 || db->v.n_pep == 0) return none;
     const uint64_t nf = db->v.n_frag;
-    cudaDeviceSynchronize();   // a rebuild with another block size (tests) must not free arrays a kernel still reads
-    slot.release();
+    slot.retire();   // a rebuild with another block size (tests, scorers with very different tolerances): see BlockIndexSlot::retire
     void *k_a = nullptr, *k_b = nullptr, *p_a = nullptr, *p_b = nullptr, *tmp = nullptr, *d_rng = nullptr;
     auto cleanup = [&]() { for (void* p : {k_a, k_b, p_a, p_b, tmp, d_rng}) if (p) cudaFree(p); };
-    auto give_up = [&]() { cleanup(); slot.release(); cudaGetLastError(); slot.failed = 1; return WideIndexView{}; };
+    auto give_up = [&]() { cleanup(); for (void** p : {&slot.d_frag, &slot.d_blk, &slot.d_lut}) { if (*p) cudaFree(*p); *p = nullptr; } slot.v = WideIndexView{}; slot.bytes = 0; cudaGetLastError(); slot.failed = 1; return WideIndexView{}; };
     const uint32_t n_block = (db->v.n_pep + block - 1) / block;
     while (cells > 256 && (uint64_t)n_block * (cells + 1) * 4 > (1024ull << 20)) cells >>= 1;   // at most 1 GB of LUT
     if (cudaMalloc(&slot.d_frag, 8 * nf + 64) != cudaSuccess || cudaMalloc(&slot.d_blk, 8 * ((size_t)n_block + 1)) != cudaSuccess ||
