@@ -12,9 +12,12 @@ scaling: every rank scores its own 50k spectra against a replicated index; no co
              events on the launching stream (sage_b200_batch_run), max over ranks.
   e2e        spectra/s through the C-ABI call sage_b200_score_batch with pinned HOST buffers: H2D of the spectra and D2H of the Feature rows
              inside the timed region; `e2e.pageable` is the same call with ordinary (malloc'd) host arrays, as a Rust Vec<f32> would be.
+             `ms_per_call_median_rank0` / `ms_in_library_median_rank0`: per-call wall clock at the Python caller / inside the C call.
   roofline   the kernel that takes longest in a step: its share of the SURVEY.md §8d algorithmic bytes / its CUDA-event duration vs the
              measured HBM peak (`frac`), and the same with the DRAM bytes ncu measured for that kernel (`dram_frac`, from profiles/traffic.json
-             when that capture belongs to the sources being timed); `kernels` lists both for every kernel of the step.
+             when that capture belongs to the sources being timed); `kernels` lists both for every kernel of the step. The algorithmic bytes
+             are the reference algorithm's work terms, collected by ONE untimed step in the reference's loop order (option narrow_index = 0):
+             the timed steps count narrow windows against a small-block copy of the index and never visit those pages.
   cpu_baseline  the CPU oracle (bit-faithful port of sage-core's path; OpenMP over spectra) on this box's host cores.
   extra      the other BASELINE.json configurations, each with its own value / e2e / parity check, so that they are driver-run numbers too:
              cfg4 (open search), cfg5 (chimeric, report_psms 5) and cfg3 (15 M-peptide index with two variable modifications); their spectra
