@@ -1066,7 +1066,8 @@ static int chunk_upload(sage_b200_scorer* S, Lane& L, const sage_b200_spectra* s
     // once per part and starts on part p while part p + 1 is still in flight (it walks its spectra in precursor order either way).
     C.nparts = (pin_m && npk > (1u << 21) && n >= 4096) ? (uint32_t)S->mass_parts : 1u;
     for (uint32_t q = 0; q <= C.nparts; q++) C.part_lo[q] = (uint32_t)((uint64_t)n * q / C.nparts);
-    auto part_off = [&](uint32_t q) -> uint64_t { return sp->peak_offsets[c0 + C.part_lo[q]] - pk0; };
+    // (clamped: the offsets are only validated by pack() below, and a copy must never leave the caller's array)
+    auto part_off = [&](uint32_t q) -> uint64_t { const uint64_t o = sp->peak_offsets[c0 + C.part_lo[q]]; return o < pk0 ? 0 : std::min(o - pk0, npk); };
     // floats of the masses sent ahead of the blob: half of part 0 (a quarter of everything when there is one part)
     const uint64_t npk_a = !pin_m ? 0 : (npk > (1u << 21) ? (C.nparts > 1 ? part_off(1) / 2 : npk / 4) : npk);
     if (npk_a) CUDA_TRY(cudaMemcpyAsync(L.d_masses.p, src_m, 4 * npk_a, cudaMemcpyHostToDevice, cp));
