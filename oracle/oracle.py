@@ -377,5 +377,18 @@ def find_reporter_ions(peak_off, masses, intens, labels, tol):
     return out
 
 
+def hyperscore(score_type: int, matched_b: int, matched_y: int, summed_b, summed_y) -> float:
+    """Score::hyperscore (scoring.rs:179-201) for one candidate."""
+    L = lib()
+    L.so_hyperscore.restype = C.c_double
+    return float(L.so_hyperscore(C.c_int32(score_type), C.c_uint32(matched_b), C.c_uint32(matched_y), C.c_float(float(summed_b)), C.c_float(float(summed_y))))
+
+
+def lnfact(n: int) -> float:
+    L = lib()
+    L.so_lnfact.restype = C.c_double
+    return float(L.so_lnfact(C.c_uint32(n)))
+
+
 def num_threads() -> int:
     return int(lib().so_num_threads())

@@ -1470,6 +1470,12 @@ void so_find_reporter_ions(uint64_t n, const uint64_t* peak_off, const float* ma
             out[i * n_labels + l] = pk >= 0 ? intens[peak_off[i] + pk] : 0.0f;
         }
 }
+// Score::hyperscore (scoring.rs:179-201) and the ln-factorial approximation (:170-177) on their own, for the high-precision cross-check in
+// tests/test_oracle_known_answers.py (the f64 fields are otherwise pinned only by the oracle itself).
+double so_hyperscore(int32_t score_type, uint32_t matched_b, uint32_t matched_y, float summed_b, float summed_y) {
+    return score_type_score(score_type, (uint16_t)matched_b, (uint16_t)matched_y, summed_b, summed_y);
+}
+double so_lnfact(uint32_t n) { return lnfact((uint16_t)n); }
 int so_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -240,3 +240,69 @@ def test_config1_tests_config_json(config1):
     assert feats[0]["matched_peaks"] == 22
     assert db.sequence(int(feats[0]["peptide_idx"])) == "LQSRPAAPPAPGPGQLTLR"
     assert abs(feats[0]["hyperscore"] - 72.26591574) < 1e-6
+
+
+def test_hyperscore_against_high_precision_arithmetic():
+    """The f64 scores pinned by something other than the oracle: Score::hyperscore (scoring.rs:179-201) re-evaluated with 60-digit arithmetic
+    (mpmath) from the same f32 inputs. The oracle evaluates ln through the host libm (< 1 ulp) and sums four f64 terms, so it must agree with the
+    exactly rounded value to a few ulp of the result — and the ORDER of two candidates whose exact scores differ by more than that must be the
+    exact order (the rank is a stable sort on this value, scoring.rs:495)."""
+    mpmath = pytest.importorskip("mpmath")
+    import ctypes
+    import ctypes.util
+    log1pf = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6").log1pf
+    log1pf.restype, log1pf.argtypes = ctypes.c_float, [ctypes.c_float]
+    mp = mpmath.mp
+    mp.prec = 200
+    rng = np.random.default_rng(0x5C0E)
+
+    def exact_lnfact(n):   # scoring.rs:170-177 (Stirling-style approximation; n == 0 -> 1.0), every f64 operation replaced by an exact one
+        if n == 0:
+            return mpmath.mpf(1)
+        x = mpmath.mpf(n)
+        return x * mpmath.log(x) - x + mpmath.mpf(0.5) * mpmath.log(x) + mpmath.mpf(0.5) * mpmath.log(mpmath.pi * 2 * x)
+
+    def exact_score(score_type, mb, my, sb, sy):
+        sb32, sy32 = np.float32(sb), np.float32(sy)
+        if score_type == 0:
+            i = mpmath.mpf(float(np.float32(sb32 + np.float32(1.0)))) * mpmath.mpf(float(np.float32(sy32 + np.float32(1.0))))   # the f64 product of two f32 is exact
+            return mpmath.log(i) + exact_lnfact(mb) + exact_lnfact(my)
+        si = float(np.float32(sb32 + sy32))
+        return mpmath.mpf(float(log1pf(ctypes.c_float(si)))) + exact_lnfact(mb) + exact_lnfact(my)   # ln_1p is evaluated in f32 by the reference (libm log1pf)
+
+    cases = []
+    for _ in range(4000):
+        mb, my = int(rng.integers(0, 60)), int(rng.integers(0, 60))
+        sb, sy = float(np.float32(rng.uniform(0, 5e6))), float(np.float32(rng.uniform(0, 5e6)))
+        cases.append((mb, my, sb, sy))
+    worst = 0.0
+    scored = []
+    for mb, my, sb, sy in cases:
+        got = O.hyperscore(0, mb, my, sb, sy)
+        want = exact_score(0, mb, my, sb, sy)
+        ulp = float(np.spacing(np.float64(abs(float(want)))))
+        err = abs(float(mpmath.mpf(got) - want)) / ulp
+        worst = max(worst, err)
+        scored.append((got, want))
+    # ln < 1 ulp of its own result (<= 1 ulp of the sum, which is larger), each lnfact carries its own libm roundings (4 of them at most 1 ulp of
+    # terms no larger than the sum) and three f64 additions add 0.5 ulp each
+    assert worst <= 8.0, worst
+    # order: pairs whose exact scores are further apart than that bound must sort the same way
+    idx = rng.integers(0, len(scored), (20000, 2))
+    for a, b in idx:
+        ga, wa = scored[a]
+        gb, wb = scored[b]
+        gap = abs(float(wa - wb))
+        if gap > 16 * float(np.spacing(np.float64(max(abs(float(wa)), abs(float(wb)))))):
+            assert (ga < gb) == (wa < wb)
+    # lnfact itself (its large terms cancel, so the bound is relative to the largest term, not to the result)
+    for n in (1, 2, 3, 10, 59, 255, 1000):
+        want = exact_lnfact(n)
+        big = float(n) * float(np.log(max(n, 2)))
+        assert abs(O.lnfact(n) - float(want)) <= 8 * np.spacing(np.float64(max(big, 1.0))), n
+    # the OpenMS-style score goes through f32 ln_1p: checked bit for bit against libm elsewhere (tests/test_glibc_log.py); here only that the
+    # remaining f64 arithmetic agrees
+    for mb, my, sb, sy in cases[:500]:
+        got = O.hyperscore(1, mb, my, sb, sy)
+        want = exact_score(1, mb, my, sb, sy)
+        assert abs(got - float(want)) <= 8 * np.spacing(np.float64(abs(float(want)))), (mb, my, sb, sy)
